@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- gate-applies/sec on the reference's headline workloads, on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload qft30|larose28|hsweep30]
+                    [--impl ours|reference]
+
+Metric (BASELINE.json): gate-applies/sec at 30 qubits + achieved HBM GB/s.  A "step" is one
+full pass of the workload's gate stream over the resident 2^n complex128 state:
+  qft30     circuit.qc.qft on 30 qubits: 30 h + 435 cu1 = 465 gates          (configs[2], default)
+  larose28  larose_benchmark.py at 28 qubits, depth 28: 2324 gates            (configs[1])
+  hsweep30  one h on each of 30 qubits, gate-by-gate (no fusion): the "30-qubit single-qubit
+            gate application" roofline target of BASELINE.json
+The state (16 GiB at 30 qubits) is >> the 126 MB L2, so no explicit L2 flush is needed.
+
+Timing: CUDA events on the engine's own stream (qb_timer_*), synchronised on both sides,
+max over ranks.  `value` counts inputs resident in HBM; `e2e` goes through the host-buffer
+C-ABI path (pinned host state -> qb_copy_in -> gates -> qb_copy_out) every step.
+`roofline` is the dominant kernel's algorithmic bytes / its summed CUDA-event time, measured
+in the same timed region (qb_profile_*), against MEASURED_PEAKS.json's hbm_gbs.
+`cpu_baseline` times the reference's own xgates build (oracle/_ref/libxgates.so, 1 thread --
+the reference has no threading) on a bounded sample of the same gate stream.
+
+N > 1 (torchrun): each rank owns one GPU and runs its own copy of the workload -- independent
+replicas, weak scaling, no data-path collective (state sharding across GPUs is not built
+yet).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "qft30": dict(n=30, desc="30-qubit QFT (circuit.qc.qft): 30 h + 435 cu1", fusion=True),
+    "larose28": dict(n=28, desc="28-qubit larose_benchmark depth 28: 784 h + 784 v + 756 cx", fusion=True),
+    "hsweep30": dict(n=30, desc="h on each of 30 qubits, one kernel per gate (no fusion)", fusion=False),
+}
+
+
+def build_stream(name, n):
+  from qcc_b200 import workloads
+  if name.startswith("qft"):
+    return workloads.qft(n)
+  if name.startswith("larose"):
+    return workloads.larose(n, n)
+  if name.startswith("hsweep"):
+    return workloads.hsweep(n)
+  raise ValueError(name)
+
+
+def hbm_peak():
+  p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(p):
+    try:
+      return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # pylint: disable=broad-except
+      pass
+  return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+  """nvidia-smi clocks + throttle reasons while the timed region runs."""
+  Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+       "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+       "clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, index):
+    super().__init__(daemon=True)
+    self.index = index
+    self.samples = []
+    self.stop_flag = False
+
+  def run(self):
+    while not self.stop_flag:
+      try:
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                             timeout=5).stdout.strip()
+        if out:
+          self.samples.append([x.strip() for x in out.split(",")])
+      except Exception:  # pylint: disable=broad-except
+        pass
+      time.sleep(0.2)
+
+  def summary(self):
+    self.stop_flag = True
+    self.join(timeout=6)
+    if not self.samples:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    reasons = [nm for k, nm in enumerate(names) if any(s[3 + k] == "Active" for s in self.samples)]
+    return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+            "sm_max_mhz": float(self.samples[0][1]) if self.samples[0][1].replace(".", "").isdigit() else None,
+            "power_w_max": max((float(s[2]) for s in self.samples if s[2].replace(".", "").isdigit()), default=None),
+            "samples": len(self.samples), "reasons": reasons}
+
+
+def cpu_reference_sample(n, stream, budget_s=20.0, max_gates=8):
+  """Time the REFERENCE xgates build on the first gates of `stream` at full size n.
+  Returns (gates_per_sec, description)."""
+  from oracle import oracle
+  if not oracle.have_ref("libxgates.so"):
+    return None, "oracle/_ref/libxgates.so missing"
+  xg = oracle.RefXgates()
+  scale = 1.0
+  nn = n
+  while True:
+    try:
+      psi = np.zeros(1 << nn, dtype=np.complex128)
+      break
+    except MemoryError:
+      nn -= 2
+      scale /= 4.0
+  psi[1] = 1.0
+  psi[:] += 1.0 / (1 << (nn // 2 + 1))  # dense, so every pair does real arithmetic; also first-touches the pages
+  t_total, done = 0.0, 0
+  for kind, c, t, m in stream[:max_gates]:
+    if nn != n:  # remap qubit numbers into the smaller register
+      t = min(t, nn - 1)
+      c = min(c, nn - 1)
+      if kind == 2 and c == t:
+        c = (t + 1) % nn
+    t0 = time.perf_counter()
+    if kind == 1:
+      xg.apply1(psi, m, nn, t)
+    else:
+      xg.applyc(psi, m, nn, c, t)
+    t_total += time.perf_counter() - t0
+    done += 1
+    if t_total > budget_s:
+      break
+  gps = done / t_total * scale
+  desc = (f"first {done} gates of the stream with reference xgates (bit_width=128) on a dense "
+          f"{nn}-qubit numpy state, {t_total:.1f} s of CPU work, 1 thread")
+  if nn != n:
+    desc += f"; host RAM could not hold {n} qubits: scaled by 4^-{(n - nn) // 2} (time ~ 2^n)"
+  return gps, desc
+
+
+def run_reference_arm(args, wl, stream):
+  """--impl reference: the reference's own CPU implementation of the path, bounded sample per step."""
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  n = wl["n"]
+  total = args.steps + args.warmup
+  from oracle import oracle
+  if not oracle.have_ref("libxgates.so"):
+    print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libxgates.so not built"}))
+    return
+  xg = oracle.RefXgates()
+  psi = np.zeros(1 << n, dtype=np.complex128)
+  psi[:] = 1.0 / np.sqrt(float(1 << n))
+  # one probe gate decides how many gates a step can afford (whole run <= ~150 s)
+  t0 = time.perf_counter()
+  xg.apply1(psi, stream[0][3], n, stream[0][2])
+  probe = time.perf_counter() - t0
+  per_step = max(1, min(len(stream), int(150.0 / max(probe, 1e-3) / max(total, 1))))
+  pos = 0
+
+  def step():
+    nonlocal pos
+    for _ in range(per_step):
+      kind, c, t, m = stream[pos % len(stream)]
+      pos += 1
+      if kind == 1:
+        xg.apply1(psi, m, n, t)
+      else:
+        xg.applyc(psi, m, n, c, t)
+
+  for _ in range(args.warmup):
+    step()
+  t0 = time.perf_counter()
+  for _ in range(args.steps):
+    step()
+  dt = time.perf_counter() - t0
+  value = per_step * args.steps / dt
+  sample = (f"{per_step} consecutive gates of the {args.workload} stream per step on a dense {n}-qubit "
+            f"complex128 numpy state, reference xgates (src/lib/xgates.cc built -O3 -ffast-math), 1 thread")
+  print(json.dumps({
+      "impl": "reference", "metric": "gate-applies/sec", "value": value, "unit": "gates/s",
+      "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+      "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+      "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+      "config": {"workload": args.workload, "desc": wl["desc"], "qubits": n, "gates_per_step": per_step},
+      "cpu_baseline": {"value": value, "unit": "gates/s", "cores": 1, "kind": "reference", "sample": sample},
+      "e2e": {"value": value, "unit": "gates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+      "host_cores": os.cpu_count(),
+  }))
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=10)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--workload", default="qft30", choices=sorted(WORKLOADS))
+  ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  ap.add_argument("--qubits", type=int, default=0, help="override the workload's qubit count (debug)")
+  ap.add_argument("--tile-bits", type=int, default=12)
+  ap.add_argument("--e2e-steps", type=int, default=2)
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--no-e2e", action="store_true")
+  args = ap.parse_args()
+  args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+  wl = dict(WORKLOADS[args.workload])
+  if args.qubits:
+    wl["n"] = args.qubits
+  n = wl["n"]
+  stream = build_stream(args.workload, n)
+
+  if args.impl == "reference":
+    run_reference_arm(args, wl, stream)
+    return
+
+  rank = int(os.environ.get("RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  dist = None
+  if world > 1:
+    import torch
+    import torch.distributed as dist  # plumbing only: barrier + max-reduce of the timings
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+  from qcc_b200 import _cabi
+  packed = _cabi.pack_xg_gates(stream)
+  ngates = len(stream)
+  s = _cabi.DeviceState(n, 0, local_rank)
+  s.set_fusion(wl["fusion"])
+  if wl["fusion"]:
+    s.set_tile_bits(args.tile_bits)
+  s.fill_random(1234 + rank)
+
+  def barrier():
+    s.sync()
+    if dist is not None:
+      dist.barrier()
+
+  for _ in range(args.warmup):
+    s.xg_apply_gates(packed)
+    s.flush()
+  barrier()
+  sampler = ClockSampler(local_rank)
+  sampler.start()
+  c0 = s.counters()
+  s.profile_enable(True)
+  s.profile_read(reset=True)
+  t_wall0 = time.perf_counter()
+  s.timer_start()
+  for _ in range(args.steps):
+    s.xg_apply_gates(packed)
+    s.flush()
+  ms = s.timer_stop()
+  barrier()
+  wall = time.perf_counter() - t_wall0
+  prof = s.profile_read(reset=True)
+  s.profile_enable(False)
+  c1 = s.counters()
+  clocks = sampler.summary()
+  if dist is not None:
+    import torch
+    t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+  norm = s.norm2()
+
+  # ---- roofline of the dominant kernel class --------------------------------------------
+  peak, peak_src = hbm_peak()
+  dom = max(prof, key=lambda k: prof[k]["ms"])
+  d = prof[dom]
+  roof = None
+  if d["launches"]:
+    ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": {"apply1": "k_apply_u", "phase": "k_apply_phase", "fused": "k_fused_pass",
+                                      "aux": "aux"}[dom],
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+            "peak_source": peak_src, "launches": d["launches"],
+            "avg_launch_ms": d["ms"] / d["launches"],
+            "algorithmic_bytes_per_launch": d["bytes"] / d["launches"],
+            "share_of_step": d["ms"] / ms if ms else None,
+            "note": "achieved = algorithmic bytes (32 B x 2^n per full sweep; SURVEY 8d) / summed "
+                    "CUDA-event time of that kernel inside the timed region; traffic (ncu dram bytes) "
+                    "is recorded under profiles/"}
+  by_gate_alg = (c1["bytes_algorithmic"] - c0["bytes_algorithmic"]) / (ms * 1e-3) / 1e9
+
+  # ---- e2e: host buffers through the C ABI ------------------------------------------------
+  e2e = None
+  e2e_res = None
+  if rank == 0 or world > 1:
+    if not args.no_e2e:
+      try:
+        host = _cabi.PinnedBuffer(1 << n)
+        host.array[:] = 0
+        host.array[5] = 1.0
+        s.copy_in(host.array)            # warm-up of the path
+        s.xg_apply_gates(packed)
+        _cabi.check(_cabi.lib().qb_copy_out(s._h, 0, 1 << n, host.array.ctypes.data))
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+          _cabi.check(_cabi.lib().qb_copy_in(s._h, 0, 1 << n, host.array.ctypes.data))
+          s.xg_apply_gates(packed)
+          _cabi.check(_cabi.lib().qb_copy_out(s._h, 0, 1 << n, host.array.ctypes.data))
+        dt = time.perf_counter() - t0
+        e2e = {"value": ngates * args.e2e_steps * world / dt, "unit": "gates/s",
+               "h2d_bytes_per_step": (1 << n) * 16 + len(packed) * 80, "d2h_bytes_per_step": (1 << n) * 16,
+               "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
+               "path": "pinned host complex128 state -> qb_copy_in -> qb_xg_apply_gates -> qb_copy_out "
+                       "(what a host-buffer caller such as the libxgates/libq faces pays per circuit)"}
+        host.close()
+      except Exception as ex:  # pylint: disable=broad-except
+        e2e = {"value": None, "unit": "gates/s", "error": str(ex)[:200]}
+    # resident flavour: what a circuit.qc()/libq user pays -- init label in, readout out
+    t0 = time.perf_counter()
+    reps = max(2, args.e2e_steps)
+    for _ in range(reps):
+      s.set_basis(5)
+      s.xg_apply_gates(packed)
+      s.argmax()
+    dt = time.perf_counter() - t0
+    e2e_res = {"value": ngates * reps * world / dt, "unit": "gates/s", "h2d_bytes_per_step": len(packed) * 80 + 16,
+               "d2h_bytes_per_step": 16 * 1184, "ms_per_step": dt / reps * 1e3,
+               "path": "qb_set_basis -> qb_xg_apply_gates -> qb_argmax (state stays in HBM, as with the "
+                       "reference where it stays in one numpy array)"}
+
+  cpu = None
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    try:
+      gps, desc = cpu_reference_sample(n, stream)
+      if gps:
+        cpu = {"value": gps, "unit": "gates/s", "cores": 1, "kind": "reference", "sample": desc,
+               "host_cores": os.cpu_count()}
+      else:
+        cpu = {"value": None, "unit": "gates/s", "cores": 1, "kind": "reference", "sample": desc}
+    except Exception as ex:  # pylint: disable=broad-except
+      cpu = {"value": None, "unit": "gates/s", "cores": 1, "kind": "reference", "sample": f"failed: {ex}"[:200]}
+
+  if rank == 0:
+    value = ngates * args.steps * world / (ms * 1e-3)
+    line = {
+        "metric": "gate-applies/sec", "value": value, "unit": "gates/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "desc": wl["desc"], "qubits": n, "gates_per_step": ngates,
+                   "state_bytes": (1 << n) * 16, "l2": "state (>= 4 GiB) >> 126 MB L2; no flush needed",
+                   "fusion": wl["fusion"], "tile_bits": args.tile_bits if wl["fusion"] else None,
+                   "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (no collective)"},
+        "passes_per_step": (c1["passes"] - c0["passes"]) / args.steps,
+        "gpu_launches": c1["kernel_launches"] - c0["kernel_launches"],
+        "achieved_gbs_algorithmic_by_gate": by_gate_alg,
+        "achieved_gbs_swept": (c1["bytes_swept"] - c0["bytes_swept"]) / (ms * 1e-3) / 1e9,
+        "roofline": roof, "kernel_ms": {k: v["ms"] for k, v in prof.items() if v["launches"]},
+        "cpu_baseline": cpu, "e2e": e2e, "e2e_resident": e2e_res, "clocks": clocks,
+        "wall_s_timed_region": wall, "norm2_after": norm,
+    }
+    print(json.dumps(line))
+  s.close()
+  if dist is not None:
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+  main()

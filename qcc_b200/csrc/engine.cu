@@ -1,0 +1,811 @@
+// engine.cu -- host side of the C ABI (include/qcc_b200.h): state lifetime, the gate
+// queue, dispatch to single-gate kernels or fused passes, readouts, the host-buffer
+// entry points the `libxgates` shim binds, and the measurement helpers.
+//
+// Reference behaviour mirrored here (paths relative to the reference tree):
+//   * gate semantics: src/lib/xgates.cc:23-67 (dense butterfly, python numbering,
+//     negative-control predicate) and src/libq/gates.cc:9-146 (named gates);
+//   * queue / flush protocol: src/libq/gates_jit.cc:53-132 -- gates may be deferred
+//     and are guaranteed applied at flush and before anything observes the state;
+//   * readouts: src/lib/state.py:30-78 (ampl / prob / maxprob), src/libq/qureg.cc:64-86.
+// There is no CPU execution path in this file: without a CUDA device every state
+// operation fails with QB_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "../../include/qcc_b200.h"
+#include "kernels.h"
+#include "planner.h"
+#include "qb_types.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CU(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e__ = (call);                                                          \
+    if (e__ != cudaSuccess)                                                            \
+      return fail(QB_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                  __FILE__, __LINE__);                                                 \
+  } while (0)
+
+#define QB(call)            \
+  do {                      \
+    int rc__ = (call);      \
+    if (rc__ != QB_OK) return rc__; \
+  } while (0)
+
+struct ProfRec {
+  int kclass;
+  double bytes;
+  cudaEvent_t e0, e1;
+};
+
+}  // namespace
+
+struct qb_state {
+  int n = 0;            // qubits == index bits
+  uint64_t len = 0;     // 2^n
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  double2 *psi = nullptr;
+  bool fusion = true;
+  int tile_bits = 12;
+  std::vector<QbGate> queue;
+  // scratch
+  double *d_scalar = nullptr;            // 1 double
+  unsigned long long *d_counter = nullptr;
+  double *d_blk_prob = nullptr;
+  uint64_t *d_blk_idx = nullptr;
+  // fused-pass staging (device copies of the current plan)
+  void *d_plan = nullptr;
+  size_t d_plan_cap = 0;
+  void *h_plan = nullptr;  // pinned
+  size_t h_plan_cap = 0;
+  cudaEvent_t plan_free = nullptr;  // signalled when the staged plan has been consumed
+  // measurement
+  qb_counters cnt{};
+  bool profiling = false;
+  std::vector<ProfRec> prof_pending;
+  std::vector<cudaEvent_t> event_pool;
+  qb_profile prof{};
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+};
+
+namespace {
+
+const double kEps = 0.0;  // classification is exact: only literal zeros / ones specialise
+
+// Decide how a 2x2 acts (qb_types.h QbKind).  Exact comparisons on purpose: a matrix
+// that is merely *close* to diagonal must still go through the general butterfly so
+// that results track the reference's arithmetic.
+int classify(const double m[8]) {
+  auto z = [&](int k) { return std::fabs(m[2 * k]) <= kEps && std::fabs(m[2 * k + 1]) <= kEps; };
+  auto one = [&](int k) { return m[2 * k] == 1.0 && m[2 * k + 1] == 0.0; };
+  if (z(1) && z(2)) {
+    if (one(0) && one(3)) return QB_K_NOP;
+    if (one(0)) return QB_K_PHASE;
+    return QB_K_DIAG;
+  }
+  if (z(0) && z(3)) return QB_K_PERM;
+  return QB_K_U;
+}
+
+double gate_bytes(const qb_state *s, const QbGate &g) {
+  // general 32N, controlled-general / 1-bit diagonal 16N, ...
+  int nb = __builtin_popcountll(g.ctl_mask);
+  double n = double(s->len) * 32.0;
+  if (g.kind == QB_K_NOP) return 0.0;
+  if (g.kind == QB_K_PHASE) nb += 1;
+  return n / double(uint64_t(1) << nb);
+}
+
+cudaEvent_t get_event(qb_state *s) {
+  if (!s->event_pool.empty()) {
+    cudaEvent_t e = s->event_pool.back();
+    s->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+struct ProfScope {
+  qb_state *s;
+  ProfRec rec;
+  bool on;
+  ProfScope(qb_state *st, int kclass, double bytes) : s(st), on(st->profiling) {
+    if (on) {
+      rec.kclass = kclass;
+      rec.bytes = bytes;
+      rec.e0 = get_event(s);
+      rec.e1 = get_event(s);
+      cudaEventRecord(rec.e0, s->stream);
+    }
+  }
+  ~ProfScope() {
+    if (on) {
+      cudaEventRecord(rec.e1, s->stream);
+      s->prof_pending.push_back(rec);
+    }
+  }
+};
+
+int resolve_profile(qb_state *s) {
+  for (auto &r : s->prof_pending) {
+    float ms = 0.f;
+    CU(cudaEventSynchronize(r.e1));
+    CU(cudaEventElapsedTime(&ms, r.e0, r.e1));
+    s->prof.launches[r.kclass] += 1;
+    s->prof.ms[r.kclass] += ms;
+    s->prof.bytes[r.kclass] += r.bytes;
+    s->event_pool.push_back(r.e0);
+    s->event_pool.push_back(r.e1);
+  }
+  s->prof_pending.clear();
+  return QB_OK;
+}
+
+int run_single(qb_state *s, const QbGate &g) {
+  if (g.kind == QB_K_NOP) {
+    s->cnt.gates_applied += 1;
+    return QB_OK;
+  }
+  double bytes = gate_bytes(s, g);
+  {
+    ProfScope ps(s, g.kind == QB_K_PHASE ? QB_KCLASS_PHASE : QB_KCLASS_APPLY1, bytes);
+    CU(qb::launch_gate(s->psi, s->n, g, true, s->stream));
+  }
+  s->cnt.gates_applied += 1;
+  s->cnt.kernel_launches += 1;
+  s->cnt.passes += 1;
+  s->cnt.bytes_algorithmic += uint64_t(bytes);
+  s->cnt.bytes_swept += uint64_t(bytes);
+  return QB_OK;
+}
+
+int ensure_plan_buffers(qb_state *s, size_t bytes) {
+  if (bytes > s->h_plan_cap) {
+    if (s->h_plan) cudaFreeHost(s->h_plan);
+    if (s->d_plan) cudaFree(s->d_plan);
+    size_t cap = std::max<size_t>(bytes * 2, 1 << 20);
+    CU(cudaMallocHost(&s->h_plan, cap));
+    CU(cudaMalloc(&s->d_plan, cap));
+    s->h_plan_cap = s->d_plan_cap = cap;
+  }
+  return QB_OK;
+}
+
+// Fused execution: plan the queue into tile-resident passes and launch one kernel per pass.
+int run_fused(qb_state *s, const std::vector<QbGate> &gates) {
+  qb::Plan plan;
+  qb::plan_gates(s->n, gates.data(), int64_t(gates.size()), s->tile_bits, &plan);
+  // The staging buffers are reused flush after flush: wait until the previous plan's
+  // kernels have consumed them.
+  CU(cudaEventSynchronize(s->plan_free));
+  size_t bytes = plan.blob_bytes();
+  QB(ensure_plan_buffers(s, bytes));
+  plan.serialize(static_cast<char *>(s->h_plan));
+  CU(cudaMemcpyAsync(s->d_plan, s->h_plan, bytes, cudaMemcpyHostToDevice, s->stream));
+  const char *dbase = static_cast<const char *>(s->d_plan);
+  for (size_t k = 0; k < plan.passes.size(); ++k) {
+    const qb::PlannedPass &pp = plan.passes[k];
+    if (pp.single_gate >= 0) {
+      // planner decided this gate is better off as a plain sweep (e.g. a lone PHASE)
+      QB(run_single(s, gates[size_t(pp.single_gate)]));
+      s->cnt.gates_applied += uint64_t(pp.ngates - 1);  // no-op gates retired alongside
+      continue;
+    }
+    qb::DevicePass dp;
+    dp.desc = pp.desc;
+    dp.ops = reinterpret_cast<const QbOp *>(dbase + pp.ops_off);
+    dp.rounds = reinterpret_cast<const QbRound *>(dbase + pp.rounds_off);
+    dp.tables = pp.desc.ntable ? reinterpret_cast<const double2 *>(dbase + pp.tables_off) : nullptr;
+    dp.outbits = pp.noutbits ? reinterpret_cast<const int32_t *>(dbase + pp.outbits_off) : nullptr;
+    double sweep = double(s->len) * 32.0;
+    {
+      ProfScope ps(s, QB_KCLASS_FUSED, sweep);
+      CU(qb::launch_fused_pass(s->psi, s->n, dp, s->stream));
+    }
+    s->cnt.kernel_launches += 1;
+    s->cnt.passes += 1;
+    s->cnt.bytes_swept += uint64_t(sweep);
+    s->cnt.gates_applied += uint64_t(pp.ngates);
+    s->cnt.bytes_algorithmic += uint64_t(pp.bytes_algorithmic_per_amp * double(s->len));
+  }
+  CU(cudaEventRecord(s->plan_free, s->stream));
+  return QB_OK;
+}
+
+int flush(qb_state *s) {
+  if (s->queue.empty()) return QB_OK;
+  CU(cudaSetDevice(s->device));
+  std::vector<QbGate> q;
+  q.swap(s->queue);
+  if (s->fusion && s->n > QB_TILE_LOW) return run_fused(s, q);
+  for (const QbGate &g : q) QB(run_single(s, g));
+  return QB_OK;
+}
+
+int enqueue(qb_state *s, uint64_t ctl_mask, int target, const double m[8]) {
+  if (!s) return fail(QB_ERR_ARG, "null state");
+  if (!m) return fail(QB_ERR_ARG, "null gate matrix");
+  if (target < 0 || target >= s->n) return fail(QB_ERR_ARG, "target bit %d out of range [0,%d)", target, s->n);
+  if (s->n < 64 && (ctl_mask >> s->n)) return fail(QB_ERR_ARG, "control mask has bits >= %d", s->n);
+  if (ctl_mask >> target & 1) return fail(QB_ERR_ARG, "control and target coincide (bit %d)", target);
+  if (__builtin_popcountll(ctl_mask) > 3) return fail(QB_ERR_UNSUPPORTED, "more than 3 controls");
+  QbGate g;
+  g.ctl_mask = ctl_mask;
+  g.target = target;
+  g.kind = classify(m);
+  memcpy(g.m, m, sizeof g.m);
+  if (!s->fusion) {
+    CU(cudaSetDevice(s->device));
+    return run_single(s, g);
+  }
+  s->queue.push_back(g);
+  if (s->queue.size() >= 16384) return flush(s);
+  return QB_OK;
+}
+
+// xgates.cc:45-67 predicate with python numbering -> (ctl_mask | no-op) in index bits.
+// Returns 1 if the gate acts on nothing, 0 if *mask is valid, <0 on error.
+int xg_control_mask(int nbits, int ctl, int tgt, uint64_t *mask) {
+  int t = nbits - tgt - 1;
+  long long c = (long long)nbits - ctl - 1;
+  if (c < 0) return fail(QB_ERR_ARG, "control index %d >= nbits %d (negative shift in xgates)", ctl, nbits);
+  if (c < nbits) {
+    if (c == t) return 1;  // pair base has the target bit clear: predicate never true
+    *mask = uint64_t(1) << c;
+    return 0;
+  }
+  // bit c of (g << nbits) + i == bit (c - nbits) of the pair-group base g, whose low
+  // t+1 bits are zero and which is < 2^nbits.
+  long long cc = c - nbits;
+  if (cc <= t || cc >= nbits) return 1;
+  *mask = uint64_t(1) << cc;
+  return 0;
+}
+
+}  // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+extern "C" {
+
+int qb_abi_version(void) { return QB_ABI_VERSION; }
+
+const char *qb_last_error(void) { return g_err.c_str(); }
+
+int qb_device_count(int *count) {
+  if (!count) return fail(QB_ERR_ARG, "null pointer");
+  *count = 0;
+  CU(cudaGetDeviceCount(count));
+  return QB_OK;
+}
+
+int qb_device_info(int device, char *name, size_t name_len, int *sm_count, size_t *total_mem,
+                   int *cc_major, int *cc_minor) {
+  cudaDeviceProp p;
+  CU(cudaGetDeviceProperties(&p, device));
+  if (name && name_len) snprintf(name, name_len, "%s", p.name);
+  if (sm_count) *sm_count = p.multiProcessorCount;
+  if (total_mem) *total_mem = p.totalGlobalMem;
+  if (cc_major) *cc_major = p.major;
+  if (cc_minor) *cc_minor = p.minor;
+  return QB_OK;
+}
+
+int qb_state_create(int nqubits, uint64_t init_label, int device, qb_state **out) {
+  if (!out) return fail(QB_ERR_ARG, "null out pointer");
+  *out = nullptr;
+  if (nqubits < 1 || nqubits > 40) return fail(QB_ERR_ARG, "nqubits %d out of range [1,40]", nqubits);
+  if (nqubits < 64 && (init_label >> nqubits)) return fail(QB_ERR_ARG, "init label does not fit %d qubits", nqubits);
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (ndev == 0) return fail(QB_ERR_CUDA, "no CUDA device visible (this engine has no CPU path)");
+  if (device < 0) device = 0;
+  if (device >= ndev) return fail(QB_ERR_ARG, "device %d out of range (%d visible)", device, ndev);
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(QB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                prop.major, prop.minor);
+  qb_state *s = new qb_state;
+  s->n = nqubits;
+  s->len = uint64_t(1) << nqubits;
+  s->device = device;
+  size_t freeb = 0, totalb = 0;
+  cudaMemGetInfo(&freeb, &totalb);
+  size_t need = size_t(s->len) * sizeof(double2);
+  if (need + (size_t(64) << 20) > freeb) {
+    delete s;
+    return fail(QB_ERR_NOMEM, "state needs %zu MiB, device has %zu MiB free", need >> 20, freeb >> 20);
+  }
+  cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc(&s->psi, need);
+  if (e == cudaSuccess) e = cudaMalloc(&s->d_scalar, sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&s->d_counter, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&s->d_blk_prob, sizeof(double) * qb::argmax_blocks());
+  if (e == cudaSuccess) e = cudaMalloc(&s->d_blk_idx, sizeof(uint64_t) * qb::argmax_blocks());
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->plan_free, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventRecord(s->plan_free, s->stream);
+  if (e == cudaSuccess) e = cudaEventCreate(&s->t0);
+  if (e == cudaSuccess) e = cudaEventCreate(&s->t1);
+  if (e == cudaSuccess) e = qb::fused_configure(device);
+  if (e != cudaSuccess) {
+    int rc = fail(e == cudaErrorMemoryAllocation ? QB_ERR_NOMEM : QB_ERR_CUDA, "state allocation failed: %s",
+                  cudaGetErrorString(e));
+    qb_state_destroy(s);
+    return rc;
+  }
+  int rc = qb_set_basis(s, init_label);
+  if (rc != QB_OK) {
+    qb_state_destroy(s);
+    return rc;
+  }
+  *out = s;
+  return QB_OK;
+}
+
+int qb_state_destroy(qb_state *s) {
+  if (!s) return QB_OK;
+  cudaSetDevice(s->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  for (auto &r : s->prof_pending) {
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  for (auto e : s->event_pool) cudaEventDestroy(e);
+  if (s->psi) cudaFree(s->psi);
+  if (s->d_scalar) cudaFree(s->d_scalar);
+  if (s->d_counter) cudaFree(s->d_counter);
+  if (s->d_blk_prob) cudaFree(s->d_blk_prob);
+  if (s->d_blk_idx) cudaFree(s->d_blk_idx);
+  if (s->d_plan) cudaFree(s->d_plan);
+  if (s->h_plan) cudaFreeHost(s->h_plan);
+  if (s->plan_free) cudaEventDestroy(s->plan_free);
+  if (s->t0) cudaEventDestroy(s->t0);
+  if (s->t1) cudaEventDestroy(s->t1);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+  return QB_OK;
+}
+
+int qb_state_nqubits(qb_state *s, int *nqubits) {
+  if (!s || !nqubits) return fail(QB_ERR_ARG, "null pointer");
+  *nqubits = s->n;
+  return QB_OK;
+}
+
+int qb_set_basis(qb_state *s, uint64_t label) {
+  if (!s) return fail(QB_ERR_ARG, "null state");
+  if (label >= s->len) return fail(QB_ERR_ARG, "label out of range");
+  CU(cudaSetDevice(s->device));
+  s->queue.clear();
+  CU(cudaMemsetAsync(s->psi, 0, size_t(s->len) * sizeof(double2), s->stream));
+  const double2 one = make_double2(1.0, 0.0);
+  CU(cudaMemcpyAsync(s->psi + label, &one, sizeof one, cudaMemcpyHostToDevice, s->stream));
+  CU(cudaStreamSynchronize(s->stream));  // `one` is a stack temporary
+  s->cnt.kernel_launches += 1;
+  return QB_OK;
+}
+
+int qb_fill_random(qb_state *s, uint64_t seed) {
+  if (!s) return fail(QB_ERR_ARG, "null state");
+  CU(cudaSetDevice(s->device));
+  s->queue.clear();
+  CU(qb::launch_fill_random(s->psi, s->len, seed, s->stream));
+  double n2 = 0.0;
+  CU(qb::launch_norm2(s->psi, s->len, s->d_scalar, s->stream));
+  CU(cudaMemcpyAsync(&n2, s->d_scalar, sizeof n2, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  CU(qb::launch_scale(s->psi, s->len, 1.0 / std::sqrt(n2), s->stream));
+  s->cnt.kernel_launches += 3;
+  return QB_OK;
+}
+
+int qb_copy_in(qb_state *s, uint64_t first, uint64_t count, const double *host) {
+  if (!s || !host) return fail(QB_ERR_ARG, "null pointer");
+  if (first > s->len || count > s->len - first) return fail(QB_ERR_ARG, "range out of bounds");
+  QB(flush(s));
+  CU(cudaMemcpyAsync(s->psi + first, host, size_t(count) * sizeof(double2), cudaMemcpyHostToDevice, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return QB_OK;
+}
+
+int qb_copy_out(qb_state *s, uint64_t first, uint64_t count, double *host) {
+  if (!s || !host) return fail(QB_ERR_ARG, "null pointer");
+  if (first > s->len || count > s->len - first) return fail(QB_ERR_ARG, "range out of bounds");
+  QB(flush(s));
+  CU(cudaMemcpyAsync(host, s->psi + first, size_t(count) * sizeof(double2), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return QB_OK;
+}
+
+// ---- gates, index-bit numbering ---------------------------------------------------
+int qb_apply1(qb_state *s, int target, const double m[8]) { return enqueue(s, 0, target, m); }
+
+int qb_applyc(qb_state *s, int control, int target, const double m[8]) {
+  if (!s) return fail(QB_ERR_ARG, "null state");
+  if (control < 0 || control >= s->n) return fail(QB_ERR_ARG, "control bit %d out of range", control);
+  return enqueue(s, uint64_t(1) << control, target, m);
+}
+
+int qb_applycc(qb_state *s, int c0, int c1, int target, const double m[8]) {
+  if (!s) return fail(QB_ERR_ARG, "null state");
+  if (c0 < 0 || c0 >= s->n || c1 < 0 || c1 >= s->n) return fail(QB_ERR_ARG, "control bit out of range");
+  if (c0 == c1) return fail(QB_ERR_ARG, "identical controls");
+  return enqueue(s, (uint64_t(1) << c0) | (uint64_t(1) << c1), target, m);
+}
+
+int qb_apply_gates(qb_state *s, const qb_gate *gates, int64_t ngates) {
+  if (!s || (!gates && ngates)) return fail(QB_ERR_ARG, "null pointer");
+  for (int64_t k = 0; k < ngates; ++k) QB(enqueue(s, gates[k].ctl_mask, gates[k].target, gates[k].m));
+  return QB_OK;
+}
+
+// ---- gates, python numbering --------------------------------------------------------
+int qb_xg_apply1(qb_state *s, int tgt, const double m[8]) {
+  if (!s) return fail(QB_ERR_ARG, "null state");
+  return enqueue(s, 0, s->n - tgt - 1, m);  // out-of-range tgt is rejected by enqueue
+}
+
+int qb_xg_applyc(qb_state *s, int ctl, int tgt, const double m[8]) {
+  if (!s) return fail(QB_ERR_ARG, "null state");
+  int t = s->n - tgt - 1;
+  if (t < 0 || t >= s->n) return fail(QB_ERR_ARG, "target qubit %d out of range", tgt);
+  uint64_t mask = 0;
+  int r = xg_control_mask(s->n, ctl, tgt, &mask);
+  if (r < 0) return r;
+  if (r == 1) {  // acts on nothing; still counts as an applied gate
+    s->cnt.gates_applied += 1;
+    return QB_OK;
+  }
+  return enqueue(s, mask, t, m);
+}
+
+int qb_xg_apply_gates(qb_state *s, const qb_xg_gate *gates, int64_t ngates) {
+  if (!s || (!gates && ngates)) return fail(QB_ERR_ARG, "null pointer");
+  for (int64_t k = 0; k < ngates; ++k) {
+    const qb_xg_gate &g = gates[k];
+    if (g.kind == 1) QB(qb_xg_apply1(s, g.tgt, g.m));
+    else if (g.kind == 2) QB(qb_xg_applyc(s, g.ctl, g.tgt, g.m));
+    else return fail(QB_ERR_ARG, "gate %lld: kind %d", (long long)k, g.kind);
+  }
+  return QB_OK;
+}
+
+// ---- queue control --------------------------------------------------------------------
+int qb_set_fusion(qb_state *s, int fusion) {
+  if (!s) return fail(QB_ERR_ARG, "null state");
+  QB(flush(s));
+  s->fusion = fusion != 0;
+  return QB_OK;
+}
+
+int qb_flush(qb_state *s) {
+  if (!s) return fail(QB_ERR_ARG, "null state");
+  return flush(s);
+}
+
+int qb_sync(qb_state *s) {
+  if (!s) return fail(QB_ERR_ARG, "null state");
+  QB(flush(s));
+  CU(cudaStreamSynchronize(s->stream));
+  return QB_OK;
+}
+
+// ---- readouts ---------------------------------------------------------------------------
+int qb_get_amplitude(qb_state *s, uint64_t index, double out[2]) {
+  if (!s || !out) return fail(QB_ERR_ARG, "null pointer");
+  if (index >= s->len) return fail(QB_ERR_ARG, "index out of range");
+  return qb_copy_out(s, index, 1, out);
+}
+
+int qb_norm2(qb_state *s, double *out) {
+  if (!s || !out) return fail(QB_ERR_ARG, "null pointer");
+  QB(flush(s));
+  {
+    ProfScope ps(s, QB_KCLASS_AUX, double(s->len) * 16.0);
+    CU(qb::launch_norm2(s->psi, s->len, s->d_scalar, s->stream));
+  }
+  s->cnt.kernel_launches += 1;
+  CU(cudaMemcpyAsync(out, s->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return QB_OK;
+}
+
+int qb_prob_bit(qb_state *s, int bit, double *p_one) {
+  if (!s || !p_one) return fail(QB_ERR_ARG, "null pointer");
+  if (bit < 0 || bit >= s->n) return fail(QB_ERR_ARG, "bit out of range");
+  QB(flush(s));
+  {
+    ProfScope ps(s, QB_KCLASS_AUX, double(s->len) * 8.0);
+    CU(qb::launch_prob_mask(s->psi, s->len, uint64_t(1) << bit, s->d_scalar, s->stream));
+  }
+  s->cnt.kernel_launches += 1;
+  CU(cudaMemcpyAsync(p_one, s->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return QB_OK;
+}
+
+int qb_argmax(qb_state *s, uint64_t *index, double *prob) {
+  if (!s || !index || !prob) return fail(QB_ERR_ARG, "null pointer");
+  QB(flush(s));
+  int nb = qb::argmax_blocks();
+  {
+    ProfScope ps(s, QB_KCLASS_AUX, double(s->len) * 16.0);
+    CU(qb::launch_argmax(s->psi, s->len, s->d_blk_prob, s->d_blk_idx, s->stream));
+  }
+  s->cnt.kernel_launches += 1;
+  std::vector<double> hp(nb);
+  std::vector<uint64_t> hi(nb);
+  CU(cudaMemcpyAsync(hp.data(), s->d_blk_prob, sizeof(double) * nb, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaMemcpyAsync(hi.data(), s->d_blk_idx, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  double best = -1.0;
+  uint64_t bi = 0;
+  for (int b = 0; b < nb; ++b)
+    if (hp[b] > best || (hp[b] == best && hi[b] < bi)) {
+      best = hp[b];
+      bi = hi[b];
+    }
+  *index = bi;
+  *prob = best;
+  return QB_OK;
+}
+
+int qb_list_above(qb_state *s, double threshold, uint64_t cap, uint64_t *labels, double *amps,
+                  uint64_t *count) {
+  if (!s || !count) return fail(QB_ERR_ARG, "null pointer");
+  if (cap && (!labels || !amps)) return fail(QB_ERR_ARG, "null output buffers with cap > 0");
+  QB(flush(s));
+  uint64_t *d_labels = nullptr;
+  double2 *d_amps = nullptr;
+  if (cap) {
+    CU(cudaMalloc(&d_labels, cap * sizeof(uint64_t)));
+    cudaError_t e = cudaMalloc(&d_amps, cap * sizeof(double2));
+    if (e != cudaSuccess) {
+      cudaFree(d_labels);
+      return fail(QB_ERR_NOMEM, "list buffers: %s", cudaGetErrorString(e));
+    }
+  }
+  cudaError_t e;
+  {
+    ProfScope ps(s, QB_KCLASS_AUX, double(s->len) * 16.0);
+    e = qb::launch_list_above(s->psi, s->len, threshold, cap, s->d_counter, d_labels, d_amps, s->stream);
+  }
+  s->cnt.kernel_launches += 1;
+  unsigned long long found = 0;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&found, s->d_counter, sizeof found, cudaMemcpyDeviceToHost, s->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+  uint64_t got = std::min<uint64_t>(found, cap);
+  std::vector<uint64_t> hl(got);
+  std::vector<double2> ha(got);
+  if (e == cudaSuccess && got) {
+    e = cudaMemcpy(hl.data(), d_labels, got * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(ha.data(), d_amps, got * sizeof(double2), cudaMemcpyDeviceToHost);
+  }
+  if (d_labels) cudaFree(d_labels);
+  if (d_amps) cudaFree(d_amps);
+  if (e != cudaSuccess) return fail(QB_ERR_CUDA, "list_above: %s", cudaGetErrorString(e));
+  // the kernel's slots are in arrival order; present them by ascending label
+  std::vector<uint64_t> order(got);
+  for (uint64_t i = 0; i < got; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return hl[a] < hl[b]; });
+  for (uint64_t i = 0; i < got; ++i) {
+    labels[i] = hl[order[i]];
+    amps[2 * i] = ha[order[i]].x;
+    amps[2 * i + 1] = ha[order[i]].y;
+  }
+  *count = found;
+  return QB_OK;
+}
+
+// ---- host-buffer entry points (the libxgates binding) -----------------------------------
+namespace {
+struct HostScratch {
+  int device = -1;
+  void *d = nullptr;
+  size_t cap = 0;
+  cudaStream_t st = nullptr;
+};
+thread_local HostScratch g_hs;
+
+int host_scratch(int device, size_t bytes, HostScratch **out) {
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (ndev == 0) return fail(QB_ERR_CUDA, "no CUDA device visible (this engine has no CPU path)");
+  if (device < 0) device = 0;
+  if (device >= ndev) return fail(QB_ERR_ARG, "device %d out of range", device);
+  CU(cudaSetDevice(device));
+  HostScratch &h = g_hs;
+  if (h.device != device) {
+    if (h.d) cudaFree(h.d);
+    h.d = nullptr;
+    h.cap = 0;
+    if (h.st) cudaStreamDestroy(h.st);
+    h.st = nullptr;
+    h.device = device;
+  }
+  if (!h.st) CU(cudaStreamCreateWithFlags(&h.st, cudaStreamNonBlocking));
+  if (bytes > h.cap) {
+    if (h.d) cudaFree(h.d);
+    h.d = nullptr;
+    h.cap = 0;
+    cudaError_t e = cudaMalloc(&h.d, bytes);
+    if (e != cudaSuccess) return fail(QB_ERR_NOMEM, "host-path scratch of %zu MiB: %s", bytes >> 20, cudaGetErrorString(e));
+    h.cap = bytes;
+  }
+  *out = &h;
+  return QB_OK;
+}
+
+int host_gate(void *psi, const void *gate, int nbits, uint64_t mask, int t, int bit_width, int device) {
+  bool dbl = bit_width == 128;
+  size_t esz = dbl ? sizeof(double2) : sizeof(float2);
+  size_t bytes = (size_t(1) << nbits) * esz;
+  HostScratch *h = nullptr;
+  QB(host_scratch(device, bytes, &h));
+  QbGate g;
+  g.ctl_mask = mask;
+  g.target = t;
+  if (dbl) memcpy(g.m, gate, sizeof g.m);
+  else
+    for (int k = 0; k < 8; ++k) g.m[k] = static_cast<const float *>(gate)[k];
+  g.kind = classify(g.m);
+  if (g.kind == QB_K_NOP) return QB_OK;
+  CU(cudaMemcpyAsync(h->d, psi, bytes, cudaMemcpyHostToDevice, h->st));
+  CU(qb::launch_gate(h->d, nbits, g, dbl, h->st));
+  CU(cudaMemcpyAsync(psi, h->d, bytes, cudaMemcpyDeviceToHost, h->st));
+  CU(cudaStreamSynchronize(h->st));
+  return QB_OK;
+}
+}  // namespace
+
+int qb_host_apply1(void *psi, const void *gate, int nbits, int tgt, int bit_width, int device) {
+  if (!psi || !gate) return fail(QB_ERR_ARG, "null pointer");
+  if (nbits < 1 || nbits > 40) return fail(QB_ERR_ARG, "nbits out of range");
+  int t = nbits - tgt - 1;
+  if (t < 0 || t >= nbits) return fail(QB_ERR_ARG, "Negative qubit index in apply1(): tgt %d, nbits %d", tgt, nbits);
+  return host_gate(psi, gate, nbits, 0, t, bit_width, device);
+}
+
+int qb_host_applyc(void *psi, const void *gate, int nbits, int ctl, int tgt, int bit_width,
+                   int device) {
+  if (!psi || !gate) return fail(QB_ERR_ARG, "null pointer");
+  if (nbits < 1 || nbits > 40) return fail(QB_ERR_ARG, "nbits out of range");
+  int t = nbits - tgt - 1;
+  if (t < 0 || t >= nbits) return fail(QB_ERR_ARG, "Negative qubit index in applyc(): tgt %d, nbits %d", tgt, nbits);
+  uint64_t mask = 0;
+  int r = xg_control_mask(nbits, ctl, tgt, &mask);
+  if (r < 0) return r;
+  if (r == 1) return QB_OK;
+  return host_gate(psi, gate, nbits, mask, t, bit_width, device);
+}
+
+int qb_host_run(void *psi, int nbits, const qb_xg_gate *gates, int64_t ngates, int device) {
+  if (!psi || (!gates && ngates)) return fail(QB_ERR_ARG, "null pointer");
+  qb_state *s = nullptr;
+  QB(qb_state_create(nbits, 0, device, &s));
+  int rc = qb_copy_in(s, 0, s->len, static_cast<const double *>(psi));
+  if (rc == QB_OK) rc = qb_xg_apply_gates(s, gates, ngates);
+  if (rc == QB_OK) rc = qb_copy_out(s, 0, s->len, static_cast<double *>(psi));
+  qb_state_destroy(s);
+  return rc;
+}
+
+int qb_host_alloc(size_t bytes, void **out) {
+  if (!out) return fail(QB_ERR_ARG, "null pointer");
+  *out = nullptr;
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (ndev == 0) return fail(QB_ERR_CUDA, "no CUDA device visible");
+  cudaError_t e = cudaHostAlloc(out, bytes, cudaHostAllocPortable);
+  if (e != cudaSuccess) return fail(QB_ERR_NOMEM, "cudaHostAlloc(%zu MiB): %s", bytes >> 20, cudaGetErrorString(e));
+  return QB_OK;
+}
+
+int qb_host_free(void *p) {
+  if (p) CU(cudaFreeHost(p));
+  return QB_OK;
+}
+
+// ---- measurement helpers ------------------------------------------------------------------
+int qb_get_counters(qb_state *s, qb_counters *out) {
+  if (!s || !out) return fail(QB_ERR_ARG, "null pointer");
+  *out = s->cnt;
+  return QB_OK;
+}
+
+int qb_profile_enable(qb_state *s, int enable) {
+  if (!s) return fail(QB_ERR_ARG, "null state");
+  QB(qb_sync(s));
+  QB(resolve_profile(s));
+  s->profiling = enable != 0;
+  return QB_OK;
+}
+
+int qb_profile_read(qb_state *s, qb_profile *out, int reset) {
+  if (!s || !out) return fail(QB_ERR_ARG, "null pointer");
+  QB(qb_sync(s));
+  QB(resolve_profile(s));
+  *out = s->prof;
+  if (reset) s->prof = qb_profile{};
+  return QB_OK;
+}
+
+int qb_timer_start(qb_state *s) {
+  if (!s) return fail(QB_ERR_ARG, "null state");
+  QB(qb_sync(s));
+  CU(cudaEventRecord(s->t0, s->stream));
+  return QB_OK;
+}
+
+int qb_timer_stop(qb_state *s, double *ms) {
+  if (!s || !ms) return fail(QB_ERR_ARG, "null pointer");
+  QB(flush(s));
+  CU(cudaEventRecord(s->t1, s->stream));
+  CU(cudaEventSynchronize(s->t1));
+  float f = 0.f;
+  CU(cudaEventElapsedTime(&f, s->t0, s->t1));
+  *ms = f;
+  return QB_OK;
+}
+
+int qb_set_tile_bits(qb_state *s, int tile_bits) {
+  if (!s) return fail(QB_ERR_ARG, "null state");
+  if (tile_bits < 4 || tile_bits > QB_MAX_TILE_BITS) return fail(QB_ERR_ARG, "tile_bits out of range [4,%d]", QB_MAX_TILE_BITS);
+  QB(flush(s));
+  s->tile_bits = tile_bits;
+  return QB_OK;
+}
+
+int qb_plan_json(int nqubits, const qb_gate *gates, int64_t ngates, int tile_bits, char *buf,
+                 size_t cap, size_t *needed) {
+  if ((!gates && ngates) || !needed) return fail(QB_ERR_ARG, "null pointer");
+  if (nqubits < 4 || nqubits > 40) return fail(QB_ERR_ARG, "nqubits out of range [4,40]");
+  std::vector<QbGate> q;
+  q.reserve(size_t(ngates));
+  for (int64_t k = 0; k < ngates; ++k) {
+    const qb_gate &g = gates[k];
+    if (g.target < 0 || g.target >= nqubits || (g.ctl_mask >> g.target & 1) || (g.ctl_mask >> nqubits))
+      return fail(QB_ERR_ARG, "gate %lld: bad bits", (long long)k);
+    QbGate x;
+    x.ctl_mask = g.ctl_mask;
+    x.target = g.target;
+    x.kind = classify(g.m);
+    memcpy(x.m, g.m, sizeof x.m);
+    q.push_back(x);
+  }
+  qb::Plan plan;
+  qb::plan_gates(nqubits, q.data(), ngates, tile_bits, &plan);
+  std::string js = plan.to_json();
+  *needed = js.size() + 1;
+  if (buf && cap >= js.size() + 1) memcpy(buf, js.c_str(), js.size() + 1);
+  return QB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,342 @@
+// kernels.cu -- single-gate sweeps and init/readout kernels for sm_100a.
+//
+// Every gate of the reference's hot path (xgates.cc:23-67, apply.cc:110-144,
+// gates.cc:17-146) is a strided butterfly over the dense amplitude vector.  The
+// kernels here are the UNFUSED form: one launch = one gate = one sweep over exactly
+// the amplitudes the gate touches.  They are bandwidth-bound (0.25-0.5 flop/B in
+// fp64), so the whole design is about the memory system:
+//   * 128-bit accesses: one amplitude (complex128) per LDG.128/STG.128;
+//   * consecutive lanes take consecutive "free" indices p, and the touched index is
+//     p with a 0 (target) or 1 (control) bit inserted -- for any target >= 5 a warp
+//     reads two fully coalesced 512 B runs; for targets 0..4 the two loads of a warp
+//     together cover one contiguous 1 KiB window, so every DRAM sector that is
+//     fetched is fully used;
+//   * controlled and diagonal gates enumerate only the indices they change (half,
+//     quarter, eighth of the vector) instead of predicating a full sweep, which is
+//     what makes their algorithmic bytes (16N, 8N) the real traffic;
+//   * 4 independent pairs per thread are loaded before any is used (8 LDG.128 in
+//     flight per thread) and streaming cache hints (ld.global.cs / st.global.cs)
+//     keep the 126 MB L2 from thrashing on data that is never re-read.
+// Grids are sized from the pair count; at 30 qubits that is 2^19 CTAs of 256
+// threads, i.e. thousands of waves over the 148 SMs, so no tail effect.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+namespace qb {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
+
+// Bits to insert into a dense "free" counter to obtain a touched index.
+struct InsertSpec {
+  int n;
+  int pos[4];        // ascending final positions
+  uint64_t setmask;  // bits forced to 1 after insertion (controls / phase bits)
+};
+
+__device__ __forceinline__ uint64_t expand_index(uint64_t p, const InsertSpec &s) {
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k < s.n) {
+      uint64_t low = (uint64_t(1) << s.pos[k]) - 1;
+      p = ((p & ~low) << 1) | (p & low);
+    }
+  }
+  return p | s.setmask;
+}
+
+template <typename V>
+struct Mat2 {
+  V a, b, c, d;
+};
+
+template <typename V>
+__device__ __forceinline__ V cmul(V x, V y) {
+  V r;
+  r.x = x.x * y.x - x.y * y.y;
+  r.y = x.x * y.y + x.y * y.x;
+  return r;
+}
+template <typename V>
+__device__ __forceinline__ V cadd(V x, V y) {
+  V r;
+  r.x = x.x + y.x;
+  r.y = x.y + y.y;
+  return r;
+}
+
+// General 2x2 on pairs (i0, i0 | tmask); same arithmetic as xgates.cc:34-37.
+template <typename V>
+__global__ void __launch_bounds__(kThreads)
+k_apply_u(V *__restrict__ psi, uint64_t npairs, InsertSpec ins, uint64_t tmask, Mat2<V> m) {
+  uint64_t base = (uint64_t(blockIdx.x) * kUnroll) * kThreads + threadIdx.x;
+  uint64_t idx[kUnroll];
+  V x[kUnroll], y[kUnroll];
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    uint64_t p = base + uint64_t(u) * kThreads;
+    if (p < npairs) {
+      idx[u] = expand_index(p, ins);
+      x[u] = __ldcs(psi + idx[u]);
+      y[u] = __ldcs(psi + (idx[u] | tmask));
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    uint64_t p = base + uint64_t(u) * kThreads;
+    if (p < npairs) {
+      V t1 = cadd(cmul(m.a, x[u]), cmul(m.b, y[u]));
+      V t2 = cadd(cmul(m.c, x[u]), cmul(m.d, y[u]));
+      __stcs(psi + idx[u], t1);
+      __stcs(psi + (idx[u] | tmask), t2);
+    }
+  }
+}
+
+// diag(1, p): multiply every amplitude whose index has all `setmask` bits set.
+template <typename V>
+__global__ void __launch_bounds__(kThreads)
+k_apply_phase(V *__restrict__ psi, uint64_t count, InsertSpec ins, V phase) {
+  uint64_t base = (uint64_t(blockIdx.x) * kUnroll) * kThreads + threadIdx.x;
+  uint64_t idx[kUnroll];
+  V x[kUnroll];
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    uint64_t p = base + uint64_t(u) * kThreads;
+    if (p < count) {
+      idx[u] = expand_index(p, ins);
+      x[u] = __ldcs(psi + idx[u]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    uint64_t p = base + uint64_t(u) * kThreads;
+    if (p < count) __stcs(psi + idx[u], cmul(phase, x[u]));
+  }
+}
+
+template <typename V, typename T>
+cudaError_t launch_gate_t(V *psi, int nbits, const QbGate &g, cudaStream_t st) {
+  // positions to insert: target (as 0 for U/DIAG/PERM, as 1 for PHASE) and controls (as 1)
+  InsertSpec ins{};
+  uint64_t ones = g.ctl_mask;
+  uint64_t all = g.ctl_mask | (uint64_t(1) << g.target);
+  if (__builtin_popcountll(all) > 4) return cudaErrorInvalidValue;
+  int n = 0;
+  for (int b = 0; b < nbits; ++b)
+    if (all >> b & 1) ins.pos[n++] = b;
+  ins.n = n;
+  uint64_t count = uint64_t(1) << (nbits - n);
+  unsigned blocks = unsigned((count + uint64_t(kThreads) * kUnroll - 1) / (uint64_t(kThreads) * kUnroll));
+  if (g.kind == QB_K_PHASE) {
+    ins.setmask = all;
+    V ph;
+    ph.x = T(g.m[6]);
+    ph.y = T(g.m[7]);
+    k_apply_phase<V><<<blocks, kThreads, 0, st>>>(psi, count, ins, ph);
+  } else {
+    ins.setmask = ones;
+    Mat2<V> m;
+    m.a.x = T(g.m[0]); m.a.y = T(g.m[1]);
+    m.b.x = T(g.m[2]); m.b.y = T(g.m[3]);
+    m.c.x = T(g.m[4]); m.c.y = T(g.m[5]);
+    m.d.x = T(g.m[6]); m.d.y = T(g.m[7]);
+    k_apply_u<V><<<blocks, kThreads, 0, st>>>(psi, count, ins, uint64_t(1) << g.target, m);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_gate(void *psi, int nbits, const QbGate &g, bool is_double, cudaStream_t st) {
+  if (g.kind == QB_K_NOP) return cudaSuccess;
+  if (is_double) return launch_gate_t<double2, double>(static_cast<double2 *>(psi), nbits, g, st);
+  return launch_gate_t<float2, float>(static_cast<float2 *>(psi), nbits, g, st);
+}
+
+// ---------------------------------------------------------------------------
+// init / readout
+// ---------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__global__ void __launch_bounds__(kThreads) k_fill_random(double2 *psi, uint64_t n, uint64_t seed) {
+  uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    uint64_t a = splitmix64(seed ^ (2 * i));
+    uint64_t b = splitmix64(seed ^ (2 * i + 1));
+    double2 v;
+    v.x = double(int64_t(a >> 11)) * (1.0 / 4503599627370496.0) - 1.0;  // [-1, 1)
+    v.y = double(int64_t(b >> 11)) * (1.0 / 4503599627370496.0) - 1.0;
+    psi[i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_scale(double2 *psi, uint64_t n, double f) {
+  uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double2 v = psi[i];
+    v.x *= f;
+    v.y *= f;
+    psi[i] = v;
+  }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_prob_mask(const double2 *__restrict__ psi, uint64_t n, uint64_t mask, double *out) {
+  __shared__ double part[kThreads / 32];
+  double acc = 0.0;
+  uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if ((i & mask) == mask) {
+      double2 v = psi[i];
+      acc += v.x * v.x + v.y * v.y;
+    }
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < kThreads / 32 ? part[threadIdx.x] : 0.0;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(out, v);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_argmax(const double2 *__restrict__ psi, uint64_t n, double *blk_prob, uint64_t *blk_idx) {
+  __shared__ double sp[kThreads / 32];
+  __shared__ uint64_t si[kThreads / 32];
+  double best = -1.0;
+  uint64_t bidx = 0;
+  uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double2 v = psi[i];
+    double p = v.x * v.x + v.y * v.y;
+    if (p > best) {  // ascending i per thread: strict > keeps the lowest index
+      best = p;
+      bidx = i;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double op = __shfl_xor_sync(0xffffffffu, best, o);
+    uint64_t oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+    if (op > best || (op == best && oi < bidx)) {
+      best = op;
+      bidx = oi;
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sp[threadIdx.x >> 5] = best;
+    si[threadIdx.x >> 5] = bidx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kThreads / 32; ++w)
+      if (sp[w] > best || (sp[w] == best && si[w] < bidx)) {
+        best = sp[w];
+        bidx = si[w];
+      }
+    blk_prob[blockIdx.x] = best;
+    blk_idx[blockIdx.x] = bidx;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_list_above(const double2 *__restrict__ psi, uint64_t n, double thr, uint64_t cap,
+             unsigned long long *counter, uint64_t *labels, double2 *amps) {
+  uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double2 v = psi[i];
+    if (v.x * v.x + v.y * v.y >= thr) {
+      unsigned long long slot = atomicAdd(counter, 1ull);
+      if (slot < cap) {
+        labels[slot] = i;
+        amps[slot] = v;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_cvt_f2d(const float2 *in, double2 *out, uint64_t n) {
+  uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float2 v = in[i];
+    out[i] = make_double2(v.x, v.y);
+  }
+}
+
+// 148 SMs x 8 resident CTAs of 256 threads: one full wave of grid-stride workers.
+constexpr int kReduceBlocks = 148 * 8;
+
+unsigned stride_blocks(uint64_t n) {
+  uint64_t want = (n + kThreads - 1) / kThreads;
+  if (want < 1) want = 1;
+  return unsigned(want < uint64_t(kReduceBlocks) ? want : kReduceBlocks);
+}
+
+}  // namespace
+
+cudaError_t launch_fill_random(double2 *psi, uint64_t n, uint64_t seed, cudaStream_t st) {
+  k_fill_random<<<stride_blocks(n), kThreads, 0, st>>>(psi, n, seed);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scale(double2 *psi, uint64_t n, double f, cudaStream_t st) {
+  k_scale<<<stride_blocks(n), kThreads, 0, st>>>(psi, n, f);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_norm2(const double2 *psi, uint64_t n, double *out, cudaStream_t st) {
+  return launch_prob_mask(psi, n, 0, out, st);
+}
+
+cudaError_t launch_prob_mask(const double2 *psi, uint64_t n, uint64_t mask, double *out,
+                             cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(out, 0, sizeof(double), st);
+  if (e != cudaSuccess) return e;
+  k_prob_mask<<<stride_blocks(n), kThreads, 0, st>>>(psi, n, mask, out);
+  return cudaGetLastError();
+}
+
+int argmax_blocks() { return kReduceBlocks; }
+
+cudaError_t launch_argmax(const double2 *psi, uint64_t n, double *blk_prob, uint64_t *blk_idx,
+                          cudaStream_t st) {
+  // always kReduceBlocks entries: blocks beyond the data report prob = -1
+  k_argmax<<<kReduceBlocks, kThreads, 0, st>>>(psi, n, blk_prob, blk_idx);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_list_above(const double2 *psi, uint64_t n, double thr, uint64_t cap,
+                              unsigned long long *counter, uint64_t *labels, double2 *amps,
+                              cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
+  if (e != cudaSuccess) return e;
+  k_list_above<<<stride_blocks(n), kThreads, 0, st>>>(psi, n, thr, cap, counter, labels, amps);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cvt_f2d(const float2 *in, double2 *out, uint64_t n, cudaStream_t st) {
+  k_cvt_f2d<<<stride_blocks(n), kThreads, 0, st>>>(in, out, n);
+  return cudaGetLastError();
+}
+
+}  // namespace qb

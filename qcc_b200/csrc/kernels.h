@@ -1,0 +1,49 @@
+// kernels.h -- host-callable launchers of the sm_100a kernels in kernels.cu / fused.cu.
+#ifndef QCC_B200_CSRC_KERNELS_H_
+#define QCC_B200_CSRC_KERNELS_H_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "qb_types.h"
+
+namespace qb {
+
+// ---- single-gate kernels (kernels.cu) ----------------------------------------
+// psi: 2^nbits complex (double2 when is_double, else float2).  One launch, one sweep
+// over exactly the amplitudes the gate touches.
+cudaError_t launch_gate(void *psi, int nbits, const QbGate &g, bool is_double, cudaStream_t st);
+
+// ---- init / readout kernels (kernels.cu) -------------------------------------
+cudaError_t launch_fill_random(double2 *psi, uint64_t n, uint64_t seed, cudaStream_t st);
+cudaError_t launch_scale(double2 *psi, uint64_t n, double f, cudaStream_t st);
+// out: 1 double (sum |psi|^2), zeroed by the launcher
+cudaError_t launch_norm2(const double2 *psi, uint64_t n, double *out, cudaStream_t st);
+// out: 1 double = sum of |psi_i|^2 over i with (i & mask) == mask
+cudaError_t launch_prob_mask(const double2 *psi, uint64_t n, uint64_t mask, double *out,
+                             cudaStream_t st);
+// Per-block partial argmax: blk_prob[b], blk_idx[b] for b < *nblocks_out; host finishes.
+int argmax_blocks();
+cudaError_t launch_argmax(const double2 *psi, uint64_t n, double *blk_prob, uint64_t *blk_idx,
+                          cudaStream_t st);
+// Compaction of indices with |psi|^2 >= thr: counter (1 x u64, zeroed by launcher), and up to
+// cap (label, amp) pairs in arbitrary order.
+cudaError_t launch_list_above(const double2 *psi, uint64_t n, double thr, uint64_t cap,
+                              unsigned long long *counter, uint64_t *labels, double2 *amps,
+                              cudaStream_t st);
+cudaError_t launch_cvt_f2d(const float2 *in, double2 *out, uint64_t n, cudaStream_t st);
+
+// ---- fused tile-resident pass (fused.cu) ---------------------------------------
+struct DevicePass {
+  QbPassDesc desc;
+  const QbOp *ops;        // device
+  const QbRound *rounds;  // device
+  const double2 *tables;  // device (ladder tables) or nullptr
+  const int32_t *outbits; // device (ladder outside-bit lists) or nullptr
+};
+cudaError_t fused_configure(int device);  // opt in to large dynamic shared memory, query SM count
+cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cudaStream_t st);
+
+}  // namespace qb
+
+#endif  // QCC_B200_CSRC_KERNELS_H_

@@ -1,0 +1,518 @@
+// planner.cc -- see planner.h / qb_types.h for the pass format.
+//
+// Pipeline:  gates -> items (plain gate | phase ladder) -> passes -> rounds -> ops.
+//
+//  1. Ladder merge.  Consecutive PHASE gates (they all commute) on <= 2 bits that share
+//     one "pivot" bit are merged into a LADDER item: for every index with the pivot
+//     set, multiply by the product of the partner phases whose bit is set.  This is the
+//     controlled-phase ladder that follows each h in circuit.py:320-328 (qft): up to
+//     n-1 cu1 gates become one op whose phase is looked up in two 64-entry tables.
+//  2. Pass cut.  Only U / PERM / SWAP items need their target inside the tile (they mix
+//     two amplitudes); PHASE / DIAG / LADDER items are diagonal and can run in any tile.
+//     A pass greedily collects items until it would need more than K-3 distinct targets
+//     above bit 2.  Tile bits = {0,1,2} + targets, padded with the lowest unused bits so
+//     that tiles are as contiguous in memory as possible.
+//  3. Round cut.  Inside a pass, ops are greedily grouped while their targets fit in 3
+//     tile-local bits (8 amplitudes per thread in registers).
+#include "planner.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+namespace qb {
+
+namespace {
+
+inline Cplx cmulh(Cplx a, Cplx b) { return Cplx{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x}; }
+
+struct Item {
+  int kind;            // QbKind; LADDER for merged runs
+  int64_t first_gate;  // index of the first source gate
+  int64_t ngates;      // source gates merged into this item (incl. skipped no-ops)
+  double bytes_per_amp;
+  // plain gate
+  QbGate g;
+  // ladder
+  int pivot = -1;
+  std::vector<int> pbits;     // partner index bits
+  std::vector<Cplx> pphase;   // their phases
+  Cplx self{1.0, 0.0};        // phase applied whenever the pivot is set
+};
+
+bool needs_target(int kind) { return kind == QB_K_U || kind == QB_K_PERM || kind == QB_K_SWAP; }
+
+// --- 1. ladder merge -------------------------------------------------------------
+void build_items(const QbGate *gates, int64_t ng, bool ladders, std::vector<Item> *items) {
+  struct Open {
+    bool active = false;
+    int64_t first = 0, count = 0;
+    double bytes = 0;
+    uint64_t cand = 0;  // candidate pivot bits
+    std::vector<std::pair<uint64_t, Cplx>> parts;  // (bit set of the gate, phase)
+    QbGate first_gate;
+  } open;
+
+  auto close = [&]() {
+    if (!open.active) return;
+    Item it;
+    it.first_gate = open.first;
+    it.ngates = open.count;
+    it.bytes_per_amp = open.bytes;
+    if (open.parts.size() == 1) {
+      it.kind = QB_K_PHASE;
+      it.g = open.first_gate;
+    } else {
+      it.kind = QB_K_LADDER;
+      it.pivot = __builtin_ctzll(open.cand);
+      for (auto &p : open.parts) {
+        uint64_t rest = p.first & ~(uint64_t(1) << it.pivot);
+        if (rest == 0) {
+          it.self = cmulh(it.self, p.second);
+        } else {
+          int b = __builtin_ctzll(rest);
+          size_t k = 0;
+          for (; k < it.pbits.size(); ++k)
+            if (it.pbits[k] == b) break;
+          if (k == it.pbits.size()) {
+            it.pbits.push_back(b);
+            it.pphase.push_back(p.second);
+          } else {
+            it.pphase[k] = cmulh(it.pphase[k], p.second);
+          }
+        }
+      }
+    }
+    items->push_back(std::move(it));
+    open = Open();
+  };
+
+  for (int64_t i = 0; i < ng; ++i) {
+    const QbGate &g = gates[i];
+    if (g.kind == QB_K_NOP) {
+      // retire it with whatever item is open / comes next; costs nothing
+      if (open.active) {
+        open.count += 1;
+      } else if (!items->empty()) {
+        items->back().ngates += 1;
+      } else {
+        Item it;
+        it.kind = QB_K_NOP;
+        it.first_gate = i;
+        it.ngates = 1;
+        it.bytes_per_amp = 0;
+        it.g = g;
+        items->push_back(it);
+      }
+      continue;
+    }
+    uint64_t bits = g.ctl_mask | (uint64_t(1) << g.target);
+    if (ladders && g.kind == QB_K_PHASE && __builtin_popcountll(bits) <= 2) {
+      Cplx ph{g.m[6], g.m[7]};
+      if (open.active && (open.cand & bits)) {
+        open.cand &= bits;
+        open.parts.push_back({bits, ph});
+        open.count += 1;
+        open.bytes += gate_bytes_per_amp(g);
+        continue;
+      }
+      close();
+      open.active = true;
+      open.first = i;
+      open.count = 1;
+      open.bytes = gate_bytes_per_amp(g);
+      open.cand = bits;
+      open.parts.push_back({bits, ph});
+      open.first_gate = g;
+      continue;
+    }
+    close();
+    Item it;
+    it.kind = g.kind;
+    if (g.kind == QB_K_PERM && g.m[2] == 1.0 && g.m[3] == 0.0 && g.m[4] == 1.0 && g.m[5] == 0.0)
+      it.kind = QB_K_SWAP;
+    it.first_gate = i;
+    it.ngates = 1;
+    it.bytes_per_amp = gate_bytes_per_amp(g);
+    it.g = g;
+    items->push_back(it);
+  }
+  close();
+}
+
+// --- helpers ---------------------------------------------------------------------
+struct TileMap {
+  int K = 0;
+  int bits[QB_MAX_TILE_BITS + 3];
+  int lpos[64];  // index bit -> tile-local position or -1
+  uint64_t mask = 0;
+};
+
+TileMap make_tile(int nbits, int K, const std::vector<int> &targets_hi) {
+  TileMap t;
+  std::vector<int> b;
+  int low = std::min(QB_TILE_LOW, K);
+  for (int i = 0; i < low; ++i) b.push_back(i);
+  for (int x : targets_hi) b.push_back(x);
+  // pad with the lowest unused bits: keeps each tile as contiguous as possible
+  for (int i = low; i < nbits && int(b.size()) < K; ++i)
+    if (std::find(b.begin(), b.end(), i) == b.end()) b.push_back(i);
+  std::sort(b.begin(), b.end());
+  t.K = int(b.size());
+  for (int i = 0; i < 64; ++i) t.lpos[i] = -1;
+  for (int k = 0; k < t.K; ++k) {
+    t.bits[k] = b[k];
+    t.lpos[b[k]] = k;
+    t.mask |= uint64_t(1) << b[k];
+  }
+  return t;
+}
+
+struct PendingOp {
+  const Item *it;
+  int variant;  // DIAG: 0 -> d0 where target clear, 1 -> d1 where target set; else 0
+};
+
+// Split "index bits in `mask` must equal `want`" into the three predicate levels.
+void split_pred(const TileMap &tm, const int *rbit, int nr, uint64_t mask, uint64_t want, QbOp *op) {
+  op->lmask = op->lwant = op->rmask = op->rwant = 0;
+  op->gmask = op->gwant = 0;
+  for (int b = 0; b < 64; ++b) {
+    if (!(mask >> b & 1)) continue;
+    uint64_t w = want >> b & 1;
+    int lp = tm.lpos[b];
+    if (lp < 0) {
+      op->gmask |= uint64_t(1) << b;
+      op->gwant |= w << b;
+      continue;
+    }
+    int rp = -1;
+    for (int k = 0; k < nr; ++k)
+      if (rbit[k] == lp) rp = k;
+    if (rp >= 0) {
+      op->rmask |= 1u << rp;
+      op->rwant |= uint32_t(w) << rp;
+    } else {
+      op->lmask |= 1u << lp;
+      op->lwant |= uint32_t(w) << lp;
+    }
+  }
+}
+
+void build_ladder_tables(const TileMap &tm, const QbRound &r, const Item &it, int slot, PlannedPass *pp, QbOp *op) {
+  const int K = tm.K;
+  const int lo_bits = std::min(K, QB_LADDER_CHUNK);
+  const int hi_bits = K - lo_bits;
+  // per tile-local position phase (1 where the position is not a partner / the pivot)
+  Cplx per[QB_MAX_TILE_BITS];
+  for (int k = 0; k < K; ++k) per[k] = Cplx{1.0, 0.0};
+  std::vector<int> out_bits;
+  std::vector<Cplx> out_ph;
+  for (size_t k = 0; k < it.pbits.size(); ++k) {
+    int lp = tm.lpos[it.pbits[k]];
+    if (lp >= 0) per[lp] = cmulh(per[lp], it.pphase[k]);
+    else {
+      out_bits.push_back(it.pbits[k]);
+      out_ph.push_back(it.pphase[k]);
+    }
+  }
+  int plp = tm.lpos[it.pivot];
+  Cplx self_out = it.self;  // pivot outside the tile: folded into the per-tile constant
+  if (plp >= 0) {
+    per[plp] = cmulh(per[plp], it.self);
+    self_out = Cplx{1.0, 0.0};
+  }
+  // Table layout (double2 units from table_off):
+  //   [0, 64)            T_lo[j & 63]
+  //   [64, 64 + 2^hi)    T_hi[j >> 6]
+  //   next 8             F[e]   product over round bits set in e
+  //   next 1             constant factor (self phase when the pivot is outside the tile)
+  //   next nout          phases of the outside partner bits
+  // T_lo / T_hi are evaluated on the group base (round bits zero), F covers the round bits.
+  op->table_off = int32_t(pp->tables.size());
+  bool is_round[QB_MAX_TILE_BITS] = {false};
+  for (int k = 0; k < r.nbits; ++k) is_round[r.rbit[k]] = true;
+  for (int v = 0; v < 64; ++v) {
+    Cplx p{1.0, 0.0};
+    for (int k = 0; k < lo_bits; ++k)
+      if ((v >> k & 1) && !is_round[k]) p = cmulh(p, per[k]);
+    pp->tables.push_back(p);
+  }
+  for (int v = 0; v < (1 << hi_bits); ++v) {
+    Cplx p{1.0, 0.0};
+    for (int k = 0; k < hi_bits; ++k)
+      if ((v >> k & 1) && !is_round[lo_bits + k]) p = cmulh(p, per[lo_bits + k]);
+    pp->tables.push_back(p);
+  }
+  for (int e = 0; e < 8; ++e) {
+    Cplx p{1.0, 0.0};
+    for (int k = 0; k < r.nbits; ++k)
+      if (e >> k & 1) p = cmulh(p, per[r.rbit[k]]);
+    pp->tables.push_back(p);
+  }
+  pp->tables.push_back(self_out);
+  for (auto &p : out_ph) pp->tables.push_back(p);
+  op->nout = int32_t(out_bits.size());
+  op->out_off = int32_t(pp->outbits.size());
+  for (int b : out_bits) pp->outbits.push_back(b);
+  op->flags = slot;
+}
+
+void close_round(const TileMap &tm, std::vector<int> &rset, std::vector<PendingOp> &pend, int *nladders,
+                 PlannedPass *pp) {
+  if (pend.empty()) {
+    rset.clear();
+    return;
+  }
+  QbRound r{};
+  const int K = tm.K;
+  const int nr = std::min(K, QB_ROUND_BITS);
+  // pad the round's bit set with the lowest unused local positions
+  for (int k = 0; k < K && int(rset.size()) < nr; ++k)
+    if (std::find(rset.begin(), rset.end(), k) == rset.end()) rset.push_back(k);
+  std::sort(rset.begin(), rset.end());
+  r.nbits = nr;
+  for (int k = 0; k < nr; ++k) r.rbit[k] = rset[k];
+  // group-index bit -> local position.  The tile is stored swizzled (fused.cu): the
+  // 16-byte bank group of local index j is (j ^ j>>3 ^ j>>6 ^ j>>9 ...) & 7, so local bit
+  // b feeds bank-group bit b % 3.  Give group-index bits 0,1,2 one free local bit of each
+  // class so 8 consecutive lanes land in 8 distinct bank groups.
+  std::vector<int> freeb;
+  for (int k = 0; k < K; ++k)
+    if (std::find(rset.begin(), rset.end(), k) == rset.end()) freeb.push_back(k);
+  std::vector<int> order;
+  for (int cls = 0; cls < 3; ++cls)
+    for (size_t k = 0; k < freeb.size(); ++k)
+      if (freeb[k] >= 0 && freeb[k] % 3 == cls) {
+        order.push_back(freeb[k]);
+        freeb[k] = -1;
+        break;
+      }
+  for (int b : freeb)
+    if (b >= 0) order.push_back(b);
+  for (size_t k = 0; k < order.size(); ++k) r.qmap[k] = order[k];
+  r.op_begin = int32_t(pp->ops.size());
+  for (const PendingOp &po : pend) {
+    const Item &it = *po.it;
+    QbOp op{};
+    op.kind = it.kind;
+    op.tpos = 0;
+    if (it.kind == QB_K_LADDER) {
+      op.kind = QB_K_LADDER;
+      split_pred(tm, r.rbit, nr, uint64_t(1) << it.pivot, uint64_t(1) << it.pivot, &op);
+      build_ladder_tables(tm, r, it, (*nladders)++, pp, &op);
+    } else if (it.kind == QB_K_PHASE) {
+      uint64_t bits = it.g.ctl_mask | (uint64_t(1) << it.g.target);
+      split_pred(tm, r.rbit, nr, bits, bits, &op);
+      op.m[0] = it.g.m[6];
+      op.m[1] = it.g.m[7];
+    } else if (it.kind == QB_K_DIAG) {
+      // lowered to two phase ops: d0 where the target bit is clear, d1 where it is set
+      uint64_t bits = it.g.ctl_mask | (uint64_t(1) << it.g.target);
+      uint64_t want = it.g.ctl_mask | (po.variant ? (uint64_t(1) << it.g.target) : 0);
+      split_pred(tm, r.rbit, nr, bits, want, &op);
+      op.kind = QB_K_PHASE;
+      op.m[0] = it.g.m[po.variant ? 6 : 0];
+      op.m[1] = it.g.m[po.variant ? 7 : 1];
+    } else {  // U / PERM / SWAP
+      split_pred(tm, r.rbit, nr, it.g.ctl_mask, it.g.ctl_mask, &op);
+      int lp = tm.lpos[it.g.target];
+      for (int k = 0; k < nr; ++k)
+        if (r.rbit[k] == lp) op.tpos = k;
+      memcpy(op.m, it.g.m, sizeof op.m);
+    }
+    pp->ops.push_back(op);
+  }
+  r.op_end = int32_t(pp->ops.size());
+  pp->rounds.push_back(r);
+  rset.clear();
+  pend.clear();
+}
+
+void emit_pass(int nbits, int K, const std::vector<const Item *> &items, const std::vector<int> &targets_hi,
+               Plan *out) {
+  if (items.empty()) return;
+  // Cheap cases first: one real gate, or a handful of plain PHASE gates whose own sweeps
+  // move less data than a full 32 B/amplitude pass.
+  int64_t real = 0;
+  bool all_phase = true;
+  double bytes = 0;
+  for (const Item *it : items) {
+    if (it->kind == QB_K_NOP) continue;
+    real += 1;
+    bytes += it->bytes_per_amp;
+    if (it->kind != QB_K_PHASE) all_phase = false;
+  }
+  if (real == 0 || (real == 1 && items.size() == 1 && items[0]->kind != QB_K_LADDER) ||
+      (all_phase && bytes <= 24.0)) {
+    for (const Item *it : items) {
+      PlannedPass pp;
+      pp.single_gate = it->first_gate;
+      pp.ngates = it->ngates;
+      pp.bytes_algorithmic_per_amp = it->bytes_per_amp;
+      out->passes.push_back(std::move(pp));
+    }
+    return;
+  }
+  PlannedPass pp;
+  TileMap tm = make_tile(nbits, K, targets_hi);
+  pp.desc.K = tm.K;
+  pp.desc.tile_mask = tm.mask;
+  for (int k = 0; k < tm.K; ++k) pp.desc.tile_bits[k] = tm.bits[k];
+  std::vector<int> rset;
+  std::vector<PendingOp> pend;
+  int nlad = 0;
+  const int nr = std::min(tm.K, QB_ROUND_BITS);
+  for (const Item *it : items) {
+    pp.ngates += it->ngates;
+    pp.bytes_algorithmic_per_amp += it->bytes_per_amp;
+    if (it->kind == QB_K_NOP) continue;
+    if (needs_target(it->kind)) {
+      int lp = tm.lpos[it->g.target];
+      if (std::find(rset.begin(), rset.end(), lp) == rset.end()) {
+        if (int(rset.size()) == nr) close_round(tm, rset, pend, &nlad, &pp);
+        rset.push_back(lp);
+      }
+    }
+    pend.push_back(PendingOp{it, 0});
+    if (it->kind == QB_K_DIAG) pend.push_back(PendingOp{it, 1});
+  }
+  close_round(tm, rset, pend, &nlad, &pp);
+  pp.desc.nrounds = int32_t(pp.rounds.size());
+  pp.desc.nops = int32_t(pp.ops.size());
+  pp.desc.ntable = int32_t(pp.tables.size());
+  pp.noutbits = int(pp.outbits.size());
+  out->passes.push_back(std::move(pp));
+}
+
+size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+
+}  // namespace
+
+double gate_bytes_per_amp(const QbGate &g) {
+  if (g.kind == QB_K_NOP) return 0.0;
+  int nb = __builtin_popcountll(g.ctl_mask);
+  if (g.kind == QB_K_PHASE || g.kind == QB_K_DIAG) nb += 1;  // diagonal = half
+  return 32.0 / double(uint64_t(1) << nb);
+}
+
+void plan_gates(int nbits, const QbGate *gates, int64_t ngates, int tile_bits, Plan *out) {
+  out->passes.clear();
+  int K = std::max(4, std::min(tile_bits, QB_MAX_TILE_BITS));
+  K = std::min(K, nbits);
+  const int cap = K - std::min(QB_TILE_LOW, K);
+  static const bool no_ladder = getenv("QCC_B200_NO_LADDER") != nullptr;
+  std::vector<Item> items;
+  build_items(gates, ngates, !no_ladder, &items);
+  std::vector<const Item *> cur;
+  std::vector<int> targets;
+  size_t nladders = 0;
+  for (const Item &it : items) {
+    bool new_target = needs_target(it.kind) && it.g.target >= QB_TILE_LOW &&
+                      std::find(targets.begin(), targets.end(), it.g.target) == targets.end();
+    bool too_many_ladders = it.kind == QB_K_LADDER && nladders >= 64;
+    if ((new_target && int(targets.size()) == cap) || too_many_ladders) {
+      emit_pass(nbits, K, cur, targets, out);
+      cur.clear();
+      targets.clear();
+      nladders = 0;
+    }
+    if (new_target) targets.push_back(it.g.target);
+    if (it.kind == QB_K_LADDER) nladders += 1;
+    cur.push_back(&it);
+  }
+  emit_pass(nbits, K, cur, targets, out);
+}
+
+size_t Plan::blob_bytes() {
+  size_t off = 0;
+  for (PlannedPass &p : passes) {
+    if (p.single_gate >= 0) continue;
+    p.ops_off = off;
+    off = align16(off + p.ops.size() * sizeof(QbOp));
+    p.rounds_off = off;
+    off = align16(off + p.rounds.size() * sizeof(QbRound));
+    p.tables_off = off;
+    off = align16(off + p.tables.size() * sizeof(Cplx));
+    p.outbits_off = off;
+    off = align16(off + p.outbits.size() * sizeof(int32_t));
+  }
+  return std::max<size_t>(off, 16);
+}
+
+void Plan::serialize(char *dst) const {
+  for (const PlannedPass &p : passes) {
+    if (p.single_gate >= 0) continue;
+    memcpy(dst + p.ops_off, p.ops.data(), p.ops.size() * sizeof(QbOp));
+    memcpy(dst + p.rounds_off, p.rounds.data(), p.rounds.size() * sizeof(QbRound));
+    if (!p.tables.empty()) memcpy(dst + p.tables_off, p.tables.data(), p.tables.size() * sizeof(Cplx));
+    if (!p.outbits.empty()) memcpy(dst + p.outbits_off, p.outbits.data(), p.outbits.size() * sizeof(int32_t));
+  }
+}
+
+std::string Plan::to_json() const {
+  std::string s = "{\"passes\":[";
+  char buf[256];
+  bool firstp = true;
+  for (const PlannedPass &p : passes) {
+    if (!firstp) s += ",";
+    firstp = false;
+    if (p.single_gate >= 0) {
+      snprintf(buf, sizeof buf, "{\"single_gate\":%lld,\"ngates\":%lld}", (long long)p.single_gate,
+               (long long)p.ngates);
+      s += buf;
+      continue;
+    }
+    snprintf(buf, sizeof buf, "{\"single_gate\":-1,\"ngates\":%lld,\"K\":%d,\"tile_bits\":[", (long long)p.ngates,
+             p.desc.K);
+    s += buf;
+    for (int k = 0; k < p.desc.K; ++k) {
+      snprintf(buf, sizeof buf, "%s%d", k ? "," : "", p.desc.tile_bits[k]);
+      s += buf;
+    }
+    s += "],\"rounds\":[";
+    for (size_t r = 0; r < p.rounds.size(); ++r) {
+      const QbRound &R = p.rounds[r];
+      snprintf(buf, sizeof buf, "%s{\"nbits\":%d,\"rbit\":[%d,%d,%d],\"op_begin\":%d,\"op_end\":%d,\"qmap\":[",
+               r ? "," : "", R.nbits, R.rbit[0], R.rbit[1], R.rbit[2], R.op_begin, R.op_end);
+      s += buf;
+      for (int k = 0; k < p.desc.K - R.nbits; ++k) {
+        snprintf(buf, sizeof buf, "%s%d", k ? "," : "", R.qmap[k]);
+        s += buf;
+      }
+      s += "]}";
+    }
+    s += "],\"ops\":[";
+    for (size_t o = 0; o < p.ops.size(); ++o) {
+      const QbOp &O = p.ops[o];
+      snprintf(buf, sizeof buf,
+               "%s{\"kind\":%d,\"tpos\":%d,\"lmask\":%u,\"lwant\":%u,\"rmask\":%u,\"rwant\":%u,"
+               "\"gmask\":%llu,\"gwant\":%llu,\"table_off\":%d,\"nout\":%d,\"out_off\":%d,\"flags\":%d,\"m\":[",
+               o ? "," : "", O.kind, O.tpos, O.lmask, O.lwant, O.rmask, O.rwant, (unsigned long long)O.gmask,
+               (unsigned long long)O.gwant, O.table_off, O.nout, O.out_off, O.flags);
+      s += buf;
+      for (int k = 0; k < 8; ++k) {
+        snprintf(buf, sizeof buf, "%s%.17g", k ? "," : "", O.m[k]);
+        s += buf;
+      }
+      s += "]}";
+    }
+    s += "],\"tables\":[";
+    for (size_t t = 0; t < p.tables.size(); ++t) {
+      snprintf(buf, sizeof buf, "%s[%.17g,%.17g]", t ? "," : "", p.tables[t].x, p.tables[t].y);
+      s += buf;
+    }
+    s += "],\"outbits\":[";
+    for (size_t t = 0; t < p.outbits.size(); ++t) {
+      snprintf(buf, sizeof buf, "%s%d", t ? "," : "", p.outbits[t]);
+      s += buf;
+    }
+    s += "]}";
+  }
+  s += "]}";
+  return s;
+}
+
+}  // namespace qb

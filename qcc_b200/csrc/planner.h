@@ -1,0 +1,53 @@
+// planner.h -- gate-stream -> fused-pass planner (pure host code, no CUDA calls).
+//
+// The reference's only fusion attempt is src/libq/gates_jit.cc:53-132: a queue of
+// diagonal / permutation ops replayed per basis state in one sweep, flushed by any
+// general gate.  On a GPU the same idea pays off because a sweep costs an HBM round
+// trip: this planner cuts the queued gate stream into PASSES (one HBM sweep each) and
+// each pass into ROUNDS (one shared-memory round trip each) -- see qb_types.h.
+#ifndef QCC_B200_CSRC_PLANNER_H_
+#define QCC_B200_CSRC_PLANNER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "qb_types.h"
+
+namespace qb {
+
+struct Cplx {
+  double x, y;
+};
+
+struct PlannedPass {
+  QbPassDesc desc{};
+  std::vector<QbOp> ops;
+  std::vector<QbRound> rounds;
+  std::vector<Cplx> tables;
+  std::vector<int32_t> outbits;
+  // filled by Plan::layout(): byte offsets inside the serialized blob
+  size_t ops_off = 0, rounds_off = 0, tables_off = 0, outbits_off = 0;
+  int noutbits = 0;
+  int64_t single_gate = -1;  // >= 0: run gates[single_gate] with the plain sweep kernel instead
+  int64_t ngates = 0;        // gate records this pass retires (including no-ops)
+  double bytes_algorithmic_per_amp = 0.0;
+};
+
+struct Plan {
+  std::vector<PlannedPass> passes;
+  size_t blob_bytes();               // lays the passes out and returns the blob size
+  void serialize(char *dst) const;   // after blob_bytes()
+  std::string to_json() const;       // for the CPU tests (tests/ interprets it with numpy)
+};
+
+// SURVEY.md 8(d) algorithmic bytes per amplitude of the full vector for one gate.
+double gate_bytes_per_amp(const QbGate &g);
+
+void plan_gates(int nbits, const QbGate *gates, int64_t ngates, int tile_bits, Plan *out);
+
+}  // namespace qb
+
+#endif  // QCC_B200_CSRC_PLANNER_H_

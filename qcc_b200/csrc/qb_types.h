@@ -1,0 +1,91 @@
+// qb_types.h -- internal types shared by the host engine, the fusion planner and
+// the CUDA kernels.  Nothing here is part of the C ABI (include/qcc_b200.h).
+#ifndef QCC_B200_CSRC_QB_TYPES_H_
+#define QCC_B200_CSRC_QB_TYPES_H_
+
+#include <stdint.h>
+
+// How a 2x2 acts, decided once on the host from its entries (engine.cu classify):
+//   U      general 2x2 on (psi[i0], psi[i1])                          h v yroot rx ry ...
+//   PHASE  diag(1, p): psi[i] *= p where target and control bits set   z s t u1 cz cu1
+//   DIAG   diag(d0, d1), d0 != 1                                       rz
+//   PERM   antidiagonal | 0 b ; c 0 |: swap with weights               x y cx ccx
+// PHASE only touches half (or a quarter, an eighth) of the vector; PERM with b = c = 1
+// is the pure label permutation of gates.cc:17-21,120-146.
+enum QbKind : int32_t {
+  QB_K_U = 0,
+  QB_K_PHASE = 1,
+  QB_K_DIAG = 2,
+  QB_K_PERM = 3,
+  QB_K_LADDER = 4,  // fused run of PHASE gates sharing one pivot bit (QFT ladder)
+  QB_K_NOP = 5,
+  QB_K_SWAP = 6,    // PERM with b = c = 1: moves amplitudes, no arithmetic
+};
+
+// A gate in physical index-bit terms, as queued by the engine.
+struct QbGate {
+  uint64_t ctl_mask;  // bits that must be 1 (never contains `target`)
+  int32_t target;
+  int32_t kind;       // QbKind
+  double m[8];        // a b c d as (re, im)
+};
+
+// ---------------------------------------------------------------------------
+// Fused-pass format (produced by planner.cc, consumed by fused.cu).
+//
+// A PASS is one HBM sweep.  It fixes a set of K "tile bits" (index-bit positions,
+// ascending, always containing bits 0..QB_TILE_LOW-1 so that every tile is made of
+// >= 128-byte contiguous runs).  A TILE is the 2^K amplitudes obtained by fixing all
+// non-tile bits; a CTA loads one tile into shared memory, applies every op of the
+// pass, and stores it back.  Inside a tile an amplitude is addressed by its K-bit
+// tile-local index j (bit k of j = index bit tile_bits[k]).
+//
+// Ops are grouped into ROUNDS.  A round names QB_ROUND_BITS tile-local positions
+// rbit[]; each thread pulls the 2^3 amplitudes that differ only in those bits into
+// registers, applies all ops of the round there, and writes them back -- one
+// shared-memory round trip per round, not per gate.  The remaining K-3 local bits
+// enumerate the groups; qmap[] says which local bit each group-index bit drives and
+// is chosen by the planner so that 8 consecutive lanes always fall into 8 distinct
+// 16-byte bank groups of the swizzled tile (see fused.cu).
+//
+// Every op carries a three-level predicate, all of the form (x & mask) == want:
+//   g*: on the index bits outside the tile  -> uniform per CTA
+//   l*: on tile-local bits outside the round -> one test per thread-group
+//   r*: on round positions (3 bits)          -> resolved per register at unroll time
+// ---------------------------------------------------------------------------
+#define QB_TILE_LOW 3        // bits 0..2 are always tile bits (8 amps = 128 B runs)
+#define QB_MAX_TILE_BITS 13  // 2^13 * 16 B = 128 KiB
+#define QB_ROUND_BITS 3      // 8 amplitudes = 16 doubles in registers per thread
+#define QB_LADDER_CHUNK 6    // ladder lookup tables are indexed by 6 tile-local bits
+
+struct alignas(16) QbOp {   // 128 bytes, read by the kernel as 16-byte pieces
+  int32_t kind;      // QbKind (never DIAG/NOP: the planner lowers those)
+  int32_t tpos;      // U/PERM/SWAP: target position inside rbit[]
+  uint32_t lmask, lwant;
+  uint32_t rmask, rwant;
+  int32_t table_off; // LADDER: first double2 of this op's tables in the pass table buffer
+  int32_t flags;     // LADDER: slot (0..63) of its per-tile constant in shared memory
+  uint64_t gmask, gwant;
+  double m[8];       // U/PERM: a b c d; PHASE: p in m[0..1]
+  int32_t nout;      // LADDER: number of partner bits outside the tile
+  int32_t out_off;   // LADDER: first entry in the pass's outside-bit array
+  int32_t pad0, pad1;
+};
+
+struct QbRound {
+  int32_t nbits;                     // == min(K, QB_ROUND_BITS)
+  int32_t rbit[QB_ROUND_BITS];       // tile-local positions, ascending
+  int32_t qmap[QB_MAX_TILE_BITS];    // local position driven by group-index bit k
+  int32_t op_begin, op_end;          // range in the pass's op array
+};
+
+struct QbPassDesc {
+  int32_t K;                           // tile bits
+  int32_t nrounds;
+  int32_t nops;
+  int32_t ntable;                      // double2 entries in the table buffer
+  int32_t tile_bits[QB_MAX_TILE_BITS + 3];  // index-bit positions, ascending
+  uint64_t tile_mask;                  // OR of 1 << tile_bits[k]
+};
+
+#endif  // QCC_B200_CSRC_QB_TYPES_H_

@@ -1,0 +1,109 @@
+"""Gate streams of the reference workloads named in BASELINE.json, as flat lists of
+(kind, ctl, tgt, 2x2) in the reference's python qubit numbering (kind 1 = apply1,
+2 = applyc -- what circuit.py:180-215 hands to xgates per call)."""
+from __future__ import annotations
+
+import math
+import random
+
+import numpy as np
+
+from qcc_b200 import ops
+
+
+def qft(n: int, reg=None):
+  """circuit.py:320-326 (qft without swaps): per i from n-1 down: h(i), then
+  cu1(i, j, pi / 2^(i-j)) for j < i.  30 qubits: 30 h + 435 cu1 = 465 gates."""
+  reg = list(range(n)) if reg is None else list(reg)
+  h = np.asarray(ops.Hadamard())
+  out = []
+  for i in reversed(range(len(reg))):
+    out.append((1, 0, reg[i], h))
+    for j in reversed(range(i)):
+      out.append((2, reg[i], reg[j], np.asarray(ops.U1(math.pi / 2 ** (i - j)))))
+  return out
+
+
+def inverse_of(stream):
+  """circuit.py:423-456: reversed order, adjoint gates."""
+  return [(k, c, t, np.asarray(m).conj().T) for k, c, t, m in reversed(stream)]
+
+
+def larose(n: int, depth: int):
+  """larose_benchmark.py:47-54: per depth, per bit: h, v, and cx(bit, 0) for bit > 0.
+  28 qubits, depth 28: 784 h + 784 v + 756 cx = 2324 gates."""
+  h, v, x = (np.asarray(g) for g in (ops.Hadamard(), ops.Vgate(), ops.PauliX()))
+  out = []
+  for _ in range(depth):
+    for bit in range(n):
+      out.append((1, 0, bit, h))
+      out.append((1, 0, bit, v))
+      if bit > 0:
+        out.append((2, bit, 0, x))
+  return out
+
+
+def hsweep(n: int):
+  """The headline micro-benchmark: one h on every qubit."""
+  h = np.asarray(ops.Hadamard())
+  return [(1, 0, q, h) for q in range(n)]
+
+
+# supremacy.py:19-97 CZ patterns are data in the reference; the generator below follows the
+# same construction rule (supremacy.py:123-158, 208-240) on a caller-supplied pattern set.
+def supremacy(n: int, depth: int, seed: int = 0, patterns=None):
+  """Random circuit in the style of supremacy.py: layer 0 is h on every qubit; each later
+  layer places cz pairs from a random pattern and fills the rest by the rules of
+  supremacy.py:147-154 (after cz -> v or yroot at random, after that or h -> t); a final h
+  layer closes it (supremacy.py:156-158).  `patterns` is a list of per-qubit offsets like the
+  reference's; by default nearest-neighbour / +6 offsets (the two distances sim_circuit
+  handles, supremacy.py:234-239) are generated from the seed."""
+  rng = random.Random(seed)
+  if patterns is None:
+    patterns = []
+    for p in range(8):
+      pat = [0] * n
+      step = 1 if p % 2 == 0 else 6
+      i = (p // 2) % (2 * step)
+      while i + step < n:
+        pat[i] = step
+        i += 2 * step if step == 1 else (1 if (i + 1) % step else step + 1)
+      patterns.append(pat)
+  H, T, U, CZ, UNK = "h", "t", "u", "cz", None
+  state0 = [H] * n
+  states = [state0]
+  for _ in range(depth - 1):
+    state1 = [UNK] * n
+    pat = patterns[rng.randint(0, len(patterns) - 1)]
+    for i in range(min(n, len(pat))):
+      if pat[i] != 0 and i + pat[i] < n and state1[i] is UNK and state1[i + pat[i]] is UNK:
+        state1[i] = (CZ, i + pat[i])
+        state1[i + pat[i]] = (CZ, -1)
+    for i in range(n):
+      is_cz = isinstance(state1[i], tuple)
+      was_cz = isinstance(state0[i], tuple)
+      if was_cz and not is_cz:
+        state1[i] = U
+      elif state0[i] == U and not is_cz:
+        state1[i] = T
+      elif state0[i] == H and not is_cz:
+        state1[i] = T
+    state0 = state1
+    states.append(state0)
+  states.append([H] * n)
+  g = {k: np.asarray(v) for k, v in (("h", ops.Hadamard()), ("t", ops.Tgate()), ("v", ops.Vgate()),
+                                     ("yroot", ops.Yroot()), ("z", ops.PauliZ()))}
+  out = []
+  for s in states:
+    for i in range(n):
+      if s[i] is UNK:
+        continue
+      if s[i] == H:
+        out.append((1, 0, i, g["h"]))
+      elif s[i] == T:
+        out.append((1, 0, i, g["t"]))
+      elif s[i] == U:
+        out.append((1, 0, i, g["v"] if rng.randint(0, 1) == 0 else g["yroot"]))
+      elif isinstance(s[i], tuple) and s[i][1] >= 0:
+        out.append((2, i, s[i][1], g["z"]))
+  return out

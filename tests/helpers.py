@@ -1,0 +1,182 @@
+"""Shared test helpers: golden loaders, index-bit reference apply, and a numpy interpreter of
+the fusion planner's pass format (so the planner can be verified on CPU, where no kernel
+can run).  Test infrastructure only -- may import oracle/, never imported by qcc_b200."""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+from oracle import oracle  # noqa: E402
+
+K_U, K_PHASE, K_DIAG, K_PERM, K_LADDER, K_NOP, K_SWAP = range(7)
+
+
+def load_golden(name):
+  return np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+
+
+def stream_of(z):
+  """(kind, ctl, tgt, 2x2) tuples in python numbering from a golden npz."""
+  return [(int(k), int(c), int(t), m.reshape(2, 2)) for k, c, t, m in
+          zip(z["kind"], z["ctl"], z["tgt"], z["mats"])]
+
+
+def xg_to_bits(n, stream):
+  """python-numbered stream -> [(ctl_mask, target_bit, 2x2)] following xgates.cc:45-67
+  (negative controls included).  Gates that act on nothing are dropped."""
+  out = []
+  for kind, ctl, tgt, m in stream:
+    t = n - 1 - tgt
+    if kind == 1:
+      out.append((0, t, m))
+      continue
+    c = n - 1 - ctl
+    if c < n:
+      if c == t:
+        continue
+      out.append((1 << c, t, m))
+    else:
+      cc = c - n
+      if cc <= t or cc >= n:
+        continue
+      out.append((1 << cc, t, m))
+  return out
+
+
+def apply_masked(psi, n, ctl_mask, target, m):
+  """Index-bit reference: 2x2 on bit `target` where all ctl_mask bits are 1 (in place)."""
+  m = np.asarray(m, dtype=np.complex128).reshape(4)
+  idx = np.arange(1 << n, dtype=np.int64)
+  sel = ((idx >> target) & 1 == 0) & ((idx & ctl_mask) == ctl_mask)
+  i0 = idx[sel]
+  i1 = i0 | (1 << target)
+  a = psi[i0].copy()
+  b = psi[i1].copy()
+  psi[i0] = m[0] * a + m[1] * b
+  psi[i1] = m[2] * a + m[3] * b
+
+
+def run_bits(psi, n, gates):
+  for mask, t, m in gates:
+    apply_masked(psi, n, mask, t, m)
+  return psi
+
+
+def random_state(n, seed):
+  rng = np.random.default_rng(seed)
+  v = rng.normal(size=1 << n) + 1j * rng.normal(size=1 << n)
+  return (v / np.linalg.norm(v)).astype(np.complex128)
+
+
+# ---------------------------------------------------------------------------------------
+# numpy interpreter of qb_plan_json output: mirrors fused.cu step by step (tile gather,
+# rounds, three-level predicates, ladder tables), vectorised over tiles and groups.
+# ---------------------------------------------------------------------------------------
+def interpret_plan(plan_json: str, n: int, gates, psi: np.ndarray) -> np.ndarray:
+  plan = json.loads(plan_json)
+  retired = 0
+  for p in plan["passes"]:
+    retired += p["ngates"]
+    if p["single_gate"] >= 0:
+      mask, t, m = gates[p["single_gate"]]
+      apply_masked(psi, n, mask, t, m)
+      continue
+    K = p["K"]
+    tb = p["tile_bits"]
+    assert tb[:3] == [0, 1, 2] and sorted(tb) == tb and len(tb) == K
+    non_tile = [b for b in range(n) if b not in tb]
+    ntiles = 1 << (n - K)
+    tids = np.arange(ntiles, dtype=np.int64)
+    base = np.zeros(ntiles, dtype=np.int64)
+    for k, b in enumerate(non_tile):
+      base |= ((tids >> k) & 1) << b
+    j = np.arange(1 << K, dtype=np.int64)
+    off = np.zeros(1 << K, dtype=np.int64)
+    for k, b in enumerate(tb):
+      off |= ((j >> k) & 1) << b
+    gidx = base[:, None] | off[None, :]
+    T = psi[gidx]                               # [tile, local]
+    tables = np.array([complex(x, y) for x, y in p["tables"]], dtype=np.complex128)
+    outbits = p["outbits"]
+    hi_bits = max(K - 6, 0)
+    for R in p["rounds"]:
+      assert R["nbits"] == 3
+      rbit = R["rbit"]
+      qmap = R["qmap"]
+      assert sorted(rbit + qmap) == list(range(K)), "round bits + qmap must partition the tile"
+      ng = 1 << (K - 3)
+      q = np.arange(ng, dtype=np.int64)
+      jb = np.zeros(ng, dtype=np.int64)
+      for k, lp in enumerate(qmap):
+        jb |= ((q >> k) & 1) << lp
+      spread = np.array([sum(((e >> k) & 1) << rbit[k] for k in range(3)) for e in range(8)])
+      je = jb[:, None] | spread[None, :]        # [group, e]
+      A = T[:, je]                              # [tile, group, e]
+      for op in p["ops"][R["op_begin"]:R["op_end"]]:
+        tile_ok = (base & op["gmask"]) == op["gwant"]
+        grp_ok = (jb & op["lmask"]) == op["lwant"]
+        ok = tile_ok[:, None] & grp_ok[None, :]                        # [tile, group]
+        m = np.array(op["m"]).view(np.complex128) if False else np.array(
+            [complex(op["m"][2 * i], op["m"][2 * i + 1]) for i in range(4)])
+        kind = op["kind"]
+        if kind in (K_U, K_PERM, K_SWAP):
+          tp = op["tpos"]
+          for e in range(8):
+            if e & (1 << tp) or (e & op["rmask"]) != op["rwant"]:
+              continue
+            e1 = e | (1 << tp)
+            x = A[:, :, e].copy()
+            y = A[:, :, e1].copy()
+            if kind == K_U:
+              nx, ny = m[0] * x + m[1] * y, m[2] * x + m[3] * y
+            elif kind == K_PERM:
+              nx, ny = m[1] * y, m[2] * x
+            else:
+              nx, ny = y, x
+            A[:, :, e] = np.where(ok, nx, x)
+            A[:, :, e1] = np.where(ok, ny, y)
+        elif kind == K_PHASE:
+          for e in range(8):
+            if (e & op["rmask"]) == op["rwant"]:
+              A[:, :, e] = np.where(ok, m[0] * A[:, :, e], A[:, :, e])
+        elif kind == K_LADDER:
+          t0 = op["table_off"]
+          cbase = t0 + 64 + (1 << hi_bits) + 8
+          pout = np.full(ntiles, tables[cbase], dtype=np.complex128)
+          for k in range(op["nout"]):
+            bit = outbits[op["out_off"] + k]
+            pout = np.where((base >> bit) & 1 == 1, pout * tables[cbase + 1 + k], pout)
+          c = pout[:, None] * tables[t0 + (jb & 63)][None, :]
+          if hi_bits:
+            c = c * tables[t0 + 64 + (jb >> 6)][None, :]
+          F = tables[t0 + 64 + (1 << hi_bits): t0 + 64 + (1 << hi_bits) + 8]
+          for e in range(8):
+            if (e & op["rmask"]) == op["rwant"]:
+              A[:, :, e] = np.where(ok, c * F[e] * A[:, :, e], A[:, :, e])
+        else:
+          raise AssertionError(f"unexpected op kind {kind}")
+      T[:, je] = A
+    psi[gidx] = T
+  assert retired == len(gates), f"plan retires {retired} of {len(gates)} gates"
+  return psi
+
+
+def plan_summary(plan_json: str):
+  plan = json.loads(plan_json)
+  fused = [p for p in plan["passes"] if p["single_gate"] < 0]
+  return {
+      "passes": len(plan["passes"]),
+      "fused": len(fused),
+      "singles": len(plan["passes"]) - len(fused),
+      "rounds": sum(len(p["rounds"]) for p in fused),
+      "ops": sum(len(p["ops"]) for p in fused),
+      "ladders": sum(1 for p in fused for o in p["ops"] if o["kind"] == K_LADDER),
+  }

@@ -1,0 +1,109 @@
+"""GPU: BASELINE.json's full sizes (28-30 qubits), checked through size-independent
+properties because no oracle finishes at these sizes in seconds (and the reference itself
+cannot run above 30 qubits, SURVEY.md trap 3):
+  * unitarity: the norm stays 1;
+  * QFT then its inverse circuit (circuit.py:423-456: reversed order, adjoint gates) returns
+    the initial basis state;
+  * QFT of a basis state has a flat spectrum |amp|^2 = 2^-n, and its amplitudes follow the
+    closed form, spot-checked;
+  * the fused path and the gate-by-gate path agree on sampled slices of a random state.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from helpers import oracle
+from qcc_b200 import _cabi
+
+pytestmark = pytest.mark.gpu
+
+
+def qft_stream(n, inverse=False):
+  s = []
+  for i in reversed(range(n)):
+    s.append((1, 0, i, oracle.GATES["h"]))
+    for j in reversed(range(i)):
+      s.append((2, i, j, oracle.u1(math.pi / 2 ** (i - j))))
+  if inverse:
+    s = [(k, c, t, np.asarray(m).conj().T) for k, c, t, m in reversed(s)]
+  return s
+
+
+def qft_amplitude(n, x, k):
+  """Amplitude <k| QFT_noswap |x> for circuit.py:320-326 (validated against the oracle at
+  n = 10 in test_qft_closed_form_small)."""
+  xrev = int(format(x, f"0{n}b")[::-1], 2)
+  return np.exp(2j * np.pi * ((xrev * k) % (1 << n)) / (1 << n)) / math.sqrt(1 << n)
+
+
+def test_qft_closed_form_small():
+  n, x = 10, 0b1011001110
+  psi = np.zeros(1 << n, dtype=np.complex128)
+  psi[x] = 1
+  oracle.c_run(psi, n, qft_stream(n))
+  want = np.array([qft_amplitude(n, x, k) for k in range(1 << n)])
+  assert np.abs(psi - want).max() < 1e-12
+
+
+@pytest.mark.parametrize("n", [28, 30])
+def test_qft_roundtrip_and_flat_spectrum(n):
+  x = 0x2F0F3A5 & ((1 << n) - 1)
+  fwd = _cabi.pack_xg_gates(qft_stream(n))
+  inv = _cabi.pack_xg_gates(qft_stream(n, inverse=True))
+  with _cabi.DeviceState(n, x) as s:
+    s.xg_apply_gates(fwd)
+    assert abs(s.norm2() - 1.0) < 1e-9
+    idx, p = s.argmax()
+    assert abs(p * (1 << n) - 1.0) < 1e-9
+    for k in (0, 1, 12345, (1 << n) - 1, 0x1234567 & ((1 << n) - 1)):
+      assert abs(s.amplitude(k) - qft_amplitude(n, x, k)) < 1e-12
+    cnt = s.counters()
+    assert cnt["passes"] <= 4, cnt
+    s.xg_apply_gates(inv)
+    a = s.amplitude(x)
+    assert abs(a - 1.0) < 1e-9
+    assert abs(s.norm2() - 1.0) < 1e-9
+    labels, amps, count = s.list_above(1e-12)
+    assert count == 1 and labels[0] == x
+
+
+def test_walsh_30():
+  n = 30
+  with _cabi.DeviceState(n, 0) as s:
+    for t in range(n):
+      s.xg_apply1(t, oracle.GATES["h"])
+    assert abs(s.norm2() - 1.0) < 1e-9
+    _, p = s.argmax()
+    assert abs(p * (1 << n) - 1.0) < 1e-9
+    for bit in (0, 13, 29):
+      assert abs(s.prob_bit(bit) - 0.5) < 1e-9
+
+
+def test_fused_equals_single_gate_path_at_28():
+  n = 28
+  rng = np.random.default_rng(28)
+  names = ["h", "v", "yroot", "t", "x", "y", "z", "s"]
+  stream = []
+  for _ in range(60):
+    m = oracle.GATES[names[rng.integers(len(names))]] if rng.random() < 0.8 else oracle.u1(float(rng.uniform(-3, 3)))
+    t = int(rng.integers(n))
+    if rng.random() < 0.5:
+      stream.append((1, 0, t, m))
+    else:
+      c = int(rng.integers(n))
+      if c != t:
+        stream.append((2, c, t, m))
+  packed = _cabi.pack_xg_gates(stream)
+  with _cabi.DeviceState(n) as a, _cabi.DeviceState(n) as b:
+    a.fill_random(5)
+    b.fill_random(5)
+    b.set_fusion(False)
+    a.xg_apply_gates(packed)
+    b.xg_apply_gates(packed)
+    assert abs(a.norm2() - 1.0) < 1e-9 and abs(b.norm2() - 1.0) < 1e-9
+    for first in (0, 1 << 20, (1 << 27) + 4093, (1 << 28) - (1 << 16)):
+      x = a.copy_out(first, 1 << 16)
+      y = b.copy_out(first, 1 << 16)
+      assert np.abs(x - y).max() < 1e-15 * 1e3  # amplitudes are ~6e-5; agreement to ~1e-16 relative
+    assert a.counters()["passes"] * 3 < b.counters()["passes"]

@@ -1,0 +1,149 @@
+"""CPU: the C-ABI library loads and exports everything include/qcc_b200.h declares, fails
+loudly without a GPU, and its fusion planner (pure host code) produces plans that compute
+the same state as gate-by-gate application -- checked by interpreting the plan with numpy
+(tests/helpers.py), since no kernel can run here."""
+import ctypes
+import json
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import (GOLDEN, ROOT, interpret_plan, load_golden, oracle, plan_summary, random_state,
+                     run_bits, stream_of, xg_to_bits)
+from qcc_b200 import _cabi
+
+
+def test_library_exports_every_declared_symbol():
+  hdr = open(os.path.join(ROOT, "include", "qcc_b200.h")).read()
+  declared = set(re.findall(r"^(?:int|const char \*)\s*\*?(qb_\w+)\(", hdr, re.M))
+  assert len(declared) >= 30
+  L = _cabi.lib()
+  for name in declared:
+    assert hasattr(L, name), f"{name} declared in qcc_b200.h but not exported"
+  assert declared == set(_cabi.PROTOTYPES), "ctypes prototypes out of sync with the header"
+  assert L.qb_abi_version() == 1
+
+
+def test_no_gpu_means_loud_failure(has_gpu):
+  if has_gpu:
+    pytest.skip("GPU present")
+  with pytest.raises(_cabi.QbError) as e:
+    _cabi.DeviceState(4)
+  assert "CUDA" in str(e.value) or "cuda" in str(e.value) or "device" in str(e.value)
+  psi = np.zeros(4, dtype=np.complex128)
+  g = np.eye(2, dtype=np.complex128).reshape(4) * 1j
+  rc = _cabi.lib().qb_host_apply1(psi.ctypes.data, g.ctypes.data, 2, 0, 128, -1)
+  assert rc < 0
+
+
+def test_argument_errors_do_not_need_a_gpu():
+  L = _cabi.lib()
+  need = ctypes.c_size_t()
+  bad = _cabi.pack_gates([(1 << 3, 3, np.eye(2))])  # control == target
+  assert L.qb_plan_json(6, bad, 1, 12, None, 0, ctypes.byref(need)) == -1
+  assert b"bad bits" in L.qb_last_error()
+  assert L.qb_state_destroy(None) == 0
+
+
+CIRCS = sorted(f for f in os.listdir(GOLDEN) if f.startswith("circ_") and f.endswith(".npz"))
+
+
+@pytest.mark.parametrize("name", CIRCS + ["dense_n8.npz", "dense_n10.npz", "dense_n12.npz", "acceleration_2.npz"])
+@pytest.mark.parametrize("tile_bits", [4, 7, 12])
+def test_plan_reproduces_golden(name, tile_bits):
+  z = load_golden(name)
+  n = int(z["nbits"])
+  if n < 4:
+    pytest.skip("fusion needs >= 4 qubits")
+  gates = xg_to_bits(n, stream_of(z))
+  pj = _cabi.plan_json(n, gates, tile_bits)
+  got = interpret_plan(pj, n, gates, z["psi0"].astype(np.complex128).copy())
+  ref = z["final_xgates"] if "final_xgates" in z.files else z["final_spec"]
+  assert np.abs(got - ref).max() <= 1e-12
+
+
+def _random_bit_gates(n, count, seed):
+  rng = np.random.default_rng(seed)
+  names = list(oracle.GATES)
+  gates = []
+  for _ in range(count):
+    r = rng.random()
+    if r < 0.15:
+      m = oracle.u1(float(rng.uniform(-3, 3)))
+    elif r < 0.25:
+      m = oracle.rotation([0, 0, 1.0], float(rng.uniform(-3, 3)))     # DIAG (rz)
+    elif r < 0.35:
+      m = oracle.rotation([1.0, 0, 0], float(rng.uniform(-3, 3)))
+    else:
+      m = oracle.GATES[names[rng.integers(len(names))]]
+    bits = [int(b) for b in rng.permutation(n)[:3]]
+    nctl = int(rng.choice([0, 0, 1, 1, 2]))
+    mask = 0
+    for b in bits[1:1 + nctl]:
+      mask |= 1 << b
+    gates.append((mask, bits[0], m))
+  return gates
+
+
+@pytest.mark.parametrize("n,tile_bits,seed", [(4, 4, 1), (5, 4, 2), (9, 6, 3), (13, 12, 4), (14, 10, 5), (15, 13, 6)])
+def test_plan_random_circuits(n, tile_bits, seed):
+  gates = _random_bit_gates(n, 160, seed)
+  psi0 = random_state(n, seed)
+  want = run_bits(psi0.copy(), n, gates)
+  pj = _cabi.plan_json(n, gates, tile_bits)
+  got = interpret_plan(pj, n, gates, psi0.copy())
+  assert np.abs(got - want).max() <= 1e-12
+
+
+def _qft_bits(n):
+  """circuit.py:320-326 in index bits: python qubit q == bit n-1-q."""
+  g = []
+  for i in reversed(range(n)):
+    g.append((0, n - 1 - i, oracle.GATES["h"]))
+    for j in reversed(range(i)):
+      g.append((1 << (n - 1 - i), n - 1 - j, oracle.u1(math.pi / 2 ** (i - j))))
+  return g
+
+
+def test_qft30_plans_into_three_passes():
+  """configs[2]: 30 h + 435 cu1 -> 3 HBM sweeps with every ladder fused."""
+  gates = _qft_bits(30)
+  assert len(gates) == 465
+  s = plan_summary(_cabi.plan_json(30, gates, 12))
+  assert s["fused"] == 3 and s["singles"] == 0
+  assert s["ladders"] == 28 and s["ops"] == 59
+  plan = json.loads(_cabi.plan_json(30, gates, 12))
+  assert sum(p["ngates"] for p in plan["passes"]) == 465
+
+
+def test_larose_plan_is_much_shorter_than_the_gate_list():
+  """configs[1] gate stream (larose_benchmark.py:47-54), 28 qubits depth 2."""
+  n = 28
+  gates = []
+  for _ in range(2):
+    for bit in range(n):
+      b = n - 1 - bit
+      gates.append((0, b, oracle.GATES["h"]))
+      gates.append((0, b, oracle.GATES["v"]))
+      if bit > 0:
+        gates.append((1 << b, n - 1, oracle.GATES["x"]))
+  s = plan_summary(_cabi.plan_json(n, gates, 12))
+  assert s["passes"] <= 10 and s["passes"] * 10 < len(gates)
+
+
+def test_round_bank_classes():
+  """QbRound::qmap gives group-index bits 0..2 one tile-local bit of each class (b % 3),
+  which is what makes the swizzled shared-memory accesses of fused.cu conflict free."""
+  gates = _random_bit_gates(14, 200, 9)
+  plan = json.loads(_cabi.plan_json(14, gates, 12))
+  seen = 0
+  for p in plan["passes"]:
+    if p["single_gate"] >= 0:
+      continue
+    for R in p["rounds"]:
+      assert sorted(q % 3 for q in R["qmap"][:3]) == [0, 1, 2]
+      seen += 1
+  assert seen > 5
