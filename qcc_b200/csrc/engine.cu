@@ -92,22 +92,7 @@ struct qb_state {
 
 namespace {
 
-const double kEps = 0.0;  // classification is exact: only literal zeros / ones specialise
-
-// Decide how a 2x2 acts (qb_types.h QbKind).  Exact comparisons on purpose: a matrix
-// that is merely *close* to diagonal must still go through the general butterfly so
-// that results track the reference's arithmetic.
-int classify(const double m[8]) {
-  auto z = [&](int k) { return std::fabs(m[2 * k]) <= kEps && std::fabs(m[2 * k + 1]) <= kEps; };
-  auto one = [&](int k) { return m[2 * k] == 1.0 && m[2 * k + 1] == 0.0; };
-  if (z(1) && z(2)) {
-    if (one(0) && one(3)) return QB_K_NOP;
-    if (one(0)) return QB_K_PHASE;
-    return QB_K_DIAG;
-  }
-  if (z(0) && z(3)) return QB_K_PERM;
-  return QB_K_U;
-}
+int classify(const double m[8]) { return qb::classify_matrix(m); }
 
 double gate_bytes(const qb_state *s, const QbGate &g) {
   // general 32N, controlled-general / 1-bit diagonal 16N, ...
@@ -211,7 +196,7 @@ int run_fused(qb_state *s, const std::vector<QbGate> &gates) {
     const qb::PlannedPass &pp = plan.passes[k];
     if (pp.single_gate >= 0) {
       // planner decided this gate is better off as a plain sweep (e.g. a lone PHASE)
-      QB(run_single(s, gates[size_t(pp.single_gate)]));
+      QB(run_single(s, pp.single));
       s->cnt.gates_applied += uint64_t(pp.ngates - 1);  // no-op gates retired alongside
       continue;
     }

@@ -1,7 +1,12 @@
 // planner.cc -- see planner.h / qb_types.h for the pass format.
 //
-// Pipeline:  gates -> items (plain gate | phase ladder) -> passes -> rounds -> ops.
+// Pipeline:  gates -> merged gates -> items (plain gate | phase ladder) -> passes -> rounds
+//            -> ops.
 //
+//  0. 2x2 pre-multiplication.  A gate is multiplied into an earlier gate with the same
+//     target and controls when everything in between commutes with it trivially (touches
+//     neither its target nor has its target among their bits): h(q); v(q) of
+//     larose_benchmark.py:50-51 becomes one general 2x2.
 //  1. Ladder merge.  Consecutive PHASE gates (they all commute) on <= 2 bits that share
 //     one "pivot" bit are merged into a LADDER item: for every index with the pivot
 //     set, multiply by the product of the partner phases whose bit is set.  This is the
@@ -44,8 +49,63 @@ struct Item {
 
 bool needs_target(int kind) { return kind == QB_K_U || kind == QB_K_PERM || kind == QB_K_SWAP; }
 
+struct Merged {
+  QbGate g;
+  int64_t first_gate;
+  int64_t ngates;
+  double bytes_per_amp;
+};
+
+// --- 0. pre-multiplication of 2x2s on the same (controls, target) -----------------
+void premultiply(const QbGate *gates, int64_t ng, bool enable, std::vector<Merged> *out) {
+  for (int64_t i = 0; i < ng; ++i) {
+    const QbGate &g = gates[i];
+    if (g.kind == QB_K_NOP) {
+      if (!out->empty()) out->back().ngates += 1;
+      else out->push_back(Merged{g, i, 1, 0.0});
+      continue;
+    }
+    const uint64_t gbits = g.ctl_mask | (uint64_t(1) << g.target);
+    bool merged = false;
+    if (enable) {
+      int looked = 0;
+      for (auto it = out->rbegin(); it != out->rend() && looked < 64; ++it, ++looked) {
+        QbGate &e = it->g;
+        if (e.kind == QB_K_NOP) continue;
+        const uint64_t ebits = e.ctl_mask | (uint64_t(1) << e.target);
+        if (e.target == g.target && e.ctl_mask == g.ctl_mask) {
+          // new = g * e  (e acts first)
+          Cplx a[4], b[4], r[4];
+          for (int k = 0; k < 4; ++k) {
+            a[k] = Cplx{g.m[2 * k], g.m[2 * k + 1]};
+            b[k] = Cplx{e.m[2 * k], e.m[2 * k + 1]};
+          }
+          for (int row = 0; row < 2; ++row)
+            for (int col = 0; col < 2; ++col) {
+              Cplx p = cmulh(a[row * 2 + 0], b[0 * 2 + col]);
+              Cplx q = cmulh(a[row * 2 + 1], b[1 * 2 + col]);
+              r[row * 2 + col] = Cplx{p.x + q.x, p.y + q.y};
+            }
+          for (int k = 0; k < 4; ++k) {
+            e.m[2 * k] = r[k].x;
+            e.m[2 * k + 1] = r[k].y;
+          }
+          e.kind = classify_matrix(e.m);
+          it->ngates += 1;
+          it->bytes_per_amp += gate_bytes_per_amp(g);
+          merged = true;
+          break;
+        }
+        // can g move in front of e?  only if neither changes a bit the other looks at
+        if ((gbits >> e.target & 1) || (ebits >> g.target & 1)) break;
+      }
+    }
+    if (!merged) out->push_back(Merged{g, i, 1, gate_bytes_per_amp(g)});
+  }
+}
+
 // --- 1. ladder merge -------------------------------------------------------------
-void build_items(const QbGate *gates, int64_t ng, bool ladders, std::vector<Item> *items) {
+void build_items(const std::vector<Merged> &mg, bool ladders, std::vector<Item> *items) {
   struct Open {
     bool active = false;
     int64_t first = 0, count = 0;
@@ -89,19 +149,22 @@ void build_items(const QbGate *gates, int64_t ng, bool ladders, std::vector<Item
     open = Open();
   };
 
-  for (int64_t i = 0; i < ng; ++i) {
-    const QbGate &g = gates[i];
+  for (size_t mi = 0; mi < mg.size(); ++mi) {
+    const QbGate &g = mg[mi].g;
+    const int64_t i = mg[mi].first_gate;
+    const int64_t cnt = mg[mi].ngates;
+    const double gbytes = mg[mi].bytes_per_amp;
     if (g.kind == QB_K_NOP) {
-      // retire it with whatever item is open / comes next; costs nothing
+      // retire it with whatever item is open / came before; costs nothing
       if (open.active) {
-        open.count += 1;
+        open.count += cnt;
       } else if (!items->empty()) {
-        items->back().ngates += 1;
+        items->back().ngates += cnt;
       } else {
         Item it;
         it.kind = QB_K_NOP;
         it.first_gate = i;
-        it.ngates = 1;
+        it.ngates = cnt;
         it.bytes_per_amp = 0;
         it.g = g;
         items->push_back(it);
@@ -114,15 +177,15 @@ void build_items(const QbGate *gates, int64_t ng, bool ladders, std::vector<Item
       if (open.active && (open.cand & bits)) {
         open.cand &= bits;
         open.parts.push_back({bits, ph});
-        open.count += 1;
-        open.bytes += gate_bytes_per_amp(g);
+        open.count += cnt;
+        open.bytes += gbytes;
         continue;
       }
       close();
       open.active = true;
       open.first = i;
-      open.count = 1;
-      open.bytes = gate_bytes_per_amp(g);
+      open.count = cnt;
+      open.bytes = gbytes;
       open.cand = bits;
       open.parts.push_back({bits, ph});
       open.first_gate = g;
@@ -134,8 +197,8 @@ void build_items(const QbGate *gates, int64_t ng, bool ladders, std::vector<Item
     if (g.kind == QB_K_PERM && g.m[2] == 1.0 && g.m[3] == 0.0 && g.m[4] == 1.0 && g.m[5] == 0.0)
       it.kind = QB_K_SWAP;
     it.first_gate = i;
-    it.ngates = 1;
-    it.bytes_per_amp = gate_bytes_per_amp(g);
+    it.ngates = cnt;
+    it.bytes_per_amp = gbytes;
     it.g = g;
     items->push_back(it);
   }
@@ -294,12 +357,24 @@ void close_round(const TileMap &tm, std::vector<int> &rset, std::vector<PendingO
     if (b >= 0) order.push_back(b);
   for (size_t k = 0; k < order.size(); ++k) r.qmap[k] = order[k];
   r.op_begin = int32_t(pp->ops.size());
-  for (const PendingOp &po : pend) {
+  for (size_t pi = 0; pi < pend.size(); ++pi) {
+    const PendingOp &po = pend[pi];
     const Item &it = *po.it;
     QbOp op{};
     op.kind = it.kind;
     op.tpos = 0;
-    if (it.kind == QB_K_LADDER) {
+    if (it.kind == QB_K_U && it.g.ctl_mask == 0 && pi + 1 < pend.size() &&
+        pend[pi + 1].it->kind == QB_K_LADDER && pend[pi + 1].it->pivot == it.g.target) {
+      // h(q) + the cu1 ladder hanging off q (circuit.py:323-326): one op, y' = (c x + d y) * phase
+      const Item &lad = *pend[pi + 1].it;
+      op.kind = QB_K_ULADDER;
+      int lp = tm.lpos[it.g.target];
+      for (int k = 0; k < nr; ++k)
+        if (r.rbit[k] == lp) op.tpos = k;
+      memcpy(op.m, it.g.m, sizeof op.m);
+      build_ladder_tables(tm, r, lad, (*nladders)++, pp, &op);
+      ++pi;
+    } else if (it.kind == QB_K_LADDER) {
       op.kind = QB_K_LADDER;
       split_pred(tm, r.rbit, nr, uint64_t(1) << it.pivot, uint64_t(1) << it.pivot, &op);
       build_ladder_tables(tm, r, it, (*nladders)++, pp, &op);
@@ -323,6 +398,9 @@ void close_round(const TileMap &tm, std::vector<int> &rset, std::vector<PendingO
         if (r.rbit[k] == lp) op.tpos = k;
       memcpy(op.m, it.g.m, sizeof op.m);
     }
+    if ((op.kind == QB_K_U || op.kind == QB_K_ULADDER || op.kind == QB_K_PERM) && op.m[1] == 0.0 &&
+        op.m[3] == 0.0 && op.m[5] == 0.0 && op.m[7] == 0.0)
+      op.mflags |= QB_MF_REAL;
     pp->ops.push_back(op);
   }
   r.op_end = int32_t(pp->ops.size());
@@ -350,6 +428,7 @@ void emit_pass(int nbits, int K, const std::vector<const Item *> &items, const s
     for (const Item *it : items) {
       PlannedPass pp;
       pp.single_gate = it->first_gate;
+      pp.single = it->g;
       pp.ngates = it->ngates;
       pp.bytes_algorithmic_per_amp = it->bytes_per_amp;
       out->passes.push_back(std::move(pp));
@@ -391,6 +470,18 @@ size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
 
 }  // namespace
 
+int classify_matrix(const double m[8]) {
+  auto z = [&](int k) { return m[2 * k] == 0.0 && m[2 * k + 1] == 0.0; };
+  auto one = [&](int k) { return m[2 * k] == 1.0 && m[2 * k + 1] == 0.0; };
+  if (z(1) && z(2)) {
+    if (one(0) && one(3)) return QB_K_NOP;
+    if (one(0)) return QB_K_PHASE;
+    return QB_K_DIAG;
+  }
+  if (z(0) && z(3)) return QB_K_PERM;
+  return QB_K_U;
+}
+
 double gate_bytes_per_amp(const QbGate &g) {
   if (g.kind == QB_K_NOP) return 0.0;
   int nb = __builtin_popcountll(g.ctl_mask);
@@ -404,23 +495,45 @@ void plan_gates(int nbits, const QbGate *gates, int64_t ngates, int tile_bits, P
   K = std::min(K, nbits);
   const int cap = K - std::min(QB_TILE_LOW, K);
   static const bool no_ladder = getenv("QCC_B200_NO_LADDER") != nullptr;
+  static const bool no_premul = getenv("QCC_B200_NO_PREMUL") != nullptr;
+  std::vector<Merged> merged;
+  premultiply(gates, ngates, !no_premul, &merged);
   std::vector<Item> items;
-  build_items(gates, ngates, !no_ladder, &items);
+  build_items(merged, !no_ladder, &items);
   std::vector<const Item *> cur;
   std::vector<int> targets;
-  size_t nladders = 0;
+  int nops = 0;       // ops this pass will hold (staged in shared memory by the kernel)
+  int nrounds_ub = 1; // upper bound on its rounds: a new round at most every 3 new targets
+  std::vector<int> round_targets;
   for (const Item &it : items) {
     bool new_target = needs_target(it.kind) && it.g.target >= QB_TILE_LOW &&
                       std::find(targets.begin(), targets.end(), it.g.target) == targets.end();
-    bool too_many_ladders = it.kind == QB_K_LADDER && nladders >= 64;
-    if ((new_target && int(targets.size()) == cap) || too_many_ladders) {
+    int cost = it.kind == QB_K_NOP ? 0 : (it.kind == QB_K_DIAG ? 2 : 1);
+    bool new_round = false;
+    if (needs_target(it.kind) &&
+        std::find(round_targets.begin(), round_targets.end(), it.g.target) == round_targets.end()) {
+      if (int(round_targets.size()) == QB_ROUND_BITS) new_round = true;
+    }
+    if ((new_target && int(targets.size()) == cap) || nops + cost > QB_MAX_PASS_OPS ||
+        (new_round && nrounds_ub == QB_MAX_PASS_ROUNDS)) {
       emit_pass(nbits, K, cur, targets, out);
       cur.clear();
       targets.clear();
-      nladders = 0;
+      round_targets.clear();
+      nops = 0;
+      nrounds_ub = 1;
+      new_round = false;
+      new_target = needs_target(it.kind) && it.g.target >= QB_TILE_LOW;
     }
+    if (new_round) {
+      round_targets.clear();
+      nrounds_ub += 1;
+    }
+    if (needs_target(it.kind) &&
+        std::find(round_targets.begin(), round_targets.end(), it.g.target) == round_targets.end())
+      round_targets.push_back(it.g.target);
     if (new_target) targets.push_back(it.g.target);
-    if (it.kind == QB_K_LADDER) nladders += 1;
+    nops += cost;
     cur.push_back(&it);
   }
   emit_pass(nbits, K, cur, targets, out);
@@ -460,9 +573,15 @@ std::string Plan::to_json() const {
     if (!firstp) s += ",";
     firstp = false;
     if (p.single_gate >= 0) {
-      snprintf(buf, sizeof buf, "{\"single_gate\":%lld,\"ngates\":%lld}", (long long)p.single_gate,
-               (long long)p.ngates);
+      snprintf(buf, sizeof buf, "{\"single_gate\":%lld,\"ngates\":%lld,\"ctl_mask\":%llu,\"target\":%d,\"m\":[",
+               (long long)p.single_gate, (long long)p.ngates, (unsigned long long)p.single.ctl_mask,
+               p.single.target);
       s += buf;
+      for (int k = 0; k < 8; ++k) {
+        snprintf(buf, sizeof buf, "%s%.17g", k ? "," : "", p.single.m[k]);
+        s += buf;
+      }
+      s += "]}";
       continue;
     }
     snprintf(buf, sizeof buf, "{\"single_gate\":-1,\"ngates\":%lld,\"K\":%d,\"tile_bits\":[", (long long)p.ngates,

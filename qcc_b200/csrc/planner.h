@@ -31,7 +31,8 @@ struct PlannedPass {
   // filled by Plan::layout(): byte offsets inside the serialized blob
   size_t ops_off = 0, rounds_off = 0, tables_off = 0, outbits_off = 0;
   int noutbits = 0;
-  int64_t single_gate = -1;  // >= 0: run gates[single_gate] with the plain sweep kernel instead
+  int64_t single_gate = -1;  // >= 0: run `single` with the plain sweep kernel instead
+  QbGate single{};           // the (possibly pre-multiplied) gate of a single-gate pass
   int64_t ngates = 0;        // gate records this pass retires (including no-ops)
   double bytes_algorithmic_per_amp = 0.0;
 };
@@ -42,6 +43,10 @@ struct Plan {
   void serialize(char *dst) const;   // after blob_bytes()
   std::string to_json() const;       // for the CPU tests (tests/ interprets it with numpy)
 };
+
+// How a 2x2 acts (QbKind): exact comparisons on purpose -- a matrix that is merely close to
+// diagonal still goes through the general butterfly so results track the reference.
+int classify_matrix(const double m[8]);
 
 // SURVEY.md 8(d) algorithmic bytes per amplitude of the full vector for one gate.
 double gate_bytes_per_amp(const QbGate &g);

@@ -20,6 +20,7 @@ enum QbKind : int32_t {
   QB_K_LADDER = 4,  // fused run of PHASE gates sharing one pivot bit (QFT ladder)
   QB_K_NOP = 5,
   QB_K_SWAP = 6,    // PERM with b = c = 1: moves amplitudes, no arithmetic
+  QB_K_ULADDER = 7, // uncontrolled U on the pivot immediately followed by that pivot's LADDER
 };
 
 // A gate in physical index-bit terms, as queued by the engine.
@@ -57,6 +58,9 @@ struct QbGate {
 #define QB_MAX_TILE_BITS 13  // 2^13 * 16 B = 128 KiB
 #define QB_ROUND_BITS 3      // 8 amplitudes = 16 doubles in registers per thread
 #define QB_LADDER_CHUNK 6    // ladder lookup tables are indexed by 6 tile-local bits
+#define QB_MAX_PASS_OPS 48   // ops of one pass are staged in shared memory (48 * 128 B)
+#define QB_MAX_PASS_ROUNDS 16
+#define QB_MF_REAL 1         // all four entries of m are real: 8 instead of 20 flops per pair
 
 struct alignas(16) QbOp {   // 128 bytes, read by the kernel as 16-byte pieces
   int32_t kind;      // QbKind (never DIAG/NOP: the planner lowers those)
@@ -69,7 +73,8 @@ struct alignas(16) QbOp {   // 128 bytes, read by the kernel as 16-byte pieces
   double m[8];       // U/PERM: a b c d; PHASE: p in m[0..1]
   int32_t nout;      // LADDER: number of partner bits outside the tile
   int32_t out_off;   // LADDER: first entry in the pass's outside-bit array
-  int32_t pad0, pad1;
+  int32_t mflags;    // QB_MF_* properties of m
+  int32_t pad1;
 };
 
 struct QbRound {

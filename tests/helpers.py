@@ -16,7 +16,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 from oracle import oracle  # noqa: E402
 
-K_U, K_PHASE, K_DIAG, K_PERM, K_LADDER, K_NOP, K_SWAP = range(7)
+K_U, K_PHASE, K_DIAG, K_PERM, K_LADDER, K_NOP, K_SWAP, K_ULADDER = range(8)
 
 
 def load_golden(name):
@@ -86,8 +86,10 @@ def interpret_plan(plan_json: str, n: int, gates, psi: np.ndarray) -> np.ndarray
   for p in plan["passes"]:
     retired += p["ngates"]
     if p["single_gate"] >= 0:
-      mask, t, m = gates[p["single_gate"]]
-      apply_masked(psi, n, mask, t, m)
+      # the plan carries the (possibly pre-multiplied) gate itself
+      m = np.array([complex(p["m"][2 * i], p["m"][2 * i + 1]) for i in range(4)])
+      if not (m[0] == 1 and m[3] == 1 and m[1] == 0 and m[2] == 0):
+        apply_masked(psi, n, p["ctl_mask"], p["target"], m)
       continue
     K = p["K"]
     tb = p["tile_bits"]
@@ -147,7 +149,22 @@ def interpret_plan(plan_json: str, n: int, gates, psi: np.ndarray) -> np.ndarray
           for e in range(8):
             if (e & op["rmask"]) == op["rwant"]:
               A[:, :, e] = np.where(ok, m[0] * A[:, :, e], A[:, :, e])
-        elif kind == K_LADDER:
+        elif kind in (K_LADDER, K_ULADDER):
+          if kind == K_ULADDER:
+            # uncontrolled butterfly on the pivot first, then the ladder on the pivot-set half
+            tp = op["tpos"]
+            assert op["rmask"] == 0 and op["lmask"] == 0 and op["gmask"] == 0
+            for e in range(8):
+              if e & (1 << tp):
+                continue
+              e1 = e | (1 << tp)
+              x = A[:, :, e].copy()
+              y = A[:, :, e1].copy()
+              A[:, :, e] = m[0] * x + m[1] * y
+              A[:, :, e1] = m[2] * x + m[3] * y
+            lad_rmask, lad_rwant = 1 << tp, 1 << tp
+          else:
+            lad_rmask, lad_rwant = op["rmask"], op["rwant"]
           t0 = op["table_off"]
           cbase = t0 + 64 + (1 << hi_bits) + 8
           pout = np.full(ntiles, tables[cbase], dtype=np.complex128)
@@ -159,7 +176,7 @@ def interpret_plan(plan_json: str, n: int, gates, psi: np.ndarray) -> np.ndarray
             c = c * tables[t0 + 64 + (jb >> 6)][None, :]
           F = tables[t0 + 64 + (1 << hi_bits): t0 + 64 + (1 << hi_bits) + 8]
           for e in range(8):
-            if (e & op["rmask"]) == op["rwant"]:
+            if (e & lad_rmask) == lad_rwant:
               A[:, :, e] = np.where(ok, c * F[e] * A[:, :, e], A[:, :, e])
         else:
           raise AssertionError(f"unexpected op kind {kind}")
@@ -178,5 +195,5 @@ def plan_summary(plan_json: str):
       "singles": len(plan["passes"]) - len(fused),
       "rounds": sum(len(p["rounds"]) for p in fused),
       "ops": sum(len(p["ops"]) for p in fused),
-      "ladders": sum(1 for p in fused for o in p["ops"] if o["kind"] == K_LADDER),
+      "ladders": sum(1 for p in fused for o in p["ops"] if o["kind"] in (K_LADDER, K_ULADDER)),
   }

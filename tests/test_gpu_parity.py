@@ -201,7 +201,7 @@ def test_fill_random_is_deterministic_and_normalised():
     a.fill_random(7)
     b.fill_random(7)
     x, y = a.copy_out(), b.copy_out()
-    assert np.array_equal(x, y)
+    assert np.abs(x - y).max() < 1e-15  # normalisation uses an atomic (order-dependent) sum
     assert abs(np.linalg.norm(x) - 1.0) < 1e-12
     b.fill_random(8)
-    assert not np.array_equal(x, b.copy_out())
+    assert np.abs(x - b.copy_out()).max() > 1e-4

@@ -114,7 +114,7 @@ def test_qft30_plans_into_three_passes():
   assert len(gates) == 465
   s = plan_summary(_cabi.plan_json(30, gates, 12))
   assert s["fused"] == 3 and s["singles"] == 0
-  assert s["ladders"] == 28 and s["ops"] == 59
+  assert s["ladders"] == 28 and s["ops"] == 31  # 28 h+ladder, h+cu1, h, (last cu1 is a PHASE)
   plan = json.loads(_cabi.plan_json(30, gates, 12))
   assert sum(p["ngates"] for p in plan["passes"]) == 465
 
