@@ -206,6 +206,8 @@ int run_fused(qb_state *s, const std::vector<QbGate> &gates) {
     dp.rounds = reinterpret_cast<const QbRound *>(dbase + pp.rounds_off);
     dp.tables = pp.desc.ntable ? reinterpret_cast<const double2 *>(dbase + pp.tables_off) : nullptr;
     dp.outbits = pp.noutbits ? reinterpret_cast<const int32_t *>(dbase + pp.outbits_off) : nullptr;
+    dp.outph = pp.outph.empty() ? nullptr : reinterpret_cast<const double2 *>(dbase + pp.outph_off);
+    dp.jbtab = reinterpret_cast<const uint32_t *>(dbase + pp.jbtab_off);
     double sweep = double(s->len) * 32.0;
     {
       ProfScope ps(s, QB_KCLASS_FUSED, sweep);

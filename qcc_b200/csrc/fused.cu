@@ -1,24 +1,27 @@
 // fused.cu -- tile-resident fused pass for sm_100a: many gates per HBM sweep.
 //
-// One CTA = one TILE of 2^K amplitudes (K <= 13, default 12 = 64 KiB), see qb_types.h.
+// PERSISTENT kernel: one CTA of 512 threads per SM walks over TILES of 2^K amplitudes
+// (K <= 13, default 12 = 64 KiB; see qb_types.h) with a two-deep shared-memory ring: while
+// tile i is being computed on, tile i+1 is already streaming in through cp.async (LDGSTS,
+// 16 B per request, L2-only), so HBM latency is hidden behind the fp64 work instead of being
+// paid twice per tile.  (With one-shot CTAs the resident CTAs of an SM ran in lockstep --
+// all loading, then all computing -- and the phases simply added up: 9.4 + 3.7 + 6 ms.)
 //
 //   0. STAGE  the pass's op and round descriptors (<= 48 x 128 B) are copied into shared
 //             memory once, so the per-op decode in the hot loop is LDS broadcasts, not
 //             dependent global loads.
-//   1. LOAD   the tile is gathered from HBM into shared memory: thread t of 256 takes
-//             tile-local indices t, t+256, ...; 8 consecutive lanes read one 128-byte
-//             run, and the planner pads the tile with the lowest free index bits so the
-//             runs of one CTA are mostly adjacent (a tile whose bits are 0..K-1 is one
-//             contiguous 64 KiB block).  8 LDG.128 are in flight per thread before the
-//             first STS; the CTAs resident on an SM are in different phases, so one
-//             CTA's arithmetic overlaps the others' loads and stores.
-//   2. ROUNDS each thread owns groups of 8 amplitudes that differ only in the round's 3
-//             tile-local bits, pulls NG groups (16 or 32 fp64 registers) out of shared
-//             memory, runs every op of the round on registers -- each op is decoded once
-//             and applied to all NG groups -- and writes them back: ONE shared-memory
-//             round trip for any number of gates on those 3 qubits, plus every diagonal
-//             gate queued in between.
-//   3. STORE  the mirror image of LOAD with streaming stores.
+//   1. LOAD   the tile is gathered from HBM straight into (swizzled) shared memory with
+//             cp.async: thread t of 512 takes tile-local indices t, t+512, ...; 8
+//             consecutive lanes fetch one 128-byte run, and the planner pads the tile with
+//             the lowest free index bits so the runs of one tile are mostly adjacent (a
+//             tile whose bits are 0..K-1 is one contiguous 64 KiB block).  No registers are
+//             staged and nobody waits: the copy of the NEXT tile is issued before the
+//             rounds of the current one start.
+//   2. ROUNDS each thread owns one group of 8 amplitudes that differ only in the round's 3
+//             tile-local bits, pulls it into 16 fp64 registers, runs every op of the round
+//             on registers and writes it back: ONE shared-memory round trip for any number
+//             of gates on those 3 qubits, plus every diagonal gate queued in between.
+//   3. STORE  shared -> HBM with streaming 128-bit stores (fire and forget).
 //
 // Shared-memory layout: the tile is stored XOR-swizzled, slot(j) = j ^ (fold(j >> 3) & 7)
 // with fold(x) = x ^ x>>3 ^ x>>6 ^ x>>9, in 16-byte units.  The 16-byte bank group of j is
@@ -56,7 +59,13 @@ struct FusedParams {
   const QbOp *ops;
   const QbRound *rounds;
   const double2 *tables;
+  const double2 *outph;
   const int32_t *outbits;
+  const uint32_t *jbtab;
+  int debug;  // bit 0: skip the op loop, bit 1: skip the rounds (timing experiments only)
+  int nbuf;   // tile buffers in the shared-memory ring (1 or 2)
+  int stagger_ns;  // first-wave start offset between the CTA slots of an SM (see launch_fused_pass)
+  int sms;
 };
 
 __device__ __forceinline__ uint32_t swz(uint32_t j) {
@@ -169,32 +178,41 @@ __device__ __forceinline__ void uladder(double2 (&a)[8], const Mat &m, double2 c
     else { CALL2; }                             \
   } while (0)
 
-template <int NG>
-__global__ void __launch_bounds__(kFThreads, NG == 1 ? 3 : 2)
-k_fused_pass(const __grid_constant__ FusedParams P) {
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  const uint32_t sa = uint32_t(__cvta_generic_to_shared(smem));
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+__global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_constant__ FusedParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int K = P.desc.K;
   const uint32_t tileN = 1u << K;
-  double2 *tile = reinterpret_cast<double2 *>(smem_raw);
-  double2 *s_pout = tile + tileN;                                       // kMaxLadders
+  const int nbuf = P.nbuf;
+  double2 *tiles = reinterpret_cast<double2 *>(smem_raw);               // nbuf x 2^K
+  double2 *s_pout = tiles + size_t(nbuf) * tileN;                       // kMaxLadders
   QbOp *s_ops = reinterpret_cast<QbOp *>(s_pout + kMaxLadders);         // QB_MAX_PASS_OPS
-  QbRound *s_rounds = reinterpret_cast<QbRound *>(s_ops + QB_MAX_PASS_OPS);  // QB_MAX_PASS_ROUNDS
+  double2 *s_tab = reinterpret_cast<double2 *>(s_ops + QB_MAX_PASS_OPS);  // ntable
+  QbRound *s_rounds = reinterpret_cast<QbRound *>(s_tab + P.desc.ntable);  // QB_MAX_PASS_ROUNDS
   uint32_t *hi_off = reinterpret_cast<uint32_t *>(s_rounds + QB_MAX_PASS_ROUNDS);  // 2^(K-3)
   const uint32_t tid = threadIdx.x;
+  double2 *__restrict__ psi = P.psi;
 
-  // ---- tile base: scatter blockIdx.x over the non-tile index bits -----------------
-  uint64_t base = 0;
-  {
-    uint64_t t = blockIdx.x;
-    const uint64_t tmask = P.desc.tile_mask;
-    for (int b = 0; b < P.nbits; ++b) {
-      if (!((tmask >> b) & 1)) {
-        base |= (t & 1) << b;
-        t >>= 1;
-      }
-    }
+  // De-phase the CTAs that share an SM.  All CTAs do identical work, so the ones launched
+  // together stay in lockstep for the whole kernel -- every resident CTA loading, then every
+  // one computing -- and HBM, shared memory and the fp64 pipe are used one after the other
+  // instead of concurrently.  Delaying the 2nd / 3rd CTA slot of each SM once, in the first
+  // wave only, keeps the slots a third of a tile apart from then on.
+  if (P.stagger_ns && blockIdx.x < 3u * uint32_t(P.sms)) {
+    const uint32_t slot = blockIdx.x / uint32_t(P.sms);
+    for (uint32_t k = 0; k < slot; ++k) __nanosleep(uint32_t(P.stagger_ns));
   }
-  // ---- STAGE: descriptors -> shared memory ------------------------------------------
+
+  // ---- STAGE (once per CTA): descriptors, ladder tables, run offsets -> shared memory -----
   {
     const int4 *src = reinterpret_cast<const int4 *>(P.ops);
     int4 *dst = reinterpret_cast<int4 *>(s_ops);
@@ -204,223 +222,192 @@ k_fused_pass(const __grid_constant__ FusedParams P) {
     int32_t *rd = reinterpret_cast<int32_t *>(s_rounds);
     const int n4 = P.desc.nrounds * int(sizeof(QbRound) / 4);
     for (int i = tid; i < n4; i += kFThreads) rd[i] = __ldg(rs + i);
+    for (int i = tid; i < P.desc.ntable; i += kFThreads) s_tab[i] = __ldg(P.tables + i);
+    // offset of every 8-amplitude run of a tile, in units of 8 amplitudes
+    for (uint32_t h = tid; h < (tileN >> 3); h += kFThreads) {
+      uint64_t off = 0;
+      for (int k = 3; k < K; ++k) off |= uint64_t((h >> (k - 3)) & 1u) << P.desc.tile_bits[k];
+      hi_off[h] = uint32_t(off >> 3);
+    }
   }
-  // ---- offset of every 8-amplitude run of the tile (in units of 8 amplitudes) ------
-  for (uint32_t h = tid; h < (tileN >> 3); h += kFThreads) {
-    uint64_t off = 0;
-    for (int k = 3; k < K; ++k) off |= uint64_t((h >> (k - 3)) & 1u) << P.desc.tile_bits[k];
-    hi_off[h] = uint32_t(off >> 3);
-  }
-  // ---- per-tile constants of the phase ladders ---------------------------------------
+  __syncthreads();
+
+  const uint32_t ntiles = 1u << (P.nbits - K);
+  const uint64_t tmask = P.desc.tile_mask;
+  // tile number -> index bits outside the tile
+  auto tile_base = [&](uint32_t t) {
+    uint64_t b = 0, tt = t;
+    for (int bit = 0; bit < P.nbits; ++bit) {
+      if (!((tmask >> bit) & 1)) {
+        b |= (tt & 1) << bit;
+        tt >>= 1;
+      }
+    }
+    return b;
+  };
+  auto issue_load = [&](uint32_t t, double2 *buf) {
+    const uint64_t b = tile_base(t);
+    for (uint32_t j = tid; j < tileN; j += kFThreads)
+      cp_async16(buf + swz(j), psi + (b | (uint64_t(hi_off[j >> 3]) << 3) | (j & 7u)));
+    cp_async_commit();
+  };
+
   const int hi_bits = K > QB_LADDER_CHUNK ? K - QB_LADDER_CHUNK : 0;
-  for (int oi = tid; oi < P.desc.nops; oi += kFThreads) {
-    const QbOp *op = P.ops + oi;
-    if (op->kind == QB_K_LADDER || op->kind == QB_K_ULADDER) {
-      const double2 *tb = P.tables + op->table_off + 64 + (1 << hi_bits) + 8;
-      double2 c = tb[0];
-      const int32_t *ob = P.outbits + op->out_off;
-      for (int k = 0; k < op->nout; ++k)
-        if ((base >> ob[k]) & 1) c = cmul(c, tb[1 + k]);
-      s_pout[op->flags] = c;
-    }
-  }
-  __syncthreads();
-
-  // ---- LOAD ----------------------------------------------------------------------------
-  double2 *__restrict__ psi = P.psi;
-  for (uint32_t s0 = 0; s0 < tileN; s0 += kFThreads * 8) {
-    double2 v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      uint32_t j = s0 + u * kFThreads + tid;
-      if (j < tileN) v[u] = __ldcs(psi + (base | (uint64_t(hi_off[j >> 3]) << 3) | (j & 7u)));
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      uint32_t j = s0 + u * kFThreads + tid;
-      if (j < tileN) tile[swz(j)] = v[u];
-    }
-  }
-  __syncthreads();
-
-  // ---- ROUNDS --------------------------------------------------------------------------
   const uint32_t ngroups = tileN >> 3;
-  for (int r = 0; r < P.desc.nrounds; ++r) {
-    const QbRound *R = s_rounds + r;
-    const uint32_t d0 = swz(1u << R->rbit[0]);
-    const uint32_t d1 = swz(1u << R->rbit[1]);
-    const uint32_t d2 = swz(1u << R->rbit[2]);
-    const int ob = R->op_begin, oe = R->op_end;
-    for (uint32_t q0 = tid; q0 < ngroups; q0 += kFThreads * NG) {
-      uint32_t jb[NG], pb[NG];
-      bool valid[NG];
-      double2 a[NG][8];
+  int cur = 0;
+  if (blockIdx.x < ntiles) issue_load(blockIdx.x, tiles);
+  for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const uint32_t tn = t + gridDim.x;
+    const bool more = tn < ntiles;
+    double2 *tile = tiles + size_t(cur) * tileN;
+    if (nbuf == 2 && more) issue_load(tn, tiles + size_t(cur ^ 1) * tileN);  // prefetch
+    const uint64_t base = tile_base(t);
+    // per-tile constants of the phase ladders (overlaps the wait for the tile's data): one
+    // warp per ladder, lane k owns outside bit k, product by butterfly shuffles
+    for (int oi = int(tid >> 5); oi < P.desc.nops; oi += kFThreads / 32) {
+      const QbOp *op = s_ops + oi;
+      if (op->kind == QB_K_LADDER || op->kind == QB_K_ULADDER) {
+        const int lane = int(tid & 31u);
+        const double2 *ph = P.outph + op->outph_off;
+        double2 c = make_double2(1.0, 0.0);
+        if (lane < op->nout && ((base >> __ldg(P.outbits + op->out_off + lane)) & 1)) c = __ldg(ph + 1 + lane);
+        if (lane == 0) c = cmul(c, __ldg(ph));
 #pragma unroll
-      for (int g = 0; g < NG; ++g) {
-        const uint32_t q = q0 + g * kFThreads;
-        valid[g] = q < ngroups;
-        uint32_t j = 0;
-        for (int k = 0; k < K - 3; ++k) j |= ((q >> k) & 1u) << R->qmap[k];
-        jb[g] = j;
-        pb[g] = swz(j);
-        if (valid[g]) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e)
-            a[g][e] = tile[pb[g] ^ ((e & 1) ? d0 : 0u) ^ ((e & 2) ? d1 : 0u) ^ ((e & 4) ? d2 : 0u)];
+        for (int o = 16; o > 0; o >>= 1) {
+          double2 d;
+          d.x = __shfl_xor_sync(0xffffffffu, c.x, o);
+          d.y = __shfl_xor_sync(0xffffffffu, c.y, o);
+          c = cmul(c, d);
         }
-      }
-
-      for (int oi = ob; oi < oe; ++oi) {
-        const QbOp *op = s_ops + oi;
-        const int4 h0 = *reinterpret_cast<const int4 *>(op);            // kind tpos lmask lwant
-        const int4 h1 = *(reinterpret_cast<const int4 *>(op) + 1);      // rmask rwant table_off flags
-        const ulonglong2 h2 = *(reinterpret_cast<const ulonglong2 *>(op) + 2);  // gmask gwant
-        if ((base & h2.x) != h2.y) continue;                            // uniform per CTA
-        const int kind = h0.x, tp = h0.y;
-        const uint32_t lmask = uint32_t(h0.z), lwant = uint32_t(h0.w);
-        const uint32_t rmask = uint32_t(h1.x), rwant = uint32_t(h1.y);
-        bool ok[NG];
-#pragma unroll
-        for (int g = 0; g < NG; ++g) ok[g] = valid[g] && ((jb[g] & lmask) == lwant);
-        const double2 *mp = reinterpret_cast<const double2 *>(op->m);
-        switch (kind) {
-          case QB_K_U: {
-            Mat m{mp[0], mp[1], mp[2], mp[3]};
-            if (rmask == 0) {
-              if (op->mflags & QB_MF_REAL) {
-#pragma unroll
-                for (int g = 0; g < NG; ++g)
-                  if (ok[g])
-                    QB_DISPATCH_TP(tp, (bfly_all<0, true>(a[g], m)), (bfly_all<1, true>(a[g], m)),
-                                   (bfly_all<2, true>(a[g], m)));
-              } else {
-#pragma unroll
-                for (int g = 0; g < NG; ++g)
-                  if (ok[g])
-                    QB_DISPATCH_TP(tp, (bfly_all<0, false>(a[g], m)), (bfly_all<1, false>(a[g], m)),
-                                   (bfly_all<2, false>(a[g], m)));
-              }
-            } else {
-#pragma unroll
-              for (int g = 0; g < NG; ++g)
-                if (ok[g])
-                  QB_DISPATCH_TP(tp, (bfly_masked<0>(a[g], m, rmask, rwant)), (bfly_masked<1>(a[g], m, rmask, rwant)),
-                                 (bfly_masked<2>(a[g], m, rmask, rwant)));
-            }
-            break;
-          }
-          case QB_K_ULADDER: {
-            Mat m{mp[0], mp[1], mp[2], mp[3]};
-            const double2 *tb = P.tables + h1.z;
-            const double2 *F = tb + 64 + (1 << hi_bits);
-            const double2 cp = s_pout[h1.w];
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {
-              if (!ok[g]) continue;
-              double2 c = cmul(cp, __ldg(tb + (jb[g] & 63u)));
-              if (hi_bits) c = cmul(c, __ldg(tb + 64 + (jb[g] >> QB_LADDER_CHUNK)));
-              if (op->mflags & QB_MF_REAL)
-                QB_DISPATCH_TP(tp, (uladder<0, true>(a[g], m, c, F)), (uladder<1, true>(a[g], m, c, F)),
-                               (uladder<2, true>(a[g], m, c, F)));
-              else
-                QB_DISPATCH_TP(tp, (uladder<0, false>(a[g], m, c, F)), (uladder<1, false>(a[g], m, c, F)),
-                               (uladder<2, false>(a[g], m, c, F)));
-            }
-            break;
-          }
-          case QB_K_PERM: {
-            const double2 mb = mp[1], mc = mp[2];
-#pragma unroll
-            for (int g = 0; g < NG; ++g)
-              if (ok[g])
-                QB_DISPATCH_TP(tp, (perm_masked<0>(a[g], mb, mc, rmask, rwant)),
-                               (perm_masked<1>(a[g], mb, mc, rmask, rwant)),
-                               (perm_masked<2>(a[g], mb, mc, rmask, rwant)));
-            break;
-          }
-          case QB_K_SWAP: {
-#pragma unroll
-            for (int g = 0; g < NG; ++g)
-              if (ok[g])
-                QB_DISPATCH_TP(tp, (swap_masked<0>(a[g], rmask, rwant)), (swap_masked<1>(a[g], rmask, rwant)),
-                               (swap_masked<2>(a[g], rmask, rwant)));
-            break;
-          }
-          case QB_K_PHASE: {
-            const double2 ph = mp[0];
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {
-              if (!ok[g]) continue;
-#pragma unroll
-              for (int e = 0; e < 8; ++e)
-                if ((uint32_t(e) & rmask) == rwant) a[g][e] = cmul(ph, a[g][e]);
-            }
-            break;
-          }
-          case QB_K_LADDER: {
-            const double2 *tb = P.tables + h1.z;
-            const double2 *F = tb + 64 + (1 << hi_bits);
-            const double2 cp = s_pout[h1.w];
-#pragma unroll
-            for (int g = 0; g < NG; ++g) {
-              if (!ok[g]) continue;
-              double2 c = cmul(cp, __ldg(tb + (jb[g] & 63u)));
-              if (hi_bits) c = cmul(c, __ldg(tb + 64 + (jb[g] >> QB_LADDER_CHUNK)));
-#pragma unroll
-              for (int e = 0; e < 8; ++e)
-                if ((uint32_t(e) & rmask) == rwant) a[g][e] = cmul(cmul(c, __ldg(F + e)), a[g][e]);
-            }
-            break;
-          }
-          default:
-            break;
-        }
-      }
-#pragma unroll
-      for (int g = 0; g < NG; ++g) {
-        if (valid[g]) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e)
-            tile[pb[g] ^ ((e & 1) ? d0 : 0u) ^ ((e & 2) ? d1 : 0u) ^ ((e & 4) ? d2 : 0u)] = a[g][e];
-        }
+        if (lane == 0) s_pout[op->flags] = c;
       }
     }
+    if (nbuf == 2 && more) cp_async_wait<1>();
+    else cp_async_wait<0>();
     __syncthreads();
-  }
 
-  // ---- STORE ---------------------------------------------------------------------------
-  for (uint32_t s0 = 0; s0 < tileN; s0 += kFThreads * 8) {
+    // ---- ROUNDS ------------------------------------------------------------------------
+    for (int r = 0; r < ((P.debug & 2) ? 0 : P.desc.nrounds); ++r) {
+      const QbRound *R = s_rounds + r;
+      const uint32_t d0 = swz(1u << R->rbit[0]);
+      const uint32_t d1 = swz(1u << R->rbit[1]);
+      const uint32_t d2 = swz(1u << R->rbit[2]);
+      const int ob = R->op_begin, oe = (P.debug & 1) ? R->op_begin : R->op_end;
+      const uint32_t *jbt = P.jbtab + (size_t(r) << P.desc.ngroups_log2);
+      for (uint32_t q = tid; q < ngroups; q += kFThreads) {
+        const uint32_t w = __ldg(jbt + q);
+        const uint32_t jb = w & 0xffffu, pb = w >> 16;
+        double2 a[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      uint32_t j = s0 + u * kFThreads + tid;
-      if (j < tileN) __stcs(psi + (base | (uint64_t(hi_off[j >> 3]) << 3) | (j & 7u)), tile[swz(j)]);
+        for (int e = 0; e < 8; ++e)
+          a[e] = tile[pb ^ ((e & 1) ? d0 : 0u) ^ ((e & 2) ? d1 : 0u) ^ ((e & 4) ? d2 : 0u)];
+
+#pragma unroll 1
+        for (int oi = ob; oi < oe; ++oi) {
+          const QbOp *op = s_ops + oi;
+          const int4 h0 = *reinterpret_cast<const int4 *>(op);            // kind tpos lmask lwant
+          const int4 h1 = *(reinterpret_cast<const int4 *>(op) + 1);      // rmask rwant table_off flags
+          const ulonglong2 h2 = *(reinterpret_cast<const ulonglong2 *>(op) + 2);  // gmask gwant
+          if ((base & h2.x) != h2.y) continue;                            // uniform per tile
+          const int kind = h0.x, tp = h0.y;
+          const uint32_t rmask = uint32_t(h1.x), rwant = uint32_t(h1.y);
+          const double2 *mp = reinterpret_cast<const double2 *>(op->m);
+          if (kind == QB_K_ULADDER) {  // uncontrolled by construction
+            const double2 *tb = s_tab + h1.z;
+            const double2 *F = tb + 64 + (1 << hi_bits);
+            double2 c = cmul(s_pout[h1.w], tb[jb & 63u]);
+            if (hi_bits) c = cmul(c, tb[64 + (jb >> QB_LADDER_CHUNK)]);
+            const Mat m{mp[0], mp[1], mp[2], mp[3]};
+            if (op->mflags & QB_MF_REAL)
+              QB_DISPATCH_TP(tp, (uladder<0, true>(a, m, c, F)), (uladder<1, true>(a, m, c, F)),
+                             (uladder<2, true>(a, m, c, F)));
+            else
+              QB_DISPATCH_TP(tp, (uladder<0, false>(a, m, c, F)), (uladder<1, false>(a, m, c, F)),
+                             (uladder<2, false>(a, m, c, F)));
+            continue;
+          }
+          if ((jb & uint32_t(h0.z)) != uint32_t(h0.w)) continue;         // per group
+          switch (kind) {
+            case QB_K_U: {
+              const Mat m{mp[0], mp[1], mp[2], mp[3]};
+              if (rmask == 0) {
+                if (op->mflags & QB_MF_REAL)
+                  QB_DISPATCH_TP(tp, (bfly_all<0, true>(a, m)), (bfly_all<1, true>(a, m)), (bfly_all<2, true>(a, m)));
+                else
+                  QB_DISPATCH_TP(tp, (bfly_all<0, false>(a, m)), (bfly_all<1, false>(a, m)),
+                                 (bfly_all<2, false>(a, m)));
+              } else {
+                QB_DISPATCH_TP(tp, (bfly_masked<0>(a, m, rmask, rwant)), (bfly_masked<1>(a, m, rmask, rwant)),
+                               (bfly_masked<2>(a, m, rmask, rwant)));
+              }
+              break;
+            }
+            case QB_K_PERM: {
+              const double2 mb = mp[1], mc = mp[2];
+              QB_DISPATCH_TP(tp, (perm_masked<0>(a, mb, mc, rmask, rwant)), (perm_masked<1>(a, mb, mc, rmask, rwant)),
+                             (perm_masked<2>(a, mb, mc, rmask, rwant)));
+              break;
+            }
+            case QB_K_SWAP: {
+              QB_DISPATCH_TP(tp, (swap_masked<0>(a, rmask, rwant)), (swap_masked<1>(a, rmask, rwant)),
+                             (swap_masked<2>(a, rmask, rwant)));
+              break;
+            }
+            case QB_K_PHASE: {
+              const double2 ph = mp[0];
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if ((uint32_t(e) & rmask) == rwant) a[e] = cmul(ph, a[e]);
+              break;
+            }
+            case QB_K_LADDER: {
+              const double2 *tb = s_tab + h1.z;
+              const double2 *F = tb + 64 + (1 << hi_bits);
+              double2 c = cmul(s_pout[h1.w], tb[jb & 63u]);
+              if (hi_bits) c = cmul(c, tb[64 + (jb >> QB_LADDER_CHUNK)]);
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                if ((uint32_t(e) & rmask) == rwant) a[e] = cmul(cmul(c, F[e]), a[e]);
+              break;
+            }
+            default:
+              break;
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          tile[pb ^ ((e & 1) ? d0 : 0u) ^ ((e & 2) ? d1 : 0u) ^ ((e & 4) ? d2 : 0u)] = a[e];
+      }
+      __syncthreads();
     }
+
+    // ---- STORE ---------------------------------------------------------------------------
+    if (!(P.debug & 4))
+    for (uint32_t j = tid; j < tileN; j += kFThreads)
+      __stcs(psi + (base | (uint64_t(hi_off[j >> 3]) << 3) | (j & 7u)), tile[swz(j)]);
+    __syncthreads();  // every read of this buffer is done before a later copy lands in it
+    if (nbuf == 1 && more) issue_load(tn, tiles);
+    if (nbuf == 2) cur ^= 1;
   }
 }
 
-size_t fused_smem_bytes(int K) {
-  return (size_t(1) << K) * sizeof(double2) + kMaxLadders * sizeof(double2) +
-         QB_MAX_PASS_OPS * sizeof(QbOp) + QB_MAX_PASS_ROUNDS * sizeof(QbRound) +
+size_t fused_smem_bytes(int K, int ntable, int nbuf) {
+  return size_t(nbuf) * (size_t(1) << K) * sizeof(double2) + kMaxLadders * sizeof(double2) +
+         QB_MAX_PASS_OPS * sizeof(QbOp) + size_t(ntable) * sizeof(double2) + QB_MAX_PASS_ROUNDS * sizeof(QbRound) +
          (size_t(1) << (K - 3)) * sizeof(uint32_t);
 }
 
-int g_groups = 0;  // 0 = not configured
+constexpr size_t kSmemLimit = 227 * 1024;
+int g_sms = 0;
 
 }  // namespace
 
 cudaError_t fused_configure(int device) {
-  (void)device;
   static_assert(sizeof(QbOp) == 128, "QbOp is read as 16-byte pieces");
   static_assert(sizeof(QbRound) % 4 == 0 && (QB_MAX_PASS_OPS * sizeof(QbOp)) % 16 == 0, "smem layout");
-  if (g_groups == 0) {
-    const char *e = getenv("QCC_B200_FUSED_GROUPS");
-    g_groups = (e && atoi(e) == 1) ? 1 : 2;
-  }
-  cudaError_t err = cudaFuncSetAttribute(k_fused_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         int(fused_smem_bytes(QB_MAX_TILE_BITS)));
+  cudaError_t err = cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, device);
   if (err != cudaSuccess) return err;
-  return cudaFuncSetAttribute(k_fused_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              int(fused_smem_bytes(QB_MAX_TILE_BITS)));
+  return cudaFuncSetAttribute(k_fused_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemLimit));
 }
 
 cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cudaStream_t st) {
@@ -431,15 +418,31 @@ cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cuda
   P.ops = p.ops;
   P.rounds = p.rounds;
   P.tables = p.tables;
+  P.outph = p.outph;
   P.outbits = p.outbits;
+  P.jbtab = p.jbtab;
+  static const int dbg = getenv("QCC_B200_FUSED_DEBUG") ? atoi(getenv("QCC_B200_FUSED_DEBUG")) : 0;
+  static const int force_nbuf = getenv("QCC_B200_FUSED_NBUF") ? atoi(getenv("QCC_B200_FUSED_NBUF")) : 0;
+  P.debug = dbg;
+  static const int stagger = getenv("QCC_B200_FUSED_STAGGER_NS") ? atoi(getenv("QCC_B200_FUSED_STAGGER_NS")) : 0;
+  P.stagger_ns = stagger;
+  P.sms = g_sms;
   const int K = p.desc.K;
   if (K < 4 || K > QB_MAX_TILE_BITS || K > nbits) return cudaErrorInvalidValue;
   if (p.desc.nops > QB_MAX_PASS_OPS || p.desc.nrounds > QB_MAX_PASS_ROUNDS) return cudaErrorInvalidValue;
-  unsigned blocks = 1u << (nbits - K);
-  if (g_groups == 1)
-    k_fused_pass<1><<<blocks, kFThreads, fused_smem_bytes(K), st>>>(P);
-  else
-    k_fused_pass<2><<<blocks, kFThreads, fused_smem_bytes(K), st>>>(P);
+  const unsigned ntiles = 1u << (nbits - K);
+  // Default: one CTA per tile, single buffer, two CTAs of 256 threads resident per SM (register
+  // budget 128/thread: the 16 fp64 amplitude registers plus a complex 2x2 and ladder phases fit
+  // without spilling; at 3 CTAs / 80 registers the spills and ladder-table misses cost more
+  // than the extra CTA gains).  QCC_B200_FUSED_NBUF=2 selects the persistent two-deep cp.async
+  // ring instead (one CTA per SM); measured slower (profiles/r01_fused_experiments.md).
+  int nbuf = force_nbuf == 2 && fused_smem_bytes(K, p.desc.ntable, 2) <= kSmemLimit ? 2 : 1;
+  const size_t smem = fused_smem_bytes(K, p.desc.ntable, nbuf);
+  if (smem > kSmemLimit) return cudaErrorInvalidValue;
+  P.nbuf = nbuf;
+  unsigned blocks = ntiles;
+  if (nbuf == 2) blocks = ntiles < unsigned(g_sms) ? ntiles : unsigned(g_sms);
+  k_fused_pass<<<blocks, kFThreads, smem, st>>>(P);
   return cudaGetLastError();
 }
 

@@ -291,9 +291,9 @@ void build_ladder_tables(const TileMap &tm, const QbRound &r, const Item &it, in
   //   [0, 64)            T_lo[j & 63]
   //   [64, 64 + 2^hi)    T_hi[j >> 6]
   //   next 8             F[e]   product over round bits set in e
-  //   next 1             constant factor (self phase when the pivot is outside the tile)
-  //   next nout          phases of the outside partner bits
   // T_lo / T_hi are evaluated on the group base (round bits zero), F covers the round bits.
+  // The per-tile constant lives in a second array (outph, from outph_off): the constant
+  // factor (self phase when the pivot is outside the tile), then one phase per outside bit.
   op->table_off = int32_t(pp->tables.size());
   bool is_round[QB_MAX_TILE_BITS] = {false};
   for (int k = 0; k < r.nbits; ++k) is_round[r.rbit[k]] = true;
@@ -315,8 +315,9 @@ void build_ladder_tables(const TileMap &tm, const QbRound &r, const Item &it, in
       if (e >> k & 1) p = cmulh(p, per[r.rbit[k]]);
     pp->tables.push_back(p);
   }
-  pp->tables.push_back(self_out);
-  for (auto &p : out_ph) pp->tables.push_back(p);
+  op->outph_off = int32_t(pp->outph.size());
+  pp->outph.push_back(self_out);
+  for (auto &p : out_ph) pp->outph.push_back(p);
   op->nout = int32_t(out_bits.size());
   op->out_off = int32_t(pp->outbits.size());
   for (int b : out_bits) pp->outbits.push_back(b);
@@ -356,6 +357,16 @@ void close_round(const TileMap &tm, std::vector<int> &rset, std::vector<PendingO
   for (int b : freeb)
     if (b >= 0) order.push_back(b);
   for (size_t k = 0; k < order.size(); ++k) r.qmap[k] = order[k];
+  // per-group base index and its swizzled shared-memory slot, so the kernel does one load
+  // instead of a K-3 step bit scatter per group per round
+  for (uint32_t q = 0; q < (1u << (K - 3)); ++q) {
+    uint32_t jb = 0;
+    for (int k = 0; k < K - 3; ++k) jb |= ((q >> k) & 1u) << order[size_t(k)];
+    uint32_t x = jb >> 3;
+    x ^= x >> 3;
+    x ^= x >> 6;
+    pp->jbtab.push_back(jb | ((jb ^ (x & 7u)) << 16));
+  }
   r.op_begin = int32_t(pp->ops.size());
   for (size_t pi = 0; pi < pend.size(); ++pi) {
     const PendingOp &po = pend[pi];
@@ -462,6 +473,7 @@ void emit_pass(int nbits, int K, const std::vector<const Item *> &items, const s
   pp.desc.nrounds = int32_t(pp.rounds.size());
   pp.desc.nops = int32_t(pp.ops.size());
   pp.desc.ntable = int32_t(pp.tables.size());
+  pp.desc.ngroups_log2 = tm.K - 3;
   pp.noutbits = int(pp.outbits.size());
   out->passes.push_back(std::move(pp));
 }
@@ -502,6 +514,7 @@ void plan_gates(int nbits, const QbGate *gates, int64_t ngates, int tile_bits, P
   build_items(merged, !no_ladder, &items);
   std::vector<const Item *> cur;
   std::vector<int> targets;
+  int nlad_pass = 0;  // ladders this pass holds (their tables are staged in shared memory)
   int nops = 0;       // ops this pass will hold (staged in shared memory by the kernel)
   int nrounds_ub = 1; // upper bound on its rounds: a new round at most every 3 new targets
   std::vector<int> round_targets;
@@ -514,13 +527,15 @@ void plan_gates(int nbits, const QbGate *gates, int64_t ngates, int tile_bits, P
         std::find(round_targets.begin(), round_targets.end(), it.g.target) == round_targets.end()) {
       if (int(round_targets.size()) == QB_ROUND_BITS) new_round = true;
     }
-    if ((new_target && int(targets.size()) == cap) || nops + cost > QB_MAX_PASS_OPS ||
+    bool lad_full = it.kind == QB_K_LADDER && nlad_pass == QB_MAX_PASS_LADDERS;
+    if ((new_target && int(targets.size()) == cap) || nops + cost > QB_MAX_PASS_OPS || lad_full ||
         (new_round && nrounds_ub == QB_MAX_PASS_ROUNDS)) {
       emit_pass(nbits, K, cur, targets, out);
       cur.clear();
       targets.clear();
       round_targets.clear();
       nops = 0;
+      nlad_pass = 0;
       nrounds_ub = 1;
       new_round = false;
       new_target = needs_target(it.kind) && it.g.target >= QB_TILE_LOW;
@@ -534,6 +549,7 @@ void plan_gates(int nbits, const QbGate *gates, int64_t ngates, int tile_bits, P
       round_targets.push_back(it.g.target);
     if (new_target) targets.push_back(it.g.target);
     nops += cost;
+    if (it.kind == QB_K_LADDER) nlad_pass += 1;
     cur.push_back(&it);
   }
   emit_pass(nbits, K, cur, targets, out);
@@ -551,6 +567,10 @@ size_t Plan::blob_bytes() {
     off = align16(off + p.tables.size() * sizeof(Cplx));
     p.outbits_off = off;
     off = align16(off + p.outbits.size() * sizeof(int32_t));
+    p.outph_off = off;
+    off = align16(off + p.outph.size() * sizeof(Cplx));
+    p.jbtab_off = off;
+    off = align16(off + p.jbtab.size() * sizeof(uint32_t));
   }
   return std::max<size_t>(off, 16);
 }
@@ -562,12 +582,14 @@ void Plan::serialize(char *dst) const {
     memcpy(dst + p.rounds_off, p.rounds.data(), p.rounds.size() * sizeof(QbRound));
     if (!p.tables.empty()) memcpy(dst + p.tables_off, p.tables.data(), p.tables.size() * sizeof(Cplx));
     if (!p.outbits.empty()) memcpy(dst + p.outbits_off, p.outbits.data(), p.outbits.size() * sizeof(int32_t));
+    if (!p.outph.empty()) memcpy(dst + p.outph_off, p.outph.data(), p.outph.size() * sizeof(Cplx));
+    memcpy(dst + p.jbtab_off, p.jbtab.data(), p.jbtab.size() * sizeof(uint32_t));
   }
 }
 
 std::string Plan::to_json() const {
   std::string s = "{\"passes\":[";
-  char buf[256];
+  char buf[512];
   bool firstp = true;
   for (const PlannedPass &p : passes) {
     if (!firstp) s += ",";
@@ -608,9 +630,10 @@ std::string Plan::to_json() const {
       const QbOp &O = p.ops[o];
       snprintf(buf, sizeof buf,
                "%s{\"kind\":%d,\"tpos\":%d,\"lmask\":%u,\"lwant\":%u,\"rmask\":%u,\"rwant\":%u,"
-               "\"gmask\":%llu,\"gwant\":%llu,\"table_off\":%d,\"nout\":%d,\"out_off\":%d,\"flags\":%d,\"m\":[",
+               "\"gmask\":%llu,\"gwant\":%llu,\"table_off\":%d,\"nout\":%d,\"out_off\":%d,\"outph_off\":%d,"
+               "\"flags\":%d,\"mflags\":%d,\"m\":[",
                o ? "," : "", O.kind, O.tpos, O.lmask, O.lwant, O.rmask, O.rwant, (unsigned long long)O.gmask,
-               (unsigned long long)O.gwant, O.table_off, O.nout, O.out_off, O.flags);
+               (unsigned long long)O.gwant, O.table_off, O.nout, O.out_off, O.outph_off, O.flags, O.mflags);
       s += buf;
       for (int k = 0; k < 8; ++k) {
         snprintf(buf, sizeof buf, "%s%.17g", k ? "," : "", O.m[k]);
@@ -621,6 +644,16 @@ std::string Plan::to_json() const {
     s += "],\"tables\":[";
     for (size_t t = 0; t < p.tables.size(); ++t) {
       snprintf(buf, sizeof buf, "%s[%.17g,%.17g]", t ? "," : "", p.tables[t].x, p.tables[t].y);
+      s += buf;
+    }
+    s += "],\"outph\":[";
+    for (size_t t = 0; t < p.outph.size(); ++t) {
+      snprintf(buf, sizeof buf, "%s[%.17g,%.17g]", t ? "," : "", p.outph[t].x, p.outph[t].y);
+      s += buf;
+    }
+    s += "],\"jbtab\":[";
+    for (size_t t = 0; t < p.jbtab.size(); ++t) {
+      snprintf(buf, sizeof buf, "%s%u", t ? "," : "", p.jbtab[t]);
       s += buf;
     }
     s += "],\"outbits\":[";

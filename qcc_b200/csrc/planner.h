@@ -26,10 +26,12 @@ struct PlannedPass {
   QbPassDesc desc{};
   std::vector<QbOp> ops;
   std::vector<QbRound> rounds;
-  std::vector<Cplx> tables;
-  std::vector<int32_t> outbits;
+  std::vector<Cplx> tables;      // per ladder: T_lo[64], T_hi[2^(K-6)], F[8]  (staged in smem)
+  std::vector<Cplx> outph;       // per ladder: constant factor, then one phase per outside bit
+  std::vector<int32_t> outbits;  // per ladder: the outside partner bits
+  std::vector<uint32_t> jbtab;   // per round, per group q: jb | swizzled slot(jb) << 16
   // filled by Plan::layout(): byte offsets inside the serialized blob
-  size_t ops_off = 0, rounds_off = 0, tables_off = 0, outbits_off = 0;
+  size_t ops_off = 0, rounds_off = 0, tables_off = 0, outbits_off = 0, outph_off = 0, jbtab_off = 0;
   int noutbits = 0;
   int64_t single_gate = -1;  // >= 0: run `single` with the plain sweep kernel instead
   QbGate single{};           // the (possibly pre-multiplied) gate of a single-gate pass

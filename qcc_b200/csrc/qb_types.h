@@ -60,6 +60,7 @@ struct QbGate {
 #define QB_LADDER_CHUNK 6    // ladder lookup tables are indexed by 6 tile-local bits
 #define QB_MAX_PASS_OPS 48   // ops of one pass are staged in shared memory (48 * 128 B)
 #define QB_MAX_PASS_ROUNDS 16
+#define QB_MAX_PASS_LADDERS 12  // their lookup tables (<= 200 x 16 B each) are staged in shared memory too
 #define QB_MF_REAL 1         // all four entries of m are real: 8 instead of 20 flops per pair
 
 struct alignas(16) QbOp {   // 128 bytes, read by the kernel as 16-byte pieces
@@ -74,7 +75,7 @@ struct alignas(16) QbOp {   // 128 bytes, read by the kernel as 16-byte pieces
   int32_t nout;      // LADDER: number of partner bits outside the tile
   int32_t out_off;   // LADDER: first entry in the pass's outside-bit array
   int32_t mflags;    // QB_MF_* properties of m
-  int32_t pad1;
+  int32_t outph_off; // LADDER: first entry in the pass's outside-phase array ([0] = constant factor)
 };
 
 struct QbRound {
@@ -88,7 +89,9 @@ struct QbPassDesc {
   int32_t K;                           // tile bits
   int32_t nrounds;
   int32_t nops;
-  int32_t ntable;                      // double2 entries in the table buffer
+  int32_t ntable;                      // double2 entries in the (staged) ladder table buffer
+  int32_t ngroups_log2;                // K - 3
+  int32_t pad_;
   int32_t tile_bits[QB_MAX_TILE_BITS + 3];  // index-bit positions, ascending
   uint64_t tile_mask;                  // OR of 1 << tile_bits[k]
 };

@@ -107,9 +107,11 @@ def interpret_plan(plan_json: str, n: int, gates, psi: np.ndarray) -> np.ndarray
     gidx = base[:, None] | off[None, :]
     T = psi[gidx]                               # [tile, local]
     tables = np.array([complex(x, y) for x, y in p["tables"]], dtype=np.complex128)
+    outph = np.array([complex(x, y) for x, y in p["outph"]], dtype=np.complex128)
+    jbtab = np.array(p["jbtab"], dtype=np.int64).reshape(len(p["rounds"]), 1 << (K - 3))
     outbits = p["outbits"]
     hi_bits = max(K - 6, 0)
-    for R in p["rounds"]:
+    for ri, R in enumerate(p["rounds"]):
       assert R["nbits"] == 3
       rbit = R["rbit"]
       qmap = R["qmap"]
@@ -119,6 +121,10 @@ def interpret_plan(plan_json: str, n: int, gates, psi: np.ndarray) -> np.ndarray
       jb = np.zeros(ng, dtype=np.int64)
       for k, lp in enumerate(qmap):
         jb |= ((q >> k) & 1) << lp
+      # the kernel reads jb and its swizzled slot from the host-built table
+      assert np.array_equal(jbtab[ri] & 0xFFFF, jb)
+      fold = (jb >> 3) ^ (jb >> 6) ^ (jb >> 9) ^ (jb >> 12)
+      assert np.array_equal(jbtab[ri] >> 16, jb ^ (fold & 7))
       spread = np.array([sum(((e >> k) & 1) << rbit[k] for k in range(3)) for e in range(8)])
       je = jb[:, None] | spread[None, :]        # [group, e]
       A = T[:, je]                              # [tile, group, e]
@@ -166,11 +172,11 @@ def interpret_plan(plan_json: str, n: int, gates, psi: np.ndarray) -> np.ndarray
           else:
             lad_rmask, lad_rwant = op["rmask"], op["rwant"]
           t0 = op["table_off"]
-          cbase = t0 + 64 + (1 << hi_bits) + 8
-          pout = np.full(ntiles, tables[cbase], dtype=np.complex128)
+          cbase = op["outph_off"]
+          pout = np.full(ntiles, outph[cbase], dtype=np.complex128)
           for k in range(op["nout"]):
             bit = outbits[op["out_off"] + k]
-            pout = np.where((base >> bit) & 1 == 1, pout * tables[cbase + 1 + k], pout)
+            pout = np.where((base >> bit) & 1 == 1, pout * outph[cbase + 1 + k], pout)
           c = pout[:, None] * tables[t0 + (jb & 63)][None, :]
           if hi_bits:
             c = c * tables[t0 + 64 + (jb >> 6)][None, :]
