@@ -338,6 +338,17 @@ def libq_dense(width, initval, ops, dtype=np.complex128):
       ctl(GATES["v"], op[1], op[2])
     elif name == "cv_adj":
       ctl(GATES["v"].conj().T, op[1], op[2])
+    elif name in ("s", "sdag", "tdag", "vdag", "yrootdag", "hdag", "xdag", "ydag", "zdag"):
+      base = GATES[name[:-3]] if name.endswith("dag") else GATES[name]
+      one(base.conj().T if name.endswith("dag") else base, op[1])
+    elif name in ("rx", "ry", "rz"):
+      axis = {"rx": [1.0, 0, 0], "ry": [0, 1.0, 0], "rz": [0, 0, 1.0]}[name]
+      one(rotation(axis, op[2]), op[1])
+    elif name in ("crx", "cry", "crz"):
+      axis = {"crx": [1.0, 0, 0], "cry": [0, 1.0, 0], "crz": [0, 0, 1.0]}[name]
+      ctl(rotation(axis, op[3]), op[1], op[2])
+    elif name in ("ch", "cs", "ct", "cy", "cyroot"):
+      ctl(GATES[name[1:]], op[1], op[2])
     elif name == "ccx":
       c0, c1, tq = op[1], op[2], op[3]
       idx = np.arange(1 << n)

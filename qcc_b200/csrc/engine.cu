@@ -202,8 +202,8 @@ int run_fused(qb_state *s, const std::vector<QbGate> &gates) {
     }
     qb::DevicePass dp;
     dp.desc = pp.desc;
-    dp.ops = reinterpret_cast<const QbOp *>(dbase + pp.ops_off);
-    dp.rounds = reinterpret_cast<const QbRound *>(dbase + pp.rounds_off);
+    dp.ops = pp.ops.data();
+    dp.rounds = pp.rounds.data();
     dp.tables = pp.desc.ntable ? reinterpret_cast<const double2 *>(dbase + pp.tables_off) : nullptr;
     dp.outbits = pp.noutbits ? reinterpret_cast<const int32_t *>(dbase + pp.outbits_off) : nullptr;
     dp.outph = pp.outph.empty() ? nullptr : reinterpret_cast<const double2 *>(dbase + pp.outph_off);

@@ -42,6 +42,8 @@
 // combinations of the round's own bits.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "kernels.h"
 
@@ -56,8 +58,6 @@ struct FusedParams {
   double2 *psi;
   int nbits;
   QbPassDesc desc;
-  const QbOp *ops;
-  const QbRound *rounds;
   const double2 *tables;
   const double2 *outph;
   const int32_t *outbits;
@@ -66,6 +66,11 @@ struct FusedParams {
   int nbuf;   // tile buffers in the shared-memory ring (1 or 2)
   int stagger_ns;  // first-wave start offset between the CTA slots of an SM (see launch_fused_pass)
   int sms;
+  // Pass descriptors travel as kernel parameters (7 KiB of the 32 KiB parameter space): the
+  // per-op decode in the hot loop is then LDC from the constant bank (warp-uniform index), which
+  // costs neither shared-memory wavefronts nor LSU issue slots.
+  QbRound rounds[QB_MAX_PASS_ROUNDS];
+  QbOp ops[QB_MAX_PASS_OPS];
 };
 
 __device__ __forceinline__ uint32_t swz(uint32_t j) {
@@ -195,10 +200,10 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_consta
   const int nbuf = P.nbuf;
   double2 *tiles = reinterpret_cast<double2 *>(smem_raw);               // nbuf x 2^K
   double2 *s_pout = tiles + size_t(nbuf) * tileN;                       // kMaxLadders
-  QbOp *s_ops = reinterpret_cast<QbOp *>(s_pout + kMaxLadders);         // QB_MAX_PASS_OPS
-  double2 *s_tab = reinterpret_cast<double2 *>(s_ops + QB_MAX_PASS_OPS);  // ntable
-  QbRound *s_rounds = reinterpret_cast<QbRound *>(s_tab + P.desc.ntable);  // QB_MAX_PASS_ROUNDS
-  uint32_t *hi_off = reinterpret_cast<uint32_t *>(s_rounds + QB_MAX_PASS_ROUNDS);  // 2^(K-3)
+  double2 *s_tab = s_pout + kMaxLadders;                                // ntable
+  uint32_t *hi_off = reinterpret_cast<uint32_t *>(s_tab + P.desc.ntable);  // 2^(K-3)
+  const QbOp *s_ops = P.ops;        // constant bank
+  const QbRound *s_rounds = P.rounds;
   const uint32_t tid = threadIdx.x;
   double2 *__restrict__ psi = P.psi;
 
@@ -212,16 +217,8 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_consta
     for (uint32_t k = 0; k < slot; ++k) __nanosleep(uint32_t(P.stagger_ns));
   }
 
-  // ---- STAGE (once per CTA): descriptors, ladder tables, run offsets -> shared memory -----
+  // ---- STAGE (once per CTA): ladder tables, run offsets -> shared memory --------------------
   {
-    const int4 *src = reinterpret_cast<const int4 *>(P.ops);
-    int4 *dst = reinterpret_cast<int4 *>(s_ops);
-    const int n16 = P.desc.nops * int(sizeof(QbOp) / 16);
-    for (int i = tid; i < n16; i += kFThreads) dst[i] = __ldg(src + i);
-    const int32_t *rs = reinterpret_cast<const int32_t *>(P.rounds);
-    int32_t *rd = reinterpret_cast<int32_t *>(s_rounds);
-    const int n4 = P.desc.nrounds * int(sizeof(QbRound) / 4);
-    for (int i = tid; i < n4; i += kFThreads) rd[i] = __ldg(rs + i);
     for (int i = tid; i < P.desc.ntable; i += kFThreads) s_tab[i] = __ldg(P.tables + i);
     // offset of every 8-amplitude run of a tile, in units of 8 amplitudes
     for (uint32_t h = tid; h < (tileN >> 3); h += kFThreads) {
@@ -305,12 +302,11 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_consta
 #pragma unroll 1
         for (int oi = ob; oi < oe; ++oi) {
           const QbOp *op = s_ops + oi;
-          const int4 h0 = *reinterpret_cast<const int4 *>(op);            // kind tpos lmask lwant
-          const int4 h1 = *(reinterpret_cast<const int4 *>(op) + 1);      // rmask rwant table_off flags
-          const ulonglong2 h2 = *(reinterpret_cast<const ulonglong2 *>(op) + 2);  // gmask gwant
-          if ((base & h2.x) != h2.y) continue;                            // uniform per tile
-          const int kind = h0.x, tp = h0.y;
-          const uint32_t rmask = uint32_t(h1.x), rwant = uint32_t(h1.y);
+          if ((base & op->gmask) != op->gwant) continue;                  // uniform per tile
+          const int kind = op->kind, tp = op->tpos;
+          const uint32_t rmask = op->rmask, rwant = op->rwant;
+          const int4 h1 = make_int4(0, 0, op->table_off, op->flags);
+          const int4 h0 = make_int4(0, 0, int(op->lmask), int(op->lwant));
           const double2 *mp = reinterpret_cast<const double2 *>(op->m);
           if (kind == QB_K_ULADDER) {  // uncontrolled by construction
             const double2 *tb = s_tab + h1.z;
@@ -393,8 +389,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_consta
 
 size_t fused_smem_bytes(int K, int ntable, int nbuf) {
   return size_t(nbuf) * (size_t(1) << K) * sizeof(double2) + kMaxLadders * sizeof(double2) +
-         QB_MAX_PASS_OPS * sizeof(QbOp) + size_t(ntable) * sizeof(double2) + QB_MAX_PASS_ROUNDS * sizeof(QbRound) +
-         (size_t(1) << (K - 3)) * sizeof(uint32_t);
+         size_t(ntable) * sizeof(double2) + (size_t(1) << (K - 3)) * sizeof(uint32_t);
 }
 
 constexpr size_t kSmemLimit = 227 * 1024;
@@ -415,8 +410,9 @@ cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cuda
   P.psi = psi;
   P.nbits = nbits;
   P.desc = p.desc;
-  P.ops = p.ops;
-  P.rounds = p.rounds;
+  if (p.desc.nops > QB_MAX_PASS_OPS || p.desc.nrounds > QB_MAX_PASS_ROUNDS) return cudaErrorInvalidValue;
+  memcpy(P.ops, p.ops, size_t(p.desc.nops) * sizeof(QbOp));
+  memcpy(P.rounds, p.rounds, size_t(p.desc.nrounds) * sizeof(QbRound));
   P.tables = p.tables;
   P.outph = p.outph;
   P.outbits = p.outbits;

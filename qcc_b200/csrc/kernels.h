@@ -36,8 +36,8 @@ cudaError_t launch_cvt_f2d(const float2 *in, double2 *out, uint64_t n, cudaStrea
 // ---- fused tile-resident pass (fused.cu) ---------------------------------------
 struct DevicePass {
   QbPassDesc desc;
-  const QbOp *ops;        // device
-  const QbRound *rounds;  // device
+  const QbOp *ops;        // HOST: copied into the kernel parameters
+  const QbRound *rounds;  // HOST
   const double2 *tables;  // device (ladder lookup tables, staged into smem) or nullptr
   const double2 *outph;   // device (ladder per-tile constant + outside-bit phases) or nullptr
   const int32_t *outbits; // device (ladder outside-bit lists) or nullptr

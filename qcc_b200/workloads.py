@@ -107,3 +107,39 @@ def supremacy(n: int, depth: int, seed: int = 0, patterns=None):
       elif isinstance(s[i], tuple) and s[i][1] >= 0:
         out.append((2, i, s[i][1], g["z"]))
   return out
+
+
+def grover_circuit(nbits: int, marked: int = None, *, device: int = 0, qc_factory=None, iterations: int = None):
+  """Circuit Grover of grover.py:124-168 on the device-resident qc: `nbits` search qubits,
+  one ancilla in |1>, nbits-1 helper qubits for multi_control (2*nbits qubits in total;
+  nbits=16 is configs[3], 32 qubits).  `marked` defaults to np.random.randint(0, 2^nbits),
+  the draw make_f1 makes (grover.py:20-27).  Returns (qc, marked_bits)."""
+  from qcc_b200 import circuit, helper
+  if marked is None:
+    marked = int(np.random.randint(0, 1 << nbits))
+  bits = helper.val2bits(marked, nbits)
+  qc = qc_factory("Grover") if qc_factory else circuit.qc("Grover", device=device)
+  reg = qc.reg(nbits, 0)
+  qc.reg(1, 1)
+  aux = qc.reg(nbits - 1, 0)
+  if iterations is None:
+    iterations = int(math.pi / 4 * math.sqrt(2 ** nbits))
+  idx = list(range(nbits))
+  x, z = ops.PauliX(), ops.PauliZ()
+
+  def multi_masked(gate, allow):
+    for i in idx:
+      if bits[i] == allow:
+        qc.apply1(gate, i, gate.name)
+
+  qc.h(list(range(nbits + 1)))
+  for _ in range(iterations):
+    multi_masked(x, 0)                                             # phase inversion
+    qc.multi_control(reg, nbits, aux, x, "Phase Inversion")
+    multi_masked(x, 0)
+    qc.h(idx)                                                      # inversion about the mean
+    qc.x(idx)
+    qc.multi_control(reg, nbits, aux, z, "Mean Inversion")
+    qc.x(idx)
+    qc.h(idx)
+  return qc, bits

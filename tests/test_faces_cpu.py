@@ -1,0 +1,137 @@
+"""CPU: host-side logic of the python face (IR recording, composites, transpiler text) and
+that programs written against the reference's libq header compile and link against ours."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, ROOT, load_golden, stream_of
+from qcc_b200 import circuit, helper, ops
+
+
+def ir_stream(qc):
+  out = []
+  for g in qc.ir.gates:
+    if g.is_single():
+      out.append((1, 0, g.idx0, np.asarray(g.gate), g.name, g.val))
+    elif g.is_ctl():
+      out.append((2, g.ctl, g.idx1, np.asarray(g.gate), g.name, g.val))
+  return out
+
+
+def assert_same_stream(ours, z):
+  ref = stream_of(z)
+  assert len(ours) == len(ref)
+  for (k, c, t, m, name, _), (rk, rc, rt, rm), rname in zip(ours, ref, z["names"]):
+    assert (k, t) == (rk, rt)
+    if k == 2:
+      assert c == rc
+    assert np.abs(np.asarray(m) - rm).max() < 1e-15, (name, rname)
+    assert (name or "") == str(rname)
+
+
+def test_qft6_ir_and_transpiler_text_match_the_reference():
+  """configs[0]: same IR as the reference's circuit.qc and byte-identical dumpers.libq text."""
+  qc = circuit.qc("qft6", eager=False)
+  r = qc.reg(6, 0b101101)
+  qc.qft(r)
+  assert_same_stream(ir_stream(qc), load_golden("circ_qft6.npz"))
+  want = open(os.path.join(GOLDEN, "qft6_libq.cc")).read()
+  assert qc.libq() == want
+
+
+def test_larose_and_composite_streams_match_the_reference():
+  qc = circuit.qc("larose", eager=False)
+  qc.reg(8, 5, name="q")
+  for _ in range(3):
+    for bit in range(8):
+      qc.h(bit)
+      qc.v(bit)
+      if bit > 0:
+        qc.cx(bit, 0)
+  assert_same_stream(ir_stream(qc), load_golden("circ_larose_n8_d3.npz"))
+
+  qc = circuit.qc("composites", eager=False)
+  qc.reg(9, 0)
+  qc.toffoli(0, 3, 5)
+  qc.swap(1, 7)
+  qc.cswap(2, 4, 8)
+  qc.multi_control([0, [1], 2, [3]], 8, [4, 5, 6], ops.PauliX(), "mc")
+  qc.ccu1(0, 1, 2, 0.77)
+  qc.rx(3, 0.3)
+  qc.cry(3, 4, -1.3)
+  qc.crz(8, 0, 2.1)
+  qc.cx0(6, 2)
+  qc.sdag(5)
+  qc.cvdag(1, 6)
+  qc.cyroot(7, 0)
+  z = load_golden("circ_composites9.npz")
+  ours = ir_stream(qc)
+  ref = stream_of(z)
+  assert len(ours) == len(ref) == 68
+  for (k, c, t, m, _, _), (rk, rc, rt, rm) in zip(ours, ref):
+    assert (k, t) == (rk, rt) and (k == 1 or c == rc)
+    assert np.abs(np.asarray(m) - rm).max() < 1e-12      # sqrtm of X agrees to rounding
+  inv = qc.inverse()
+  zi = load_golden("circ_composites9_inverse.npz")
+  for (k, c, t, m, _, _), (rk, rc, rt, rm) in zip(ir_stream(inv), stream_of(zi)):
+    assert (k, t) == (rk, rt) and (k == 1 or c == rc)
+    assert np.abs(np.asarray(m) - rm).max() < 1e-12
+
+
+def test_qft_swaps_inverse_qft_stream():
+  qc = circuit.qc("qft9", eager=False)
+  r = qc.reg(9, 0)
+  qc.qft(r, with_swaps=True)
+  qc.inverse_qft(r, with_swaps=False)
+  assert_same_stream(ir_stream(qc), load_golden("circ_qft9_swaps_iqft.npz"))
+
+
+def test_multi_control_gate_count():
+  """circuit_test.py:152-158: 5 controls -> 41 gates."""
+  qc = circuit.qc("multi", eager=False)
+  ctl = qc.reg(5, 0)
+  aux = qc.reg(4, 0)
+  tgt = qc.reg(1, 0)
+  qc.multi_control(ctl, tgt[0], aux, ops.PauliX(), "x")
+  assert qc.ir.ngates == 41
+  assert "Gates : 41" in qc.stats()
+
+
+def test_helpers_and_reg():
+  assert helper.bits2val((1, 0, 1)) == 5 and helper.val2bits(5, 4) == [0, 1, 0, 1]
+  assert helper.pi_fractions(np.pi / 8, "M_PI") == "M_PI/8"
+  assert helper.pi_fractions(-np.pi, "M_PI") == "-M_PI"
+  assert helper.pi_fractions(3 * np.pi / 4) == "3*pi/4"
+  assert helper.pi_fractions(0.1234) == "0.1234"
+  qc = circuit.qc(eager=False)
+  a = qc.reg(3, 0b110)
+  b = qc.reg(2, [0, 1])
+  assert a.val == [1, 1, 0] and b.val == [0, 1] and b[0] == 3 and qc.nbits == 5
+  assert str(a) == "|110>"
+
+
+def test_non_eager_circuits_never_touch_the_gpu(has_gpu):
+  """A transpile-only circuit (larose_benchmark.py:45-55) must work without a device and
+  without allocating 2^28 amplitudes anywhere."""
+  qc = circuit.qc(eager=False)
+  qc.reg(28, 3, name="q")
+  for bit in range(28):
+    qc.h(bit)
+    qc.v(bit)
+    if bit:
+      qc.cx(bit, 0)
+  text = qc.libq()
+  assert "libq::new_qureg(0, 28);" in text and text.count("libq::cx(") == 27
+  assert qc._dev is None
+
+
+@pytest.mark.parametrize("src", ["golden/qft6_libq.cc", "libq_progs/bell_u1.cc", "libq_progs/all_gates.cc"])
+def test_libq_programs_compile_against_our_header(src, tmp_path):
+  exe = tmp_path / "prog"
+  cmd = ["g++", "-O1", "-I" + os.path.join(ROOT, "qcc_b200", "libq"), os.path.join(ROOT, "tests", src),
+         "-L" + os.path.join(ROOT, "qcc_b200", "lib"), "-lqcc_libq", "-lqcc_b200",
+         "-Wl,-rpath," + os.path.join(ROOT, "qcc_b200", "lib"), "-o", str(exe)]
+  subprocess.run(cmd, check=True, capture_output=True)
+  assert exe.exists()
