@@ -209,6 +209,7 @@ def main():
   ap.add_argument("--e2e-steps", type=int, default=2)
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-e2e", action="store_true")
+  ap.add_argument("--no-secondary", action="store_true")
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
   wl = dict(WORKLOADS[args.workload])
@@ -291,6 +292,39 @@ def main():
                     "CUDA-event time of that kernel inside the timed region; traffic (ncu dram bytes) "
                     "is recorded under profiles/"}
   by_gate_alg = (c1["bytes_algorithmic"] - c0["bytes_algorithmic"]) / (ms * 1e-3) / 1e9
+  # ncu dram bytes per launch of the same kernels (profiles/r01_traffic.json, one --set full capture)
+  try:
+    traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+    if roof and n == traffic.get("qubits"):
+      roof["traffic"] = traffic.get(roof["kernel"])
+  except Exception:  # pylint: disable=broad-except
+    traffic = {}
+
+  # ---- secondary: the single-gate kernel's roofline at the same size (one h per qubit, no fusion)
+  single = None
+  if wl["fusion"] and not args.no_secondary:
+    from qcc_b200 import workloads
+    hs = _cabi.pack_xg_gates(workloads.hsweep(n))
+    s.set_fusion(False)
+    for _ in range(2):
+      s.xg_apply_gates(hs)
+    s.sync()
+    s.profile_enable(True)
+    s.profile_read(reset=True)
+    s.timer_start()
+    for _ in range(3):
+      s.xg_apply_gates(hs)
+    hms = s.timer_stop()
+    hp = s.profile_read(reset=True)["apply1"]
+    s.profile_enable(False)
+    s.set_fusion(True)
+    s.set_tile_bits(args.tile_bits)
+    ach = hp["bytes"] / (hp["ms"] * 1e-3) / 1e9
+    single = {"workload": f"h on each of {n} qubits, one k_apply_u launch per gate", "kernel": "k_apply_u",
+              "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+              "launches": hp["launches"], "avg_launch_ms": hp["ms"] / hp["launches"],
+              "gates_per_s": 3 * n / (hms * 1e-3),
+              "traffic": traffic.get("k_apply_u") if n == traffic.get("qubits") else None}
 
   # ---- e2e: host buffers through the C ABI ------------------------------------------------
   e2e = None
@@ -358,7 +392,7 @@ def main():
         "gpu_launches": c1["kernel_launches"] - c0["kernel_launches"],
         "achieved_gbs_algorithmic_by_gate": by_gate_alg,
         "achieved_gbs_swept": (c1["bytes_swept"] - c0["bytes_swept"]) / (ms * 1e-3) / 1e9,
-        "roofline": roof, "kernel_ms": {k: v["ms"] for k, v in prof.items() if v["launches"]},
+        "roofline": roof, "roofline_single_gate": single, "kernel_ms": {k: v["ms"] for k, v in prof.items() if v["launches"]},
         "cpu_baseline": cpu, "e2e": e2e, "e2e_resident": e2e_res, "clocks": clocks,
         "wall_s_timed_region": wall, "norm2_after": norm,
     }

@@ -25,7 +25,7 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-i
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 h = next(i for i, r in enumerate(rows) if "# Samples" in r)
-hdr, data = rows[h], rows[h + 1:]
+hdr, data = rows[h], [r for r in rows[h + 1:] if len(r) == len(rows[h]) and r[rows[h].index('# Samples')].isdigit()]
 si, ii, smp = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples")
 tot = sum(int(r[ii]) for r in data)
 tots = sum(int(r[smp]) for r in data)
