@@ -20,9 +20,11 @@ in the same timed region (qb_profile_*), against MEASURED_PEAKS.json's hbm_gbs.
 `cpu_baseline` times the reference's own xgates build (oracle/_ref/libxgates.so, 1 thread --
 the reference has no threading) on a bounded sample of the same gate stream.
 
-N > 1 (torchrun): each rank owns one GPU and runs its own copy of the workload -- independent
-replicas, weak scaling, no data-path collective (state sharding across GPUs is not built
-yet).
+N > 1 (torchrun): ONE state of n + log2(N) qubits is sharded over the N GPUs by its top index
+bits (each GPU keeps a 2^n shard, so per-GPU memory and work are fixed: weak scaling).  Gates on
+sharded qubits cost a pairwise half-shard exchange over NVLink (ncclSend/ncclRecv) and a bit
+remap; diagonal gates and controls on sharded qubits cost nothing extra.  `value` is the gate
+count of the one big circuit / max-over-ranks time; exchange bytes and GB/s are reported.
 """
 import argparse
 import json
@@ -233,13 +235,24 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
   from qcc_b200 import _cabi
+  comm_id = None
+  n_shard = n
+  if world > 1:
+    if world & (world - 1):
+      raise SystemExit("--gpus must be a power of two")
+    ids = [_cabi.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    comm_id = ids[0]
+    n = n_shard + int(np.log2(world))       # one bigger state, same shard per GPU
+    wl["n"] = n
+    stream = build_stream(args.workload, n)
   packed = _cabi.pack_xg_gates(stream)
   ngates = len(stream)
-  s = _cabi.DeviceState(n, 0, local_rank)
+  s = _cabi.DeviceState(n, 0, local_rank, rank=rank, nranks=world, comm_id=comm_id)
   s.set_fusion(wl["fusion"])
   if wl["fusion"]:
     s.set_tile_bits(args.tile_bits)
-  s.fill_random(1234 + rank)
+  s.fill_random(1234)
 
   def barrier():
     s.sync()
@@ -276,7 +289,7 @@ def main():
 
   # ---- roofline of the dominant kernel class --------------------------------------------
   peak, peak_src = hbm_peak()
-  dom = max(prof, key=lambda k: prof[k]["ms"])
+  dom = max((k for k in prof if k != "exchange"), key=lambda k: prof[k]["ms"])
   d = prof[dom]
   roof = None
   if d["launches"]:
@@ -302,7 +315,7 @@ def main():
 
   # ---- secondary: the single-gate kernel's roofline at the same size (one h per qubit, no fusion)
   single = None
-  if wl["fusion"] and not args.no_secondary:
+  if wl["fusion"] and not args.no_secondary and world == 1:
     from qcc_b200 import workloads
     hs = _cabi.pack_xg_gates(workloads.hsweep(n))
     s.set_fusion(False)
@@ -330,7 +343,7 @@ def main():
   e2e = None
   e2e_res = None
   if rank == 0 or world > 1:
-    if not args.no_e2e:
+    if not args.no_e2e and world == 1:
       try:
         host = _cabi.PinnedBuffer(1 << n)
         host.array[:] = 0
@@ -344,7 +357,7 @@ def main():
           s.xg_apply_gates(packed)
           _cabi.check(_cabi.lib().qb_copy_out(s._h, 0, 1 << n, host.array.ctypes.data))
         dt = time.perf_counter() - t0
-        e2e = {"value": ngates * args.e2e_steps * world / dt, "unit": "gates/s",
+        e2e = {"value": ngates * args.e2e_steps / dt, "unit": "gates/s",
                "h2d_bytes_per_step": (1 << n) * 16 + len(packed) * 80, "d2h_bytes_per_step": (1 << n) * 16,
                "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
                "path": "pinned host complex128 state -> qb_copy_in -> qb_xg_apply_gates -> qb_copy_out "
@@ -360,7 +373,7 @@ def main():
       s.xg_apply_gates(packed)
       s.argmax()
     dt = time.perf_counter() - t0
-    e2e_res = {"value": ngates * reps * world / dt, "unit": "gates/s", "h2d_bytes_per_step": len(packed) * 80 + 16,
+    e2e_res = {"value": ngates * reps / dt, "unit": "gates/s", "h2d_bytes_per_step": len(packed) * 80 + 16,
                "d2h_bytes_per_step": 16 * 1184, "ms_per_step": dt / reps * 1e3,
                "path": "qb_set_basis -> qb_xg_apply_gates -> qb_argmax (state stays in HBM, as with the "
                        "reference where it stays in one numpy array)"}
@@ -378,7 +391,16 @@ def main():
       cpu = {"value": None, "unit": "gates/s", "cores": 1, "kind": "reference", "sample": f"failed: {ex}"[:200]}
 
   if rank == 0:
-    value = ngates * args.steps * world / (ms * 1e-3)
+    value = ngates * args.steps / (ms * 1e-3)
+    xch = prof.get("exchange", {"launches": 0, "ms": 0.0, "bytes": 0.0})
+    exchange = None
+    if world > 1:
+      exchange = {"per_step": (c1["exchanges"] - c0["exchanges"]) / args.steps,
+                  "bytes_per_rank_per_step": (c1["bytes_exchanged"] - c0["bytes_exchanged"]) / args.steps,
+                  "ms_per_step_rank0": xch["ms"] / args.steps,
+                  "nvlink_gbs_per_direction_rank0": (xch["bytes"] / (xch["ms"] * 1e-3) / 1e9) if xch["ms"] else None,
+                  "note": "each exchange sends and receives half a shard per rank (ncclSend/ncclRecv pair) "
+                          "and copies the received half back in place"}
     line = {
         "metric": "gate-applies/sec", "value": value, "unit": "gates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -387,13 +409,16 @@ def main():
         "config": {"workload": args.workload, "desc": wl["desc"], "qubits": n, "gates_per_step": ngates,
                    "state_bytes": (1 << n) * 16, "l2": "state (>= 4 GiB) >> 126 MB L2; no flush needed",
                    "fusion": wl["fusion"], "tile_bits": args.tile_bits if wl["fusion"] else None,
-                   "parallelism": "1 GPU" if world == 1 else f"{world} independent replicas (no collective)"},
+                   "shard_qubits": n_shard,
+                   "parallelism": "1 GPU" if world == 1 else
+                   f"one {n}-qubit state sharded over {world} GPUs by its top {int(np.log2(world))} index bits; "
+                   "NCCL send/recv pair exchange for gates on sharded qubits"},
         "passes_per_step": (c1["passes"] - c0["passes"]) / args.steps,
         "gpu_launches": c1["kernel_launches"] - c0["kernel_launches"],
         "achieved_gbs_algorithmic_by_gate": by_gate_alg,
         "achieved_gbs_swept": (c1["bytes_swept"] - c0["bytes_swept"]) / (ms * 1e-3) / 1e9,
         "roofline": roof, "roofline_single_gate": single, "kernel_ms": {k: v["ms"] for k, v in prof.items() if v["launches"]},
-        "cpu_baseline": cpu, "e2e": e2e, "e2e_resident": e2e_res, "clocks": clocks,
+        "exchange": exchange, "cpu_baseline": cpu, "e2e": e2e, "e2e_resident": e2e_res, "clocks": clocks,
         "wall_s_timed_region": wall, "norm2_after": norm,
     }
     print(json.dumps(line))

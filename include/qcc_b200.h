@@ -101,7 +101,8 @@ typedef struct qb_counters {
 #define QB_KCLASS_PHASE 1    /* single diagonal gate */
 #define QB_KCLASS_FUSED 2    /* tile-resident fused pass */
 #define QB_KCLASS_AUX 3      /* init / reductions / compaction */
-#define QB_KCLASS_COUNT 4
+#define QB_KCLASS_EXCHANGE 4 /* multi-GPU half-shard exchange (NCCL send/recv + copy-back) */
+#define QB_KCLASS_COUNT 5
 typedef struct qb_profile {
   uint64_t launches[QB_KCLASS_COUNT];
   double ms[QB_KCLASS_COUNT];          /* summed CUDA-event durations */
@@ -119,6 +120,22 @@ int qb_device_info(int device, char *name, size_t name_len, int *sm_count, size_
 /* ---- state lifetime (qureg.cc:11-62, circuit.py:125-164) -------------------- */
 /* Dense 2^nqubits complex128 vector on `device`, initialised to basis state |init_label>. */
 int qb_state_create(int nqubits, uint64_t init_label, int device, qb_state **out);
+/* Multi-GPU: the state is split across `nranks` (power of two) processes, one GPU each, by its
+ * top log2(nranks) index bits.  Every rank calls this with the same arguments except device /
+ * rank; id128 is the 128-byte communicator id rank 0 obtained from qb_comm_get_unique_id and
+ * passed to the others out of band (bench.py: torch.distributed broadcast).  On a sharded state
+ * every gate call, flush and readout is COLLECTIVE: all ranks must make the same calls in the
+ * same order.  Gates whose target is a sharded bit trigger a pairwise half-shard exchange
+ * (ncclSend/ncclRecv) and a logical->physical bit remap; diagonal gates and controls on
+ * sharded bits need no communication.  qb_copy_in/out and qb_list_above address the LOCAL
+ * shard (call qb_canonicalize first to undo the bit remap). */
+int qb_comm_get_unique_id(void *id128);
+int qb_state_create_sharded(int nqubits, uint64_t init_label, int device, int rank, int nranks,
+                            const void *id128, qb_state **out);
+/* nlocal: index bits held per rank; perm[b] (nqubits ints): physical bit of logical bit b. */
+int qb_state_layout(qb_state *s, int *nlocal, int *rank, int *nranks, int *perm);
+/* Exchanges / local bit swaps that bring perm back to the identity. */
+int qb_canonicalize(qb_state *s);
 int qb_state_destroy(qb_state *s);
 int qb_state_nqubits(qb_state *s, int *nqubits);
 int qb_set_basis(qb_state *s, uint64_t label);
@@ -188,6 +205,11 @@ int qb_timer_stop(qb_state *s, double *ms); /* implies qb_sync */
  * The CPU tests interpret this plan with numpy to check the planner without a GPU. */
 int qb_plan_json(int nqubits, const qb_gate *gates, int64_t ngates, int tile_bits, char *buf,
                  size_t cap, size_t *needed);
+/* The per-rank lowering of a gate stream for a sharded state (local gate batches + exchange
+ * steps + final bit permutation) as JSON; canonicalize != 0 appends the steps that restore the
+ * identity layout.  Host only: the CPU tests execute it with numpy shards + gloo send/recv. */
+int qb_shard_lower_json(int nqubits, int nranks, int rank, const qb_gate *gates, int64_t ngates,
+                        int canonicalize, char *buf, size_t cap, size_t *needed);
 /* Tile size (log2 amplitudes per CTA tile, 4..13, default 12) used by qb_flush. */
 int qb_set_tile_bits(qb_state *s, int tile_bits);
 

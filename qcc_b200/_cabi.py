@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libqcc_b200.so")
 
 QB_OK = 0
-QB_KCLASS = {"apply1": 0, "phase": 1, "fused": 2, "aux": 3}
+QB_KCLASS = {"apply1": 0, "phase": 1, "fused": 2, "aux": 3, "exchange": 4}
 
 
 class QbError(RuntimeError):
@@ -40,8 +40,8 @@ class qb_counters(ctypes.Structure):
 
 
 class qb_profile(ctypes.Structure):
-  _fields_ = [("launches", ctypes.c_uint64 * 4), ("ms", ctypes.c_double * 4),
-              ("bytes", ctypes.c_double * 4)]
+  _fields_ = [("launches", ctypes.c_uint64 * 5), ("ms", ctypes.c_double * 5),
+              ("bytes", ctypes.c_double * 5)]
 
 
 _P = ctypes.c_void_p
@@ -57,6 +57,12 @@ PROTOTYPES = {
     "qb_device_info": [_I, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(_I),
                        ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(_I), ctypes.POINTER(_I)],
     "qb_state_create": [_I, _U64, _I, ctypes.POINTER(_P)],
+    "qb_comm_get_unique_id": [_P],
+    "qb_state_create_sharded": [_I, _U64, _I, _I, _I, _P, ctypes.POINTER(_P)],
+    "qb_state_layout": [_P, ctypes.POINTER(_I), ctypes.POINTER(_I), ctypes.POINTER(_I), ctypes.POINTER(_I)],
+    "qb_canonicalize": [_P],
+    "qb_shard_lower_json": [_I, _I, _I, ctypes.POINTER(qb_gate), ctypes.c_int64, _I, ctypes.c_char_p,
+                            ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)],
     "qb_state_destroy": [_P],
     "qb_state_nqubits": [_P, ctypes.POINTER(_I)],
     "qb_set_basis": [_P, _U64],
@@ -162,6 +168,24 @@ def plan_json(nqubits: int, gates, tile_bits: int = 12) -> str:
   return buf.value.decode()
 
 
+def shard_lower_json(nqubits: int, nranks: int, rank: int, gates, canonicalize: bool = True) -> str:
+  """Per-rank lowering of index-bit gates for a sharded state (host only)."""
+  arr = gates if isinstance(gates, ctypes.Array) else pack_gates(gates)
+  need = ctypes.c_size_t(0)
+  check(lib().qb_shard_lower_json(nqubits, nranks, rank, arr, len(arr), int(canonicalize), None, 0,
+                                  ctypes.byref(need)))
+  buf = ctypes.create_string_buffer(need.value)
+  check(lib().qb_shard_lower_json(nqubits, nranks, rank, arr, len(arr), int(canonicalize), buf, need.value,
+                                  ctypes.byref(need)))
+  return buf.value.decode()
+
+
+def comm_unique_id() -> bytes:
+  buf = ctypes.create_string_buffer(128)
+  check(lib().qb_comm_get_unique_id(buf))
+  return buf.raw
+
+
 class PinnedBuffer:
   """Page-locked complex128 host vector (numpy view over cudaHostAlloc memory)."""
 
@@ -188,11 +212,19 @@ class PinnedBuffer:
 class DeviceState:
   """Owning handle of a device-resident 2^n complex128 amplitude vector."""
 
-  def __init__(self, nqubits: int, init_label: int = 0, device: int = 0):
+  def __init__(self, nqubits: int, init_label: int = 0, device: int = 0, *, rank: int = 0,
+               nranks: int = 1, comm_id: bytes = None):
+    """nranks > 1: this process holds shard `rank` of a state split over nranks GPUs (all
+    calls on it are then collective); comm_id is comm_unique_id() of rank 0, shared out of band."""
     h = _P()
-    check(lib().qb_state_create(nqubits, init_label, device, ctypes.byref(h)))
+    if nranks > 1:
+      idbuf = ctypes.create_string_buffer(comm_id, 128)
+      check(lib().qb_state_create_sharded(nqubits, init_label, device, rank, nranks, idbuf, ctypes.byref(h)))
+    else:
+      check(lib().qb_state_create(nqubits, init_label, device, ctypes.byref(h)))
     self._h = h
     self.nqubits = nqubits
+    self.rank, self.nranks = rank, nranks
 
   def close(self):
     if getattr(self, "_h", None):
@@ -224,7 +256,7 @@ class DeviceState:
 
   def copy_out(self, first: int = 0, count: int | None = None) -> np.ndarray:
     if count is None:
-      count = (1 << self.nqubits) - first
+      count = ((1 << self.nqubits) // self.nranks) - first
     out = np.empty(count, dtype=np.complex128)
     check(lib().qb_copy_out(self._h, first, count, out.ctypes.data))
     return out
@@ -251,6 +283,16 @@ class DeviceState:
 
   def xg_apply_gates(self, packed):
     check(lib().qb_xg_apply_gates(self._h, packed, len(packed)))
+
+  # -- sharding
+  def layout(self) -> dict:
+    nl, r, nr = _I(), _I(), _I()
+    perm = (_I * self.nqubits)()
+    check(lib().qb_state_layout(self._h, ctypes.byref(nl), ctypes.byref(r), ctypes.byref(nr), perm))
+    return {"nlocal": nl.value, "rank": r.value, "nranks": nr.value, "perm": list(perm)}
+
+  def canonicalize(self):
+    check(lib().qb_canonicalize(self._h))
 
   # -- queue
   def set_fusion(self, on: bool):

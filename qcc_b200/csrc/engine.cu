@@ -21,9 +21,11 @@
 #include <vector>
 
 #include "../../include/qcc_b200.h"
+#include "comm.h"
 #include "kernels.h"
 #include "planner.h"
 #include "qb_types.h"
+#include "shard.h"
 
 namespace {
 
@@ -53,6 +55,13 @@ int fail(int code, const char *fmt, ...) {
     if (rc__ != QB_OK) return rc__; \
   } while (0)
 
+#define NC(api, call)                                                                   \
+  do {                                                                                  \
+    ncclResult_t r__ = (call);                                                          \
+    if (r__ != ncclSuccess)                                                             \
+      return fail(QB_ERR_COMM, "%s failed: %s (%s:%d)", #call, (api)->GetErrorString(r__), __FILE__, __LINE__); \
+  } while (0)
+
 struct ProfRec {
   int kclass;
   double bytes;
@@ -62,9 +71,16 @@ struct ProfRec {
 }  // namespace
 
 struct qb_state {
-  int n = 0;            // qubits == index bits
-  uint64_t len = 0;     // 2^n
+  int n = 0;            // LOCAL index bits of this rank's shard (== nq when not sharded)
+  uint64_t len = 0;     // 2^n amplitudes held here
+  int nq = 0;           // logical qubits of the whole state
   int device = 0;
+  // sharding (shard.h): rank bits are the top physical index bits
+  int rank = 0, nranks = 1, p = 0;
+  std::vector<int> perm;          // logical index bit -> physical index bit
+  ncclComm_t comm = nullptr;
+  double2 *xbuf = nullptr;        // half-shard receive buffer for exchanges
+  size_t xbuf_bytes = 0;
   cudaStream_t stream = nullptr;
   double2 *psi = nullptr;
   bool fusion = true;
@@ -223,21 +239,117 @@ int run_fused(qb_state *s, const std::vector<QbGate> &gates) {
   return QB_OK;
 }
 
+int run_local(qb_state *s, const std::vector<QbGate> &q) {
+  if (q.empty()) return QB_OK;
+  if (s->fusion && s->n > QB_TILE_LOW) return run_fused(s, q);
+  for (const QbGate &g : q) QB(run_single(s, g));
+  return QB_OK;
+}
+
+// Swap physical global bit (n + rank_bit) with local bit `victim`: every rank trades the half
+// of its shard whose victim bit differs from its own rank bit with rank ^ (1 << rank_bit).
+// The half is 2^(n-1-victim) contiguous runs of 2^victim amplitudes; they are received into
+// xbuf (NCCL must not write into memory it is still sending from) and copied back in place.
+int do_exchange(qb_state *s, int rank_bit, int victim) {
+  std::string why;
+  const qb::NcclApi *nc = qb::nccl_api(&why);
+  if (!nc || !s->comm) return fail(QB_ERR_COMM, "exchange without a communicator: %s", why.c_str());
+  const int b = (s->rank >> rank_bit) & 1;
+  const int partner = s->rank ^ (1 << rank_bit);
+  const uint64_t run = uint64_t(1) << victim;
+  const uint64_t nruns = uint64_t(1) << (s->n - 1 - victim);
+  const uint64_t sel = b ? 0 : 1;  // we give away the half whose victim bit is NOT our rank bit
+  const size_t half_bytes = size_t(s->len / 2) * sizeof(double2);
+  if (s->xbuf_bytes < half_bytes) {
+    if (s->xbuf) cudaFree(s->xbuf);
+    s->xbuf = nullptr;
+    s->xbuf_bytes = 0;
+    cudaError_t e = cudaMalloc(&s->xbuf, half_bytes);
+    if (e != cudaSuccess) return fail(QB_ERR_NOMEM, "exchange buffer of %zu MiB: %s", half_bytes >> 20, cudaGetErrorString(e));
+    s->xbuf_bytes = half_bytes;
+  }
+  {
+    ProfScope ps(s, QB_KCLASS_EXCHANGE, double(half_bytes));
+    NC(nc, nc->GroupStart());
+    for (uint64_t h = 0; h < nruns; ++h) {
+      const uint64_t off = (h << (victim + 1)) | (sel << victim);
+      NC(nc, nc->Send(s->psi + off, size_t(run) * 2, ncclDouble, partner, s->comm, s->stream));
+      NC(nc, nc->Recv(s->xbuf + h * run, size_t(run) * 2, ncclDouble, partner, s->comm, s->stream));
+    }
+    NC(nc, nc->GroupEnd());
+    CU(cudaMemcpy2DAsync(s->psi + (sel << victim), size_t(run) * 2 * sizeof(double2), s->xbuf,
+                         size_t(run) * sizeof(double2), size_t(run) * sizeof(double2), size_t(nruns),
+                         cudaMemcpyDeviceToDevice, s->stream));
+  }
+  s->cnt.exchanges += 1;
+  s->cnt.bytes_exchanged += half_bytes;
+  s->cnt.kernel_launches += 1;
+  return QB_OK;
+}
+
+int run_steps(qb_state *s, const std::vector<qb::ShardStep> &steps) {
+  for (const qb::ShardStep &st : steps) {
+    if (st.kind == 1) {
+      QB(do_exchange(s, st.rank_bit, st.victim));
+      continue;
+    }
+    const uint64_t before = s->cnt.gates_applied;
+    QB(run_local(s, st.gates));
+    s->cnt.gates_applied = before + uint64_t(st.retired);
+  }
+  return QB_OK;
+}
+
 int flush(qb_state *s) {
   if (s->queue.empty()) return QB_OK;
   CU(cudaSetDevice(s->device));
   std::vector<QbGate> q;
   q.swap(s->queue);
-  if (s->fusion && s->n > QB_TILE_LOW) return run_fused(s, q);
-  for (const QbGate &g : q) QB(run_single(s, g));
+  if (s->nranks == 1) return run_local(s, q);
+  qb::ShardLayout L;
+  L.n = s->nq;
+  L.nl = s->n;
+  L.p = s->p;
+  L.rank = s->rank;
+  L.perm = s->perm;
+  std::vector<qb::ShardStep> steps;
+  qb::lower_for_rank(&L, q.data(), int64_t(q.size()), &steps);
+  s->perm = L.perm;
+  return run_steps(s, steps);
+}
+
+// logical index -> (owner rank, local index) under the current bit permutation
+void locate(const qb_state *s, uint64_t logical, int *rank, uint64_t *local) {
+  uint64_t phys = 0;
+  for (int b = 0; b < s->nq; ++b)
+    if (logical >> b & 1) phys |= uint64_t(1) << s->perm[size_t(b)];
+  *rank = int(phys >> s->n);
+  *local = phys & (s->len - 1);
+}
+
+uint64_t logical_of(const qb_state *s, int rank, uint64_t local) {
+  const uint64_t phys = (uint64_t(rank) << s->n) | local;
+  uint64_t logical = 0;
+  for (int b = 0; b < s->nq; ++b)
+    if (phys >> s->perm[size_t(b)] & 1) logical |= uint64_t(1) << b;
+  return logical;
+}
+
+// Sum a device double over all ranks (no-op when not sharded).
+int allreduce_scalar(qb_state *s, double *dptr) {
+  if (s->nranks == 1) return QB_OK;
+  std::string why;
+  const qb::NcclApi *nc = qb::nccl_api(&why);
+  if (!nc) return fail(QB_ERR_COMM, "%s", why.c_str());
+  NC(nc, nc->AllReduce(dptr, dptr, 1, ncclDouble, ncclSum, s->comm, s->stream));
   return QB_OK;
 }
 
 int enqueue(qb_state *s, uint64_t ctl_mask, int target, const double m[8]) {
   if (!s) return fail(QB_ERR_ARG, "null state");
   if (!m) return fail(QB_ERR_ARG, "null gate matrix");
-  if (target < 0 || target >= s->n) return fail(QB_ERR_ARG, "target bit %d out of range [0,%d)", target, s->n);
-  if (s->n < 64 && (ctl_mask >> s->n)) return fail(QB_ERR_ARG, "control mask has bits >= %d", s->n);
+  if (target < 0 || target >= s->nq) return fail(QB_ERR_ARG, "target bit %d out of range [0,%d)", target, s->nq);
+  if (s->nq < 64 && (ctl_mask >> s->nq)) return fail(QB_ERR_ARG, "control mask has bits >= %d", s->nq);
   if (ctl_mask >> target & 1) return fail(QB_ERR_ARG, "control and target coincide (bit %d)", target);
   if (__builtin_popcountll(ctl_mask) > 3) return fail(QB_ERR_UNSUPPORTED, "more than 3 controls");
   QbGate g;
@@ -245,11 +357,12 @@ int enqueue(qb_state *s, uint64_t ctl_mask, int target, const double m[8]) {
   g.target = target;
   g.kind = classify(m);
   memcpy(g.m, m, sizeof g.m);
-  if (!s->fusion) {
+  if (!s->fusion && s->nranks == 1) {
     CU(cudaSetDevice(s->device));
     return run_single(s, g);
   }
   s->queue.push_back(g);
+  if (!s->fusion) return flush(s);
   if (s->queue.size() >= 16384) return flush(s);
   return QB_OK;
 }
@@ -303,10 +416,42 @@ int qb_device_info(int device, char *name, size_t name_len, int *sm_count, size_
   return QB_OK;
 }
 
+int qb_comm_get_unique_id(void *id128) {
+  if (!id128) return fail(QB_ERR_ARG, "null pointer");
+  std::string why;
+  const qb::NcclApi *nc = qb::nccl_api(&why);
+  if (!nc) return fail(QB_ERR_COMM, "%s", why.c_str());
+  static_assert(sizeof(ncclUniqueId) == 128, "unique id size");
+  ncclUniqueId id;
+  NC(nc, nc->GetUniqueId(&id));
+  memcpy(id128, &id, sizeof id);
+  return QB_OK;
+}
+
+static int create_impl(int nqubits, uint64_t init_label, int device, int rank, int nranks, const void *id128,
+                       qb_state **out);
+
 int qb_state_create(int nqubits, uint64_t init_label, int device, qb_state **out) {
+  return create_impl(nqubits, init_label, device, 0, 1, nullptr, out);
+}
+
+int qb_state_create_sharded(int nqubits, uint64_t init_label, int device, int rank, int nranks,
+                            const void *id128, qb_state **out) {
+  if (nranks < 1 || (nranks & (nranks - 1))) return fail(QB_ERR_ARG, "nranks %d is not a power of two", nranks);
+  if (rank < 0 || rank >= nranks) return fail(QB_ERR_ARG, "rank %d out of range", rank);
+  if (nranks > 1 && !id128) return fail(QB_ERR_ARG, "sharded state needs the communicator id");
+  return create_impl(nqubits, init_label, device, rank, nranks, id128, out);
+}
+
+static int create_impl(int nqubits, uint64_t init_label, int device, int rank, int nranks, const void *id128,
+                       qb_state **out) {
   if (!out) return fail(QB_ERR_ARG, "null out pointer");
   *out = nullptr;
   if (nqubits < 1 || nqubits > 40) return fail(QB_ERR_ARG, "nqubits %d out of range [1,40]", nqubits);
+  int pbits = 0;
+  while ((1 << pbits) < nranks) ++pbits;
+  if (nqubits - pbits < 4 && nranks > 1)
+    return fail(QB_ERR_ARG, "%d qubits over %d ranks leaves fewer than 4 local bits", nqubits, nranks);
   if (nqubits < 64 && (init_label >> nqubits)) return fail(QB_ERR_ARG, "init label does not fit %d qubits", nqubits);
   int ndev = 0;
   CU(cudaGetDeviceCount(&ndev));
@@ -320,9 +465,15 @@ int qb_state_create(int nqubits, uint64_t init_label, int device, qb_state **out
     return fail(QB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
                 prop.major, prop.minor);
   qb_state *s = new qb_state;
-  s->n = nqubits;
-  s->len = uint64_t(1) << nqubits;
+  s->nq = nqubits;
+  s->n = nqubits - pbits;
+  s->len = uint64_t(1) << s->n;
   s->device = device;
+  s->rank = rank;
+  s->nranks = nranks;
+  s->p = pbits;
+  s->perm.resize(size_t(nqubits));
+  for (int b = 0; b < nqubits; ++b) s->perm[size_t(b)] = b;
   size_t freeb = 0, totalb = 0;
   cudaMemGetInfo(&freeb, &totalb);
   size_t need = size_t(s->len) * sizeof(double2);
@@ -347,6 +498,18 @@ int qb_state_create(int nqubits, uint64_t init_label, int device, qb_state **out
     qb_state_destroy(s);
     return rc;
   }
+  if (nranks > 1) {
+    std::string why;
+    const qb::NcclApi *nc = qb::nccl_api(&why);
+    ncclUniqueId id;
+    memcpy(&id, id128, sizeof id);
+    ncclResult_t r = nc ? nc->CommInitRank(&s->comm, nranks, id, rank) : ncclSystemError;
+    if (r != ncclSuccess) {
+      int rc = fail(QB_ERR_COMM, "ncclCommInitRank: %s", nc ? nc->GetErrorString(r) : why.c_str());
+      qb_state_destroy(s);
+      return rc;
+    }
+  }
   int rc = qb_set_basis(s, init_label);
   if (rc != QB_OK) {
     qb_state_destroy(s);
@@ -365,6 +528,11 @@ int qb_state_destroy(qb_state *s) {
     cudaEventDestroy(r.e1);
   }
   for (auto e : s->event_pool) cudaEventDestroy(e);
+  if (s->comm) {
+    const qb::NcclApi *nc = qb::nccl_api(nullptr);
+    if (nc) nc->CommDestroy(s->comm);
+  }
+  if (s->xbuf) cudaFree(s->xbuf);
   if (s->psi) cudaFree(s->psi);
   if (s->d_scalar) cudaFree(s->d_scalar);
   if (s->d_counter) cudaFree(s->d_counter);
@@ -382,18 +550,20 @@ int qb_state_destroy(qb_state *s) {
 
 int qb_state_nqubits(qb_state *s, int *nqubits) {
   if (!s || !nqubits) return fail(QB_ERR_ARG, "null pointer");
-  *nqubits = s->n;
+  *nqubits = s->nq;
   return QB_OK;
 }
 
 int qb_set_basis(qb_state *s, uint64_t label) {
   if (!s) return fail(QB_ERR_ARG, "null state");
-  if (label >= s->len) return fail(QB_ERR_ARG, "label out of range");
+  if (s->nq < 64 && (label >> s->nq)) return fail(QB_ERR_ARG, "label out of range");
   CU(cudaSetDevice(s->device));
   s->queue.clear();
+  for (int b = 0; b < s->nq; ++b) s->perm[size_t(b)] = b;
   CU(cudaMemsetAsync(s->psi, 0, size_t(s->len) * sizeof(double2), s->stream));
   const double2 one = make_double2(1.0, 0.0);
-  CU(cudaMemcpyAsync(s->psi + label, &one, sizeof one, cudaMemcpyHostToDevice, s->stream));
+  if (int(label >> s->n) == s->rank)
+    CU(cudaMemcpyAsync(s->psi + (label & (s->len - 1)), &one, sizeof one, cudaMemcpyHostToDevice, s->stream));
   CU(cudaStreamSynchronize(s->stream));  // `one` is a stack temporary
   s->cnt.kernel_launches += 1;
   return QB_OK;
@@ -403,9 +573,11 @@ int qb_fill_random(qb_state *s, uint64_t seed) {
   if (!s) return fail(QB_ERR_ARG, "null state");
   CU(cudaSetDevice(s->device));
   s->queue.clear();
-  CU(qb::launch_fill_random(s->psi, s->len, seed, s->stream));
+  for (int b = 0; b < s->nq; ++b) s->perm[size_t(b)] = b;
+  CU(qb::launch_fill_random(s->psi, s->len, uint64_t(s->rank) << s->n, seed, s->stream));
   double n2 = 0.0;
   CU(qb::launch_norm2(s->psi, s->len, s->d_scalar, s->stream));
+  QB(allreduce_scalar(s, s->d_scalar));
   CU(cudaMemcpyAsync(&n2, s->d_scalar, sizeof n2, cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
   CU(qb::launch_scale(s->psi, s->len, 1.0 / std::sqrt(n2), s->stream));
@@ -436,13 +608,13 @@ int qb_apply1(qb_state *s, int target, const double m[8]) { return enqueue(s, 0,
 
 int qb_applyc(qb_state *s, int control, int target, const double m[8]) {
   if (!s) return fail(QB_ERR_ARG, "null state");
-  if (control < 0 || control >= s->n) return fail(QB_ERR_ARG, "control bit %d out of range", control);
+  if (control < 0 || control >= s->nq) return fail(QB_ERR_ARG, "control bit %d out of range", control);
   return enqueue(s, uint64_t(1) << control, target, m);
 }
 
 int qb_applycc(qb_state *s, int c0, int c1, int target, const double m[8]) {
   if (!s) return fail(QB_ERR_ARG, "null state");
-  if (c0 < 0 || c0 >= s->n || c1 < 0 || c1 >= s->n) return fail(QB_ERR_ARG, "control bit out of range");
+  if (c0 < 0 || c0 >= s->nq || c1 < 0 || c1 >= s->nq) return fail(QB_ERR_ARG, "control bit out of range");
   if (c0 == c1) return fail(QB_ERR_ARG, "identical controls");
   return enqueue(s, (uint64_t(1) << c0) | (uint64_t(1) << c1), target, m);
 }
@@ -456,15 +628,15 @@ int qb_apply_gates(qb_state *s, const qb_gate *gates, int64_t ngates) {
 // ---- gates, python numbering --------------------------------------------------------
 int qb_xg_apply1(qb_state *s, int tgt, const double m[8]) {
   if (!s) return fail(QB_ERR_ARG, "null state");
-  return enqueue(s, 0, s->n - tgt - 1, m);  // out-of-range tgt is rejected by enqueue
+  return enqueue(s, 0, s->nq - tgt - 1, m);  // out-of-range tgt is rejected by enqueue
 }
 
 int qb_xg_applyc(qb_state *s, int ctl, int tgt, const double m[8]) {
   if (!s) return fail(QB_ERR_ARG, "null state");
-  int t = s->n - tgt - 1;
-  if (t < 0 || t >= s->n) return fail(QB_ERR_ARG, "target qubit %d out of range", tgt);
+  int t = s->nq - tgt - 1;
+  if (t < 0 || t >= s->nq) return fail(QB_ERR_ARG, "target qubit %d out of range", tgt);
   uint64_t mask = 0;
-  int r = xg_control_mask(s->n, ctl, tgt, &mask);
+  int r = xg_control_mask(s->nq, ctl, tgt, &mask);
   if (r < 0) return r;
   if (r == 1) {  // acts on nothing; still counts as an applied gate
     s->cnt.gates_applied += 1;
@@ -507,8 +679,22 @@ int qb_sync(qb_state *s) {
 // ---- readouts ---------------------------------------------------------------------------
 int qb_get_amplitude(qb_state *s, uint64_t index, double out[2]) {
   if (!s || !out) return fail(QB_ERR_ARG, "null pointer");
-  if (index >= s->len) return fail(QB_ERR_ARG, "index out of range");
-  return qb_copy_out(s, index, 1, out);
+  if (s->nq < 64 && (index >> s->nq)) return fail(QB_ERR_ARG, "index out of range");
+  if (s->nranks == 1) return qb_copy_out(s, index, 1, out);
+  // sharded: collective -- the owner reads, everybody receives
+  QB(flush(s));
+  int owner = 0;
+  uint64_t local = 0;
+  locate(s, index, &owner, &local);
+  std::string why;
+  const qb::NcclApi *nc = qb::nccl_api(&why);
+  if (!nc) return fail(QB_ERR_COMM, "%s", why.c_str());
+  double *two = s->d_blk_prob;  // scratch, >= 2 doubles
+  if (owner == s->rank) CU(cudaMemcpyAsync(two, s->psi + local, sizeof(double2), cudaMemcpyDeviceToDevice, s->stream));
+  NC(nc, nc->Broadcast(two, two, 2, ncclDouble, owner, s->comm, s->stream));
+  CU(cudaMemcpyAsync(out, two, sizeof(double2), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return QB_OK;
 }
 
 int qb_norm2(qb_state *s, double *out) {
@@ -519,6 +705,7 @@ int qb_norm2(qb_state *s, double *out) {
     CU(qb::launch_norm2(s->psi, s->len, s->d_scalar, s->stream));
   }
   s->cnt.kernel_launches += 1;
+  QB(allreduce_scalar(s, s->d_scalar));
   CU(cudaMemcpyAsync(out, s->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
   return QB_OK;
@@ -526,13 +713,21 @@ int qb_norm2(qb_state *s, double *out) {
 
 int qb_prob_bit(qb_state *s, int bit, double *p_one) {
   if (!s || !p_one) return fail(QB_ERR_ARG, "null pointer");
-  if (bit < 0 || bit >= s->n) return fail(QB_ERR_ARG, "bit out of range");
+  if (bit < 0 || bit >= s->nq) return fail(QB_ERR_ARG, "bit out of range");
   QB(flush(s));
   {
     ProfScope ps(s, QB_KCLASS_AUX, double(s->len) * 8.0);
-    CU(qb::launch_prob_mask(s->psi, s->len, uint64_t(1) << bit, s->d_scalar, s->stream));
+    const int pb = s->perm[size_t(bit)];
+    if (pb < s->n) {
+      CU(qb::launch_prob_mask(s->psi, s->len, uint64_t(1) << pb, s->d_scalar, s->stream));
+    } else if ((s->rank >> (pb - s->n)) & 1) {
+      CU(qb::launch_norm2(s->psi, s->len, s->d_scalar, s->stream));  // the bit is 1 on this whole shard
+    } else {
+      CU(cudaMemsetAsync(s->d_scalar, 0, sizeof(double), s->stream));
+    }
   }
   s->cnt.kernel_launches += 1;
+  QB(allreduce_scalar(s, s->d_scalar));
   CU(cudaMemcpyAsync(p_one, s->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
   return QB_OK;
@@ -559,6 +754,32 @@ int qb_argmax(qb_state *s, uint64_t *index, double *prob) {
       best = hp[b];
       bi = hi[b];
     }
+  if (s->nranks > 1) {
+    // translate to the logical index, then pick the global winner (ties: lowest logical index)
+    bi = logical_of(s, s->rank, bi);
+    std::string why;
+    const qb::NcclApi *nc = qb::nccl_api(&why);
+    if (!nc) return fail(QB_ERR_COMM, "%s", why.c_str());
+    double mine[2];
+    mine[0] = best;
+    memcpy(&mine[1], &bi, sizeof bi);
+    double *dsend = s->d_blk_prob;                 // 2 doubles
+    double *drecv = s->d_blk_prob + 2;             // 2 * nranks doubles (argmax_blocks() >> 2 * 8 + 2)
+    CU(cudaMemcpyAsync(dsend, mine, sizeof mine, cudaMemcpyHostToDevice, s->stream));
+    NC(nc, nc->AllGather(dsend, drecv, 2, ncclDouble, s->comm, s->stream));
+    std::vector<double> all(size_t(2 * s->nranks));
+    CU(cudaMemcpyAsync(all.data(), drecv, sizeof(double) * all.size(), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    best = -1.0;
+    for (int r = 0; r < s->nranks; ++r) {
+      uint64_t idx;
+      memcpy(&idx, &all[size_t(2 * r + 1)], sizeof idx);
+      if (all[size_t(2 * r)] > best || (all[size_t(2 * r)] == best && idx < bi)) {
+        best = all[size_t(2 * r)];
+        bi = idx;
+      }
+    }
+  }
   *index = bi;
   *prob = best;
   return QB_OK;
@@ -601,6 +822,9 @@ int qb_list_above(qb_state *s, double threshold, uint64_t cap, uint64_t *labels,
   // the kernel's slots are in arrival order; present them by ascending label
   std::vector<uint64_t> order(got);
   for (uint64_t i = 0; i < got; ++i) order[i] = i;
+  std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return hl[a] < hl[b]; });
+  if (s->nranks > 1)
+    for (uint64_t i = 0; i < got; ++i) hl[i] = logical_of(s, s->rank, hl[i]);
   std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return hl[a] < hl[b]; });
   for (uint64_t i = 0; i < got; ++i) {
     labels[i] = hl[order[i]];
@@ -759,6 +983,71 @@ int qb_timer_stop(qb_state *s, double *ms) {
   float f = 0.f;
   CU(cudaEventElapsedTime(&f, s->t0, s->t1));
   *ms = f;
+  return QB_OK;
+}
+
+int qb_state_layout(qb_state *s, int *nlocal, int *rank, int *nranks, int *perm) {
+  if (!s) return fail(QB_ERR_ARG, "null state");
+  QB(flush(s));
+  if (nlocal) *nlocal = s->n;
+  if (rank) *rank = s->rank;
+  if (nranks) *nranks = s->nranks;
+  if (perm)
+    for (int b = 0; b < s->nq; ++b) perm[b] = s->perm[size_t(b)];
+  return QB_OK;
+}
+
+int qb_canonicalize(qb_state *s) {
+  if (!s) return fail(QB_ERR_ARG, "null state");
+  QB(flush(s));
+  if (s->nranks == 1) return QB_OK;
+  qb::ShardLayout L;
+  L.n = s->nq;
+  L.nl = s->n;
+  L.p = s->p;
+  L.rank = s->rank;
+  L.perm = s->perm;
+  std::vector<qb::ShardStep> steps;
+  qb::canonicalize_steps(&L, &steps);
+  s->perm = L.perm;
+  const uint64_t before = s->cnt.gates_applied;
+  int rc = run_steps(s, steps);
+  s->cnt.gates_applied = before;  // layout moves are not gates of the caller's circuit
+  return rc;
+}
+
+int qb_shard_lower_json(int nqubits, int nranks, int rank, const qb_gate *gates, int64_t ngates, int canonicalize,
+                        char *buf, size_t cap, size_t *needed) {
+  if ((!gates && ngates) || !needed) return fail(QB_ERR_ARG, "null pointer");
+  if (nranks < 1 || (nranks & (nranks - 1)) || rank < 0 || rank >= nranks) return fail(QB_ERR_ARG, "bad rank/nranks");
+  int pbits = 0;
+  while ((1 << pbits) < nranks) ++pbits;
+  if (nqubits - pbits < 1 || nqubits > 40) return fail(QB_ERR_ARG, "nqubits out of range");
+  std::vector<QbGate> q;
+  for (int64_t k = 0; k < ngates; ++k) {
+    const qb_gate &g = gates[k];
+    if (g.target < 0 || g.target >= nqubits || (g.ctl_mask >> g.target & 1) || (g.ctl_mask >> nqubits))
+      return fail(QB_ERR_ARG, "gate %lld: bad bits", (long long)k);
+    QbGate x;
+    x.ctl_mask = g.ctl_mask;
+    x.target = g.target;
+    x.kind = classify(g.m);
+    memcpy(x.m, g.m, sizeof x.m);
+    q.push_back(x);
+  }
+  qb::ShardLayout L;
+  L.n = nqubits;
+  L.nl = nqubits - pbits;
+  L.p = pbits;
+  L.rank = rank;
+  L.perm.resize(size_t(nqubits));
+  for (int b = 0; b < nqubits; ++b) L.perm[size_t(b)] = b;
+  std::vector<qb::ShardStep> steps;
+  qb::lower_for_rank(&L, q.data(), ngates, &steps);
+  if (canonicalize) qb::canonicalize_steps(&L, &steps);
+  std::string js = qb::steps_to_json(L, steps);
+  *needed = js.size() + 1;
+  if (buf && cap >= js.size() + 1) memcpy(buf, js.c_str(), js.size() + 1);
   return QB_OK;
 }
 

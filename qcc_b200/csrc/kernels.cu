@@ -170,11 +170,11 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   return x ^ (x >> 31);
 }
 
-__global__ void __launch_bounds__(kThreads) k_fill_random(double2 *psi, uint64_t n, uint64_t seed) {
+__global__ void __launch_bounds__(kThreads) k_fill_random(double2 *psi, uint64_t n, uint64_t off, uint64_t seed) {
   uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
   for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-    uint64_t a = splitmix64(seed ^ (2 * i));
-    uint64_t b = splitmix64(seed ^ (2 * i + 1));
+    uint64_t a = splitmix64(seed ^ (2 * (off + i)));
+    uint64_t b = splitmix64(seed ^ (2 * (off + i) + 1));
     double2 v;
     v.x = double(int64_t(a >> 11)) * (1.0 / 4503599627370496.0) - 1.0;  // [-1, 1)
     v.y = double(int64_t(b >> 11)) * (1.0 / 4503599627370496.0) - 1.0;
@@ -294,8 +294,8 @@ unsigned stride_blocks(uint64_t n) {
 
 }  // namespace
 
-cudaError_t launch_fill_random(double2 *psi, uint64_t n, uint64_t seed, cudaStream_t st) {
-  k_fill_random<<<stride_blocks(n), kThreads, 0, st>>>(psi, n, seed);
+cudaError_t launch_fill_random(double2 *psi, uint64_t n, uint64_t index_offset, uint64_t seed, cudaStream_t st) {
+  k_fill_random<<<stride_blocks(n), kThreads, 0, st>>>(psi, n, index_offset, seed);
   return cudaGetLastError();
 }
 

@@ -15,7 +15,8 @@ namespace qb {
 cudaError_t launch_gate(void *psi, int nbits, const QbGate &g, bool is_double, cudaStream_t st);
 
 // ---- init / readout kernels (kernels.cu) -------------------------------------
-cudaError_t launch_fill_random(double2 *psi, uint64_t n, uint64_t seed, cudaStream_t st);
+// value of element i is a hash of (seed, index_offset + i): shards of one state agree with the whole
+cudaError_t launch_fill_random(double2 *psi, uint64_t n, uint64_t index_offset, uint64_t seed, cudaStream_t st);
 cudaError_t launch_scale(double2 *psi, uint64_t n, double f, cudaStream_t st);
 // out: 1 double (sum |psi|^2), zeroed by the launcher
 cudaError_t launch_norm2(const double2 *psi, uint64_t n, double *out, cudaStream_t st);

@@ -1,0 +1,196 @@
+// shard.cc -- see shard.h.
+#include "shard.h"
+
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+
+namespace qb {
+
+namespace {
+
+const double kX[8] = {0, 0, 1, 0, 1, 0, 0, 0};
+
+std::vector<int> inverse_of(const std::vector<int> &perm) {
+  std::vector<int> inv(perm.size());
+  for (size_t b = 0; b < perm.size(); ++b) inv[size_t(perm[b])] = int(b);
+  return inv;
+}
+
+void close_step(ShardStep *cur, std::vector<ShardStep> *steps) {
+  if (!cur->gates.empty() || cur->retired) steps->push_back(std::move(*cur));
+  *cur = ShardStep();
+}
+
+void push_exchange(ShardLayout *L, int global_pos, int victim, std::vector<ShardStep> *steps) {
+  ShardStep ex;
+  ex.kind = 1;
+  ex.rank_bit = global_pos - L->nl;
+  ex.victim = victim;
+  steps->push_back(ex);
+  std::vector<int> inv = inverse_of(L->perm);
+  const int la = inv[size_t(global_pos)], lb = inv[size_t(victim)];
+  L->perm[size_t(la)] = victim;
+  L->perm[size_t(lb)] = global_pos;
+}
+
+bool nondiagonal(int kind) { return kind == QB_K_U || kind == QB_K_PERM || kind == QB_K_SWAP; }
+
+// Belady: among the top local bits, evict the qubit whose next use as a mixing target is farthest.
+int choose_victim(const ShardLayout &L, const QbGate *gates, int64_t ngates, int64_t from) {
+  std::vector<int> inv = inverse_of(L.perm);
+  int best = L.nl - 1;
+  int64_t best_dist = -1;
+  for (int v = L.nl - 1; v >= std::max(0, L.nl - kVictimWindow); --v) {
+    const int lv = inv[size_t(v)];
+    int64_t dist = ngates + 1;
+    for (int64_t j = from + 1; j < ngates; ++j)
+      if (nondiagonal(gates[j].kind) && gates[j].target == lv) {
+        dist = j - from;
+        break;
+      }
+    if (dist > best_dist) {
+      best_dist = dist;
+      best = v;
+    }
+  }
+  return best;
+}
+
+}  // namespace
+
+void lower_for_rank(ShardLayout *L, const QbGate *gates, int64_t ngates, std::vector<ShardStep> *steps) {
+  ShardStep cur;
+  const int nl = L->nl;
+  for (int64_t i = 0; i < ngates; ++i) {
+    const QbGate &g = gates[i];
+    if (g.kind == QB_K_NOP) {
+      cur.retired += 1;
+      continue;
+    }
+    if (nondiagonal(g.kind) && L->perm[size_t(g.target)] >= nl) {
+      const int victim = choose_victim(*L, gates, ngates, i);
+      close_step(&cur, steps);
+      push_exchange(L, L->perm[size_t(g.target)], victim, steps);
+    }
+    const int pt = L->perm[size_t(g.target)];
+    uint64_t lm = 0;
+    bool active = true;
+    for (int b = 0; b < L->n; ++b) {
+      if (!(g.ctl_mask >> b & 1)) continue;
+      const int pb = L->perm[size_t(b)];
+      if (pb < nl) lm |= uint64_t(1) << pb;
+      else if (!((L->rank >> (pb - nl)) & 1)) active = false;
+    }
+    cur.retired += 1;
+    if (!active) continue;  // a global control bit is 0 on this rank: the gate touches nothing here
+    QbGate out{};
+    if (pt < nl) {
+      out = g;
+      out.ctl_mask = lm;
+      out.target = pt;
+      cur.gates.push_back(out);
+      continue;
+    }
+    // diagonal gate whose target bit is a rank bit: a phase on the remaining local bits
+    const int tb = (L->rank >> (pt - nl)) & 1;
+    double pr, pi;
+    if (g.kind == QB_K_PHASE) {
+      if (!tb) continue;
+      pr = g.m[6];
+      pi = g.m[7];
+    } else {  // DIAG
+      pr = tb ? g.m[6] : g.m[0];
+      pi = tb ? g.m[7] : g.m[1];
+      if (pr == 1.0 && pi == 0.0) continue;
+    }
+    if (lm == 0) {  // scalar on the whole shard
+      out.ctl_mask = 0;
+      out.target = 0;
+      out.kind = QB_K_DIAG;
+      out.m[0] = pr; out.m[1] = pi; out.m[6] = pr; out.m[7] = pi;
+    } else {
+      const int t2 = __builtin_ctzll(lm);
+      out.ctl_mask = lm & ~(uint64_t(1) << t2);
+      out.target = t2;
+      out.kind = QB_K_PHASE;
+      out.m[0] = 1.0; out.m[6] = pr; out.m[7] = pi;
+    }
+    cur.gates.push_back(out);
+  }
+  close_step(&cur, steps);
+}
+
+void canonicalize_steps(ShardLayout *L, std::vector<ShardStep> *steps) {
+  const int nl = L->nl, n = L->n;
+  ShardStep cur;
+  auto local_swap = [&](int a, int b) {  // swap the contents of local physical bits a and b: 3 cx
+    if (a == b) return;
+    for (int k = 0; k < 3; ++k) {
+      QbGate g{};
+      g.kind = QB_K_PERM;
+      memcpy(g.m, kX, sizeof kX);
+      g.ctl_mask = uint64_t(1) << ((k & 1) ? b : a);
+      g.target = (k & 1) ? a : b;
+      cur.gates.push_back(g);
+    }
+    std::vector<int> inv = inverse_of(L->perm);
+    const int la = inv[size_t(a)], lb = inv[size_t(b)];
+    L->perm[size_t(la)] = b;
+    L->perm[size_t(lb)] = a;
+  };
+  for (int G = nl; G < n; ++G) {
+    if (L->perm[size_t(G)] == G) continue;
+    int where = L->perm[size_t(G)];  // physical position of logical bit G
+    if (where >= nl) {               // sitting in another rank bit: bring it local first
+      close_step(&cur, steps);
+      push_exchange(L, where, nl - 1, steps);
+      where = nl - 1;
+    }
+    if (where < nl - kVictimWindow) {  // keep the exchanged half shard in few contiguous runs
+      local_swap(where, nl - 1);
+      where = nl - 1;
+    }
+    close_step(&cur, steps);
+    push_exchange(L, G, where, steps);
+  }
+  for (int q = 0; q < nl; ++q)
+    while (L->perm[size_t(q)] != q) local_swap(q, L->perm[size_t(q)]);
+  close_step(&cur, steps);
+}
+
+std::string steps_to_json(const ShardLayout &L, const std::vector<ShardStep> &steps) {
+  std::string s = "{\"n\":" + std::to_string(L.n) + ",\"nl\":" + std::to_string(L.nl) + ",\"rank\":" +
+                  std::to_string(L.rank) + ",\"perm\":[";
+  char buf[256];
+  for (size_t b = 0; b < L.perm.size(); ++b) s += (b ? "," : "") + std::to_string(L.perm[b]);
+  s += "],\"steps\":[";
+  for (size_t k = 0; k < steps.size(); ++k) {
+    const ShardStep &st = steps[k];
+    if (k) s += ",";
+    if (st.kind == 1) {
+      snprintf(buf, sizeof buf, "{\"kind\":1,\"rank_bit\":%d,\"victim\":%d}", st.rank_bit, st.victim);
+      s += buf;
+      continue;
+    }
+    snprintf(buf, sizeof buf, "{\"kind\":0,\"retired\":%lld,\"gates\":[", (long long)st.retired);
+    s += buf;
+    for (size_t j = 0; j < st.gates.size(); ++j) {
+      const QbGate &g = st.gates[j];
+      snprintf(buf, sizeof buf, "%s{\"ctl_mask\":%llu,\"target\":%d,\"kind\":%d,\"m\":[", j ? "," : "",
+               (unsigned long long)g.ctl_mask, g.target, g.kind);
+      s += buf;
+      for (int e = 0; e < 8; ++e) {
+        snprintf(buf, sizeof buf, "%s%.17g", e ? "," : "", g.m[e]);
+        s += buf;
+      }
+      s += "]}";
+    }
+    s += "]}";
+  }
+  s += "]}";
+  return s;
+}
+
+}  // namespace qb

@@ -1,0 +1,63 @@
+// shard.h -- host-side lowering of a logical gate stream onto ONE rank's shard of a state
+// that is split across 2^p GPUs by its top p physical index bits.  Pure host code.
+//
+// The reference has no counterpart (its only "scaling" is the arithmetic extrapolation of
+// src/supremacy.py:255-297, which assumes zero communication).  Rules:
+//   * logical index bit b lives at physical bit perm[b]; physical bits [0, nl) are local,
+//     physical bit nl + k is bit k of the rank;
+//   * a control on a global bit is a per-rank predicate: ranks whose bit is 0 skip the gate;
+//   * a diagonal gate (PHASE / DIAG) whose target is global needs no communication: on a
+//     given rank it is a phase on the remaining local bits (or a scalar);
+//   * a non-diagonal gate whose target is global first swaps that global bit with a local
+//     "victim" bit -- one pairwise half-shard exchange with rank ^ (1 << k) -- and updates
+//     perm, so every later gate on that qubit is local.  The victim is the high local bit
+//     whose logical qubit is needed as a non-diagonal target farthest in the future.
+// Every rank runs the same lowering on the same stream, so all ranks agree on the exchange
+// sequence without talking to each other.
+#ifndef QCC_B200_CSRC_SHARD_H_
+#define QCC_B200_CSRC_SHARD_H_
+
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "qb_types.h"
+
+namespace qb {
+
+struct ShardStep {
+  // kind 0: run `gates` (physical LOCAL bits, ready for plan_gates / launch_gate) on the shard
+  // kind 1: exchange -- swap physical global bit nl + rank_bit with local bit `victim`
+  int kind = 0;
+  std::vector<QbGate> gates;
+  int64_t retired = 0;   // logical gate records this step accounts for (incl. skipped ones)
+  int rank_bit = 0;
+  int victim = 0;
+};
+
+struct ShardLayout {
+  int n = 0;       // logical qubits
+  int nl = 0;      // local physical bits
+  int p = 0;       // global physical bits (nranks = 2^p)
+  int rank = 0;
+  std::vector<int> perm;  // logical bit -> physical bit
+};
+
+// Victims are taken from the top `kVictimWindow` local bits so that the exchanged half
+// shard is made of at most 2^(kVictimWindow-1) contiguous runs.
+constexpr int kVictimWindow = 6;
+
+// Lowers `gates` (LOGICAL index bits, kinds already classified) for layout->rank, updating
+// layout->perm as exchanges are scheduled.
+void lower_for_rank(ShardLayout *layout, const QbGate *gates, int64_t ngates, std::vector<ShardStep> *steps);
+
+// Exchange sequence (as steps of kind 1) + local bit transpositions (as cx triples inside
+// kind-0 steps) that bring perm back to the identity.
+void canonicalize_steps(ShardLayout *layout, std::vector<ShardStep> *steps);
+
+std::string steps_to_json(const ShardLayout &layout, const std::vector<ShardStep> &steps);
+
+}  // namespace qb
+
+#endif  // QCC_B200_CSRC_SHARD_H_

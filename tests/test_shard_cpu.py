@@ -1,0 +1,136 @@
+"""CPU, world_size 2 and 4 over gloo: the multi-GPU path's host logic.  Each process asks the
+library for ITS rank's lowering of a circuit (qb_shard_lower_json: local gate batches, exchange
+steps, bit permutation), executes it on a numpy shard -- local gates with the index-bit
+reference, exchanges with torch.distributed send/recv exactly as engine.cu's do_exchange lays
+them out -- and the gathered shards must equal the oracle's full-state result."""
+import json
+import math
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import ROOT, apply_masked, oracle, random_state, run_bits
+
+
+def _free_port():
+  s = socket.socket()
+  s.bind(("127.0.0.1", 0))
+  p = s.getsockname()[1]
+  s.close()
+  return p
+
+
+def _circuits(n):
+  H, X, V = oracle.GATES["h"], oracle.GATES["x"], oracle.GATES["v"]
+  qft = []
+  for i in reversed(range(n)):
+    qft.append((0, n - 1 - i, H))
+    for j in reversed(range(i)):
+      qft.append((1 << (n - 1 - i), n - 1 - j, oracle.u1(math.pi / 2 ** (i - j))))
+  rng = np.random.default_rng(11)
+  names = list(oracle.GATES)
+  rnd = []
+  for _ in range(120):
+    r = rng.random()
+    m = oracle.u1(float(rng.uniform(-3, 3))) if r < 0.2 else (
+        oracle.rotation([0, 0, 1.0], float(rng.uniform(-3, 3))) if r < 0.3 else oracle.GATES[names[rng.integers(len(names))]])
+    b = [int(x) for x in rng.permutation(n)[:3]]
+    nctl = int(rng.choice([0, 0, 1, 1, 2]))
+    mask = 0
+    for c in b[1:1 + nctl]:
+      mask |= 1 << c
+    rnd.append((mask, b[0], m))
+  larose = []
+  for bit in range(n):
+    larose += [(0, n - 1 - bit, H), (0, n - 1 - bit, V)]
+    if bit:
+      larose.append((1 << (n - 1 - bit), n - 1, X))
+  return {"qft": qft, "random": rnd, "larose": larose}
+
+
+def _worker(rank, world, port, n, out_dir):
+  sys.path.insert(0, ROOT)
+  sys.path.insert(0, os.path.join(ROOT, "tests"))
+  import torch
+  import torch.distributed as dist
+  from qcc_b200 import _cabi
+  dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+  try:
+    p = int(math.log2(world))
+    nl = n - p
+    for name, gates in _circuits(n).items():
+      for canon in (True, False):
+        plan = json.loads(_cabi.shard_lower_json(n, world, rank, gates, canonicalize=canon))
+        assert plan["nl"] == nl and plan["rank"] == rank
+        psi0 = random_state(n, 5)
+        shard = psi0[rank << nl:(rank + 1) << nl].copy()
+        retired = 0
+        for st in plan["steps"]:
+          if st["kind"] == 0:
+            retired += st["retired"]
+            for g in st["gates"]:
+              m = np.array([complex(g["m"][2 * i], g["m"][2 * i + 1]) for i in range(4)])
+              assert g["ctl_mask"] < (1 << nl) and g["target"] < nl
+              apply_masked(shard, nl, g["ctl_mask"], g["target"], m)
+            continue
+          k, v = st["rank_bit"], st["victim"]
+          b = (rank >> k) & 1
+          partner = rank ^ (1 << k)
+          sel = 0 if b else 1
+          run, nruns = 1 << v, 1 << (nl - 1 - v)
+          view = shard.reshape(nruns, 2, run)
+          send = torch.from_numpy(np.ascontiguousarray(view[:, sel, :]).view(np.float64))
+          recv = torch.empty_like(send)
+          reqs = [dist.isend(send, partner), dist.irecv(recv, partner)]
+          for r in reqs:
+            r.wait()
+          view[:, sel, :] = recv.numpy().view(np.complex128).reshape(nruns, run)
+        if not canon:
+          assert retired == len(gates)
+        # gather shards on rank 0 and undo the bit permutation
+        t = torch.from_numpy(shard.view(np.float64).copy())
+        parts = [torch.empty_like(t) for _ in range(world)] if rank == 0 else None
+        dist.gather(t, parts, dst=0)
+        if rank == 0:
+          phys = np.concatenate([x.numpy().view(np.complex128) for x in parts])
+          perm = plan["perm"]
+          if canon:
+            assert perm == list(range(n))
+          idx = np.arange(1 << n)
+          pidx = np.zeros_like(idx)
+          for bl in range(n):
+            pidx |= ((idx >> bl) & 1) << perm[bl]
+          got = phys[pidx]
+          want = run_bits(psi0.copy(), n, gates)
+          err = float(np.abs(got - want).max())
+          with open(os.path.join(out_dir, f"{name}_{int(canon)}.txt"), "w") as f:
+            f.write(f"{err} {sum(1 for s in plan['steps'] if s['kind'] == 1)}")
+    dist.barrier()
+  finally:
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 9), (4, 10)])
+def test_sharded_lowering_over_gloo(world, n, tmp_path):
+  import torch.multiprocessing as mp
+  port = _free_port()
+  mp.spawn(_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
+  for name in ("qft", "random", "larose"):
+    for canon in (1, 0):
+      err, nex = open(tmp_path / f"{name}_{canon}.txt").read().split()
+      assert float(err) <= 1e-12, (name, canon, err)
+  # QFT touches each sharded bit as a non-diagonal target exactly once: one exchange per global bit
+  assert int(open(tmp_path / "qft_0.txt").read().split()[1]) == int(math.log2(world))
+
+
+def test_lowering_is_identical_in_structure_on_every_rank():
+  from qcc_b200 import _cabi
+  n, world = 10, 4
+  gates = _circuits(n)["random"]
+  plans = [json.loads(_cabi.shard_lower_json(n, world, r, gates, canonicalize=True)) for r in range(world)]
+  shape = lambda p: [(s["kind"], s.get("rank_bit"), s.get("victim")) for s in p["steps"]]
+  assert all(shape(p) == shape(plans[0]) for p in plans)
+  assert all(p["perm"] == plans[0]["perm"] for p in plans)
