@@ -39,6 +39,12 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# One-off workloads of the multi-GPU configs (not part of the default line): run the whole
+# algorithm once through the python circuit.qc surface on a sharded state.
+#   grover:     grover.py:124-168 with --qubits/2 search bits (configs[3]: --qubits 32 --gpus 4)
+#   supremacy:  supremacy.py-style random circuit, depth 20 (configs[4]: --qubits 34 --gpus 8)
+ALGOS = ("grover", "supremacy")
+
 WORKLOADS = {
     "qft30": dict(n=30, desc="30-qubit QFT (circuit.qc.qft): 30 h + 435 cu1", fusion=True),
     "larose28": dict(n=28, desc="28-qubit larose_benchmark depth 28: 784 h + 784 v + 756 cx", fusion=True),
@@ -199,12 +205,67 @@ def run_reference_arm(args, wl, stream):
   }))
 
 
+def run_algorithm(args):
+  """Whole-algorithm runs for the multi-GPU configs: wall + CUDA-event time of ONE execution."""
+  rank = int(os.environ.get("RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  dist = None
+  comm_id = None
+  from qcc_b200 import _cabi, circuit, workloads
+  if world > 1:
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ids = [_cabi.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    comm_id = ids[0]
+  n = args.qubits or (32 if args.workload == "grover" else 34)
+  factory = lambda name: circuit.qc(name, device=local_rank, rank=rank, nranks=world, comm_id=comm_id)
+  t0 = time.perf_counter()
+  if args.workload == "grover":
+    nb = n // 2
+    np.random.seed(0)
+    qc, bits = workloads.grover_circuit(nb, qc_factory=factory)
+    maxbits, maxprob = qc.psi.maxprob()
+    check = {"marked": bits, "found": maxbits[:nb], "ok": maxbits[:nb] == bits, "maxprob": maxprob}
+    desc = f"grover.py circuit version, {nb} search bits, {n} qubits"
+  else:
+    stream = workloads.supremacy(n, args.depth, seed=0)
+    qc = factory("supremacy")
+    qc.reg(n, 0)
+    qc.dev.xg_apply_gates(_cabi.pack_xg_gates(stream))
+    norm = qc.psi.norm2()
+    check = {"norm2": norm, "ok": abs(norm - 1.0) < 1e-9}
+    desc = f"supremacy.py-style random circuit, {n} qubits, depth {args.depth}, seed 0"
+  qc.sync()
+  wall = time.perf_counter() - t0
+  c = qc.dev.counters()
+  if dist is not None:
+    dist.barrier()
+  if rank == 0:
+    print(json.dumps({
+        "metric": "gate-applies/sec", "value": c["gates_applied"] / wall, "unit": "gates/s", "n_gpus": world,
+        "steps": 1, "warmup": 0, "ms_per_step": wall * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": desc, "qubits": n,
+                   "parallelism": f"state sharded over {world} GPUs" if world > 1 else "1 GPU",
+                   "timing": "wall clock of one full run incl. python gate dispatch, planning and readout"},
+        "gates": c["gates_applied"], "passes": c["passes"], "gpu_launches": c["kernel_launches"],
+        "exchanges": c["exchanges"], "bytes_exchanged_per_rank": c["bytes_exchanged"], "check": check}))
+  qc.close()
+  if dist is not None:
+    dist.destroy_process_group()
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
   ap.add_argument("--steps", type=int, default=10)
   ap.add_argument("--warmup", type=int, default=3)
-  ap.add_argument("--workload", default="qft30", choices=sorted(WORKLOADS))
+  ap.add_argument("--workload", default="qft30", choices=sorted(WORKLOADS) + list(ALGOS))
+  ap.add_argument("--depth", type=int, default=20)
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   ap.add_argument("--qubits", type=int, default=0, help="override the workload's qubit count (debug)")
   ap.add_argument("--tile-bits", type=int, default=12)
@@ -214,6 +275,8 @@ def main():
   ap.add_argument("--no-secondary", action="store_true")
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+  if args.workload in ALGOS:
+    return run_algorithm(args)
   wl = dict(WORKLOADS[args.workload])
   if args.qubits:
     wl["n"] = args.qubits

@@ -39,7 +39,9 @@ class qc:
   """Quantum circuit: device-resident state + gate surface + IR."""
 
   def __init__(self, name=None, eager: bool = True, *, device: int = 0, fusion: bool = True,
-               tile_bits: int = 12):
+               tile_bits: int = 12, rank: int = 0, nranks: int = 1, comm_id: bytes = None):
+    """rank / nranks / comm_id: this process holds one shard of a state split over nranks GPUs
+    (one process per GPU; see _cabi.DeviceState).  Every gate and readout is then collective."""
     self.name = name
     self.ir = ir.Ir()
     self.eager = eager
@@ -49,6 +51,7 @@ class qc:
     self._device = device
     self._fusion = fusion
     self._tile_bits = tile_bits
+    self._shard = dict(rank=rank, nranks=nranks, comm_id=comm_id)
     self._dev: Optional[_cabi.DeviceState] = None
     self._pending: List[Tuple[str, object, int]] = []   # ('basis', bits, n) | ('dense', vec, n)
 
@@ -69,9 +72,9 @@ class qc:
     return n + sum(f[2] for f in self._pending)
 
   def _new_device_state(self, n: int, label: int = 0) -> _cabi.DeviceState:
-    dev = _cabi.DeviceState(n, label, self._device)
+    dev = _cabi.DeviceState(n, label, self._device, **self._shard)
     dev.set_fusion(self._fusion)
-    if n >= 4:
+    if n - int(math.log2(self._shard["nranks"])) >= 4:
       dev.set_tile_bits(self._tile_bits)
     return dev
 
@@ -82,6 +85,8 @@ class qc:
         raise AssertionError("circuit has no qubits yet")
       return
     total = self.nbits
+    if self._shard["nranks"] > 1 and not (self._dev is None and all(f[0] == "basis" for f in self._pending)):
+      raise NotImplementedError("sharded circuits must be built from basis registers before the first gate")
     if self._dev is None and all(f[0] == "basis" for f in self._pending):
       label = 0
       for _, bits, _ in self._pending:
