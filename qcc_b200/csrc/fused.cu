@@ -62,7 +62,7 @@ struct FusedParams {
   const double2 *outph;
   const int32_t *outbits;
   const uint32_t *jbtab;
-  int debug;  // bit 0: skip the op loop, bit 1: skip the rounds (timing experiments only)
+  int debug;  // timing experiments only -- 1: skip the op loop, 2: skip the rounds, 4: skip the store, 8: skip the load
   int nbuf;   // tile buffers in the shared-memory ring (1 or 2)
   int stagger_ns;  // first-wave start offset between the CTA slots of an SM (see launch_fused_pass)
   int sms;
@@ -244,8 +244,9 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_consta
   };
   auto issue_load = [&](uint32_t t, double2 *buf) {
     const uint64_t b = tile_base(t);
-    for (uint32_t j = tid; j < tileN; j += kFThreads)
-      cp_async16(buf + swz(j), psi + (b | (uint64_t(hi_off[j >> 3]) << 3) | (j & 7u)));
+    if (!(P.debug & 8))
+      for (uint32_t j = tid; j < tileN; j += kFThreads)
+        cp_async16(buf + swz(j), psi + (b | (uint64_t(hi_off[j >> 3]) << 3) | (j & 7u)));
     cp_async_commit();
   };
 
