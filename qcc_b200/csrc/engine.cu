@@ -224,6 +224,7 @@ int run_fused(qb_state *s, const std::vector<QbGate> &gates) {
     dp.outbits = pp.noutbits ? reinterpret_cast<const int32_t *>(dbase + pp.outbits_off) : nullptr;
     dp.outph = pp.outph.empty() ? nullptr : reinterpret_cast<const double2 *>(dbase + pp.outph_off);
     dp.jbtab = reinterpret_cast<const uint32_t *>(dbase + pp.jbtab_off);
+    dp.noutbits = pp.noutbits;
     double sweep = double(s->len) * 32.0;
     {
       ProfScope ps(s, QB_KCLASS_FUSED, sweep);

@@ -66,6 +66,7 @@ struct FusedParams {
   int nbuf;   // tile buffers in the shared-memory ring (1 or 2)
   int stagger_ns;  // first-wave start offset between the CTA slots of an SM (see launch_fused_pass)
   int sms;
+  int nbits_out;  // entries in outbits
   // Pass descriptors travel as kernel parameters (7 KiB of the 32 KiB parameter space): the
   // per-op decode in the hot loop is then LDC from the constant bank (warp-uniform index), which
   // costs neither shared-memory wavefronts nor LSU issue slots.
@@ -200,8 +201,12 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_consta
   const int nbuf = P.nbuf;
   double2 *tiles = reinterpret_cast<double2 *>(smem_raw);               // nbuf x 2^K
   double2 *s_pout = tiles + size_t(nbuf) * tileN;                       // kMaxLadders
-  double2 *s_tab = s_pout + kMaxLadders;                                // ntable
-  uint32_t *hi_off = reinterpret_cast<uint32_t *>(s_tab + P.desc.ntable);  // 2^(K-3)
+  uint32_t *s_active = reinterpret_cast<uint32_t *>(s_pout + kMaxLadders);  // 4 words: ops whose
+                                                                        // outside-tile predicate holds for this tile
+  double2 *s_tab = s_pout + kMaxLadders + 1;                            // ntable
+  double2 *s_outph = s_tab + P.desc.ntable;                             // nout_total (+1 pad)
+  uint32_t *hi_off = reinterpret_cast<uint32_t *>(s_outph + P.desc.nout_total + 1);  // 2^(K-3)
+  int32_t *s_outbits = reinterpret_cast<int32_t *>(hi_off + (tileN >> 3));  // nout_total
   const QbOp *s_ops = P.ops;        // constant bank
   const QbRound *s_rounds = P.rounds;
   const uint32_t tid = threadIdx.x;
@@ -220,6 +225,9 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_consta
   // ---- STAGE (once per CTA): ladder tables, run offsets -> shared memory --------------------
   {
     for (int i = tid; i < P.desc.ntable; i += kFThreads) s_tab[i] = __ldg(P.tables + i);
+    // ladder constants: per-tile factors are rebuilt from these for every tile
+    for (int i = tid; i < P.desc.nout_total; i += kFThreads) s_outph[i] = __ldg(P.outph + i);
+    for (int i = tid; i < P.nbits_out; i += kFThreads) s_outbits[i] = __ldg(P.outbits + i);
     // offset of every 8-amplitude run of a tile, in units of 8 amplitudes
     for (uint32_t h = tid; h < (tileN >> 3); h += kFThreads) {
       uint64_t off = 0;
@@ -234,6 +242,17 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_consta
   // tile number -> index bits outside the tile
   auto tile_base = [&](uint32_t t) {
     uint64_t b = 0, tt = t;
+    if (P.desc.nseg >= 0) {
+#pragma unroll
+      for (int r = 0; r < QB_MAX_SEGS; ++r) {
+        if (r < P.desc.nseg) {
+          const int len = P.desc.seg_len[r];
+          b |= (tt & ((uint64_t(1) << len) - 1)) << P.desc.seg_pos[r];
+          tt >>= len;
+        }
+      }
+      return b;
+    }
     for (int bit = 0; bit < P.nbits; ++bit) {
       if (!((tmask >> bit) & 1)) {
         b |= (tt & 1) << bit;
@@ -260,16 +279,23 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_consta
     double2 *tile = tiles + size_t(cur) * tileN;
     if (nbuf == 2 && more) issue_load(tn, tiles + size_t(cur ^ 1) * tileN);  // prefetch
     const uint64_t base = tile_base(t);
+    // which ops apply to this tile at all (their controls outside the tile): one bit per op
+    if (tid < 64) {
+      const bool on = int(tid) < P.desc.nops && (base & s_ops[tid].gmask) == s_ops[tid].gwant;
+      const uint32_t bal = __ballot_sync(0xffffffffu, on);
+      if ((tid & 31u) == 0) s_active[tid >> 5] = bal;
+    }
     // per-tile constants of the phase ladders (overlaps the wait for the tile's data): one
     // warp per ladder, lane k owns outside bit k, product by butterfly shuffles
     for (int oi = int(tid >> 5); oi < P.desc.nops; oi += kFThreads / 32) {
       const QbOp *op = s_ops + oi;
-      if (op->kind == QB_K_LADDER || op->kind == QB_K_ULADDER) {
+      const int k8 = op->kind & 0xff;
+      if (k8 == QB_K_LADDER || k8 == QB_K_ULADDER) {
         const int lane = int(tid & 31u);
-        const double2 *ph = P.outph + op->outph_off;
+        const double2 *ph = s_outph + op->outph_off;
         double2 c = make_double2(1.0, 0.0);
-        if (lane < op->nout && ((base >> __ldg(P.outbits + op->out_off + lane)) & 1)) c = __ldg(ph + 1 + lane);
-        if (lane == 0) c = cmul(c, __ldg(ph));
+        if (lane < op->nout && ((base >> s_outbits[op->out_off + lane]) & 1)) c = ph[1 + lane];
+        if (lane == 0) c = cmul(c, ph[0]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           double2 d;
@@ -300,35 +326,59 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_consta
         for (int e = 0; e < 8; ++e)
           a[e] = tile[pb ^ ((e & 1) ? d0 : 0u) ^ ((e & 2) ? d1 : 0u) ^ ((e & 4) ? d2 : 0u)];
 
+        // The op loop is software-pipelined by one op: the code word and, for ladder ops, the
+        // three phase factors (per-tile constant, T_lo, T_hi) of op oi+1 are fetched before the
+        // arithmetic of op oi starts, so their LDC/LDS latency hides behind ~70 fp64 instructions
+        // instead of stalling the 4 warps of the SM sub-partition at the top of every op.
+        const uint64_t active = (uint64_t(s_active[1]) << 32) | s_active[0];
+        int ncode = 0;
+        double2 n_sp = make_double2(1.0, 0.0), n_lo = n_sp, n_hi = n_sp;
+        auto prefetch = [&](int oi) {
+          const QbOp *op = s_ops + oi;
+          ncode = op->kind;
+          const int k = ncode & 0xff;
+          if (k == QB_K_ULADDER || k == QB_K_LADDER) {
+            const double2 *tb = s_tab + op->table_off;
+            n_sp = s_pout[op->flags];
+            n_lo = tb[jb & 63u];
+            if (hi_bits) n_hi = tb[64 + (jb >> QB_LADDER_CHUNK)];
+          }
+        };
+        if (ob < oe) prefetch(ob);
 #pragma unroll 1
         for (int oi = ob; oi < oe; ++oi) {
           const QbOp *op = s_ops + oi;
-          if ((base & op->gmask) != op->gwant) continue;                  // uniform per tile
-          const int kind = op->kind, tp = op->tpos;
-          const uint32_t rmask = op->rmask, rwant = op->rwant;
-          const int4 h1 = make_int4(0, 0, op->table_off, op->flags);
-          const int4 h0 = make_int4(0, 0, int(op->lmask), int(op->lwant));
+          const int code = ncode;
+          const double2 sp = n_sp, tlo = n_lo, thi = n_hi;
+          if (oi + 1 < oe) prefetch(oi + 1);
+          if (!((active >> oi) & 1)) continue;                            // uniform per tile
+          const int kind = code & 0xff, tp = (code >> 8) & 0xff;
+          const bool real = (code >> 16) & QB_MF_REAL;
           const double2 *mp = reinterpret_cast<const double2 *>(op->m);
           if (kind == QB_K_ULADDER) {  // uncontrolled by construction
-            const double2 *tb = s_tab + h1.z;
-            const double2 *F = tb + 64 + (1 << hi_bits);
-            double2 c = cmul(s_pout[h1.w], tb[jb & 63u]);
-            if (hi_bits) c = cmul(c, tb[64 + (jb >> QB_LADDER_CHUNK)]);
-            const Mat m{mp[0], mp[1], mp[2], mp[3]};
-            if (op->mflags & QB_MF_REAL)
+            const double2 *F = s_tab + op->table_off + 64 + (1 << hi_bits);
+            double2 c = cmul(sp, tlo);
+            if (hi_bits) c = cmul(c, thi);
+            if (real) {
+              Mat m;
+              m.a.x = mp[0].x; m.b.x = mp[1].x; m.c.x = mp[2].x; m.d.x = mp[3].x;
               QB_DISPATCH_TP(tp, (uladder<0, true>(a, m, c, F)), (uladder<1, true>(a, m, c, F)),
                              (uladder<2, true>(a, m, c, F)));
-            else
+            } else {
+              const Mat m{mp[0], mp[1], mp[2], mp[3]};
               QB_DISPATCH_TP(tp, (uladder<0, false>(a, m, c, F)), (uladder<1, false>(a, m, c, F)),
                              (uladder<2, false>(a, m, c, F)));
+            }
             continue;
           }
+          const uint32_t rmask = op->rmask, rwant = op->rwant;
+          const int4 h0 = make_int4(0, 0, int(op->lmask), int(op->lwant));
           if ((jb & uint32_t(h0.z)) != uint32_t(h0.w)) continue;         // per group
           switch (kind) {
             case QB_K_U: {
               const Mat m{mp[0], mp[1], mp[2], mp[3]};
               if (rmask == 0) {
-                if (op->mflags & QB_MF_REAL)
+                if (real)
                   QB_DISPATCH_TP(tp, (bfly_all<0, true>(a, m)), (bfly_all<1, true>(a, m)), (bfly_all<2, true>(a, m)));
                 else
                   QB_DISPATCH_TP(tp, (bfly_all<0, false>(a, m)), (bfly_all<1, false>(a, m)),
@@ -358,10 +408,9 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_consta
               break;
             }
             case QB_K_LADDER: {
-              const double2 *tb = s_tab + h1.z;
-              const double2 *F = tb + 64 + (1 << hi_bits);
-              double2 c = cmul(s_pout[h1.w], tb[jb & 63u]);
-              if (hi_bits) c = cmul(c, tb[64 + (jb >> QB_LADDER_CHUNK)]);
+              const double2 *F = s_tab + op->table_off + 64 + (1 << hi_bits);
+              double2 c = cmul(sp, tlo);
+              if (hi_bits) c = cmul(c, thi);
 #pragma unroll
               for (int e = 0; e < 8; ++e)
                 if ((uint32_t(e) & rmask) == rwant) a[e] = cmul(cmul(c, F[e]), a[e]);
@@ -388,9 +437,10 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_consta
   }
 }
 
-size_t fused_smem_bytes(int K, int ntable, int nbuf) {
-  return size_t(nbuf) * (size_t(1) << K) * sizeof(double2) + kMaxLadders * sizeof(double2) +
-         size_t(ntable) * sizeof(double2) + (size_t(1) << (K - 3)) * sizeof(uint32_t);
+size_t fused_smem_bytes(int K, int ntable, int nbuf, int nout_total) {
+  return size_t(nbuf) * (size_t(1) << K) * sizeof(double2) + (kMaxLadders + 1) * sizeof(double2) +
+         size_t(ntable) * sizeof(double2) + (size_t(1) << (K - 3)) * sizeof(uint32_t) +
+         size_t(nout_total + 1) * sizeof(double2) + size_t(nout_total + 4) * sizeof(int32_t);
 }
 
 constexpr size_t kSmemLimit = 227 * 1024;
@@ -418,6 +468,7 @@ cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cuda
   P.outph = p.outph;
   P.outbits = p.outbits;
   P.jbtab = p.jbtab;
+  P.nbits_out = p.noutbits;
   static const int dbg = getenv("QCC_B200_FUSED_DEBUG") ? atoi(getenv("QCC_B200_FUSED_DEBUG")) : 0;
   static const int force_nbuf = getenv("QCC_B200_FUSED_NBUF") ? atoi(getenv("QCC_B200_FUSED_NBUF")) : 0;
   P.debug = dbg;
@@ -433,11 +484,16 @@ cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cuda
   // without spilling; at 3 CTAs / 80 registers the spills and ladder-table misses cost more
   // than the extra CTA gains).  QCC_B200_FUSED_NBUF=2 selects the persistent two-deep cp.async
   // ring instead (one CTA per SM); measured slower (profiles/r01_fused_experiments.md).
-  int nbuf = force_nbuf == 2 && fused_smem_bytes(K, p.desc.ntable, 2) <= kSmemLimit ? 2 : 1;
-  const size_t smem = fused_smem_bytes(K, p.desc.ntable, nbuf);
+  int nbuf = force_nbuf == 2 && fused_smem_bytes(K, p.desc.ntable, 2, p.desc.nout_total) <= kSmemLimit ? 2 : 1;
+  const size_t smem = fused_smem_bytes(K, p.desc.ntable, nbuf, p.desc.nout_total);
   if (smem > kSmemLimit) return cudaErrorInvalidValue;
   P.nbuf = nbuf;
+  // Persistent CTAs: 2 per SM, each walking tiles blockIdx.x, +grid, ... so that the per-CTA
+  // staging (26 KiB of ladder tables, run offsets) is paid once per SM slot, not once per tile
+  // (it was 3.5 of 16 ms per pass when every tile had its own CTA).
+  static const int persist = getenv("QCC_B200_FUSED_PERSIST") ? atoi(getenv("QCC_B200_FUSED_PERSIST")) : 2;
   unsigned blocks = ntiles;
+  if (persist > 0 && ntiles > unsigned(persist * g_sms)) blocks = unsigned(persist * g_sms);
   if (nbuf == 2) blocks = ntiles < unsigned(g_sms) ? ntiles : unsigned(g_sms);
   k_fused_pass<<<blocks, kFThreads, smem, st>>>(P);
   return cudaGetLastError();

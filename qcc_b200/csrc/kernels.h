@@ -43,6 +43,7 @@ struct DevicePass {
   const double2 *outph;   // device (ladder per-tile constant + outside-bit phases) or nullptr
   const int32_t *outbits; // device (ladder outside-bit lists) or nullptr
   const uint32_t *jbtab;  // device (per round, per group: base index | swizzled slot << 16)
+  int noutbits = 0;       // entries in outbits
 };
 cudaError_t fused_configure(int device);  // opt in to large dynamic shared memory, query SM count
 cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cudaStream_t st);

@@ -412,6 +412,8 @@ void close_round(const TileMap &tm, std::vector<int> &rset, std::vector<PendingO
     if ((op.kind == QB_K_U || op.kind == QB_K_ULADDER || op.kind == QB_K_PERM) && op.m[1] == 0.0 &&
         op.m[3] == 0.0 && op.m[5] == 0.0 && op.m[7] == 0.0)
       op.mflags |= QB_MF_REAL;
+    // the kernel decodes one word per op: kind | tpos << 8 | mflags << 16
+    op.kind = (op.kind & 0xff) | ((op.tpos & 0xff) << 8) | ((op.mflags & 0xff) << 16);
     pp->ops.push_back(op);
   }
   r.op_end = int32_t(pp->ops.size());
@@ -474,6 +476,29 @@ void emit_pass(int nbits, int K, const std::vector<const Item *> &items, const s
   pp.desc.nops = int32_t(pp.ops.size());
   pp.desc.ntable = int32_t(pp.tables.size());
   pp.desc.ngroups_log2 = tm.K - 3;
+  // runs of consecutive non-tile bits: the kernel scatters the tile number over them
+  {
+    int nseg = 0;
+    bool overflow = false;
+    for (int b = 0; b < nbits;) {
+      if (tm.mask >> b & 1) {
+        ++b;
+        continue;
+      }
+      int e = b;
+      while (e < nbits && !(tm.mask >> e & 1)) ++e;
+      if (nseg < QB_MAX_SEGS) {
+        pp.desc.seg_pos[nseg] = b;
+        pp.desc.seg_len[nseg] = e - b;
+        ++nseg;
+      } else {
+        overflow = true;
+      }
+      b = e;
+    }
+    pp.desc.nseg = overflow ? -1 : nseg;
+  }
+  pp.desc.nout_total = int32_t(pp.outph.size());
   pp.noutbits = int(pp.outbits.size());
   out->passes.push_back(std::move(pp));
 }

@@ -60,11 +60,12 @@ struct QbGate {
 #define QB_LADDER_CHUNK 6    // ladder lookup tables are indexed by 6 tile-local bits
 #define QB_MAX_PASS_OPS 48   // ops of one pass are staged in shared memory (48 * 128 B)
 #define QB_MAX_PASS_ROUNDS 16
+#define QB_MAX_SEGS 6
 #define QB_MAX_PASS_LADDERS 12  // their lookup tables (<= 200 x 16 B each) are staged in shared memory too
 #define QB_MF_REAL 1         // all four entries of m are real: 8 instead of 20 flops per pair
 
 struct alignas(16) QbOp {   // 128 bytes, read by the kernel as 16-byte pieces
-  int32_t kind;      // QbKind (never DIAG/NOP: the planner lowers those)
+  int32_t kind;      // QbKind (never DIAG/NOP: the planner lowers those) | tpos << 8 | mflags << 16
   int32_t tpos;      // U/PERM/SWAP: target position inside rbit[]
   uint32_t lmask, lwant;
   uint32_t rmask, rwant;
@@ -91,6 +92,10 @@ struct QbPassDesc {
   int32_t nops;
   int32_t ntable;                      // double2 entries in the (staged) ladder table buffer
   int32_t ngroups_log2;                // K - 3
+  int32_t nseg;                        // runs of consecutive non-tile index bits (tile number -> base)
+  int32_t seg_pos[QB_MAX_SEGS];        // first index bit of run r
+  int32_t seg_len[QB_MAX_SEGS];        // its length; nseg > QB_MAX_SEGS is flagged as nseg = -1 (generic loop)
+  int32_t nout_total;                  // entries in the pass's outside-bit / outside-phase arrays
   int32_t pad_;
   int32_t tile_bits[QB_MAX_TILE_BITS + 3];  // index-bit positions, ascending
   uint64_t tile_mask;                  // OR of 1 << tile_bits[k]

@@ -134,7 +134,8 @@ def interpret_plan(plan_json: str, n: int, gates, psi: np.ndarray) -> np.ndarray
         ok = tile_ok[:, None] & grp_ok[None, :]                        # [tile, group]
         m = np.array(op["m"]).view(np.complex128) if False else np.array(
             [complex(op["m"][2 * i], op["m"][2 * i + 1]) for i in range(4)])
-        kind = op["kind"]
+        kind = op["kind"] & 0xFF
+        assert (op["kind"] >> 8) & 0xFF == op["tpos"] and (op["kind"] >> 16) & 0xFF == op["mflags"]
         if kind in (K_U, K_PERM, K_SWAP):
           tp = op["tpos"]
           for e in range(8):
@@ -201,5 +202,5 @@ def plan_summary(plan_json: str):
       "singles": len(plan["passes"]) - len(fused),
       "rounds": sum(len(p["rounds"]) for p in fused),
       "ops": sum(len(p["ops"]) for p in fused),
-      "ladders": sum(1 for p in fused for o in p["ops"] if o["kind"] in (K_LADDER, K_ULADDER)),
+      "ladders": sum(1 for p in fused for o in p["ops"] if o["kind"] & 0xFF in (K_LADDER, K_ULADDER)),
   }
