@@ -20,11 +20,12 @@ in the same timed region (qb_profile_*), against MEASURED_PEAKS.json's hbm_gbs.
 `cpu_baseline` times the reference's own xgates build (oracle/_ref/libxgates.so, 1 thread --
 the reference has no threading) on a bounded sample of the same gate stream.
 
-N > 1 (torchrun): ONE state of n + log2(N) qubits is sharded over the N GPUs by its top index
-bits (each GPU keeps a 2^n shard, so per-GPU memory and work are fixed: weak scaling).  Gates on
-sharded qubits cost a pairwise half-shard exchange over NVLink (ncclSend/ncclRecv) and a bit
-remap; diagonal gates and controls on sharded qubits cost nothing extra.  `value` is the gate
-count of the one big circuit / max-over-ranks time; exchange bytes and GB/s are reported.
+N > 1 (torchrun): the SAME workload (same qubit count, same gate stream) with its state sharded
+over the N GPUs by the top log2(N) index bits -- strong scaling, so metric and config do not
+change with N.  Gates on sharded qubits cost a pairwise half-shard exchange over NVLink
+(ncclSend/ncclRecv) and a bit remap; diagonal gates and controls on sharded qubits cost nothing
+extra.  `value` is gates / max-over-ranks time; exchange counts, bytes and GB/s are reported.
+--weak instead grows the state to n + log2(N) qubits (16 GiB per GPU at every N).
 """
 import argparse
 import json
@@ -196,7 +197,7 @@ def run_reference_arm(args, wl, stream):
   print(json.dumps({
       "impl": "reference", "metric": "gate-applies/sec", "value": value, "unit": "gates/s",
       "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-      "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+      "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
       "vs_baseline": None, "dtype": "f64", "data": "synthetic",
       "config": {"workload": args.workload, "desc": wl["desc"], "qubits": n, "gates_per_step": per_step},
       "cpu_baseline": {"value": value, "unit": "gates/s", "cores": 1, "kind": "reference", "sample": sample},
@@ -273,6 +274,7 @@ def main():
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-e2e", action="store_true")
   ap.add_argument("--no-secondary", action="store_true")
+  ap.add_argument("--weak", action="store_true", help="N > 1: grow the state to n + log2(N) qubits")
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
   if args.workload in ALGOS:
@@ -306,9 +308,12 @@ def main():
     ids = [_cabi.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     comm_id = ids[0]
-    n = n_shard + int(np.log2(world))       # one bigger state, same shard per GPU
-    wl["n"] = n
-    stream = build_stream(args.workload, n)
+    if args.weak:
+      n = n_shard + int(np.log2(world))     # one bigger state, same shard per GPU
+      wl["n"] = n
+      stream = build_stream(args.workload, n)
+    else:
+      n_shard = n - int(np.log2(world))
   packed = _cabi.pack_xg_gates(stream)
   ngates = len(stream)
   s = _cabi.DeviceState(n, 0, local_rank, rank=rank, nranks=world, comm_id=comm_id)
@@ -467,8 +472,8 @@ def main():
     line = {
         "metric": "gate-applies/sec", "value": value, "unit": "gates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak" if (args.weak and world > 1) else "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "desc": wl["desc"], "qubits": n, "gates_per_step": ngates,
                    "state_bytes": (1 << n) * 16, "l2": "state (>= 4 GiB) >> 126 MB L2; no flush needed",
                    "fusion": wl["fusion"], "tile_bits": args.tile_bits if wl["fusion"] else None,

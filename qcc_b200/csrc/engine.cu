@@ -81,6 +81,8 @@ struct qb_state {
   ncclComm_t comm = nullptr;
   double2 *xbuf = nullptr;        // half-shard receive buffer for exchanges
   size_t xbuf_bytes = 0;
+  cudaStream_t xstream = nullptr; // copy-back of received pieces overlaps the next piece's transfer
+  std::vector<cudaEvent_t> xevents;
   cudaStream_t stream = nullptr;
   double2 *psi = nullptr;
   bool fusion = true;
@@ -263,6 +265,8 @@ int do_exchange(qb_state *s, int rank_bit, int victim) {
   const size_t half_bytes = size_t(s->len / 2) * sizeof(double2);
   if (s->xbuf_bytes < half_bytes) {
     if (s->xbuf) cudaFree(s->xbuf);
+  for (auto e : s->xevents) cudaEventDestroy(e);
+  if (s->xstream) cudaStreamDestroy(s->xstream);
     s->xbuf = nullptr;
     s->xbuf_bytes = 0;
     cudaError_t e = cudaMalloc(&s->xbuf, half_bytes);
@@ -270,17 +274,32 @@ int do_exchange(qb_state *s, int rank_bit, int victim) {
     s->xbuf_bytes = half_bytes;
   }
   {
+    // Pipelined in pieces of <= 1 GiB: while piece k+1 crosses NVLink, piece k is copied from
+    // the receive buffer back into the shard on a second stream.
     ProfScope ps(s, QB_KCLASS_EXCHANGE, double(half_bytes));
-    NC(nc, nc->GroupStart());
-    for (uint64_t h = 0; h < nruns; ++h) {
-      const uint64_t off = (h << (victim + 1)) | (sel << victim);
-      NC(nc, nc->Send(s->psi + off, size_t(run) * 2, ncclDouble, partner, s->comm, s->stream));
-      NC(nc, nc->Recv(s->xbuf + h * run, size_t(run) * 2, ncclDouble, partner, s->comm, s->stream));
+    if (!s->xstream) CU(cudaStreamCreateWithFlags(&s->xstream, cudaStreamNonBlocking));
+    const uint64_t piece = std::min<uint64_t>(run, uint64_t(1) << 26);
+    const uint64_t per_run = run / piece;
+    const uint64_t npieces = nruns * per_run;
+    while (s->xevents.size() < 2) {
+      cudaEvent_t e = nullptr;
+      CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      s->xevents.push_back(e);
     }
-    NC(nc, nc->GroupEnd());
-    CU(cudaMemcpy2DAsync(s->psi + (sel << victim), size_t(run) * 2 * sizeof(double2), s->xbuf,
-                         size_t(run) * sizeof(double2), size_t(run) * sizeof(double2), size_t(nruns),
-                         cudaMemcpyDeviceToDevice, s->stream));
+    for (uint64_t k = 0; k < npieces; ++k) {
+      const uint64_t h = k / per_run, w = k % per_run;
+      const uint64_t off = (h << (victim + 1)) | (sel << victim) | (w * piece);
+      double2 *rx = s->xbuf + k * piece;
+      NC(nc, nc->GroupStart());
+      NC(nc, nc->Send(s->psi + off, size_t(piece) * 2, ncclDouble, partner, s->comm, s->stream));
+      NC(nc, nc->Recv(rx, size_t(piece) * 2, ncclDouble, partner, s->comm, s->stream));
+      NC(nc, nc->GroupEnd());
+      CU(cudaEventRecord(s->xevents[0], s->stream));
+      CU(cudaStreamWaitEvent(s->xstream, s->xevents[0], 0));
+      CU(cudaMemcpyAsync(s->psi + off, rx, size_t(piece) * sizeof(double2), cudaMemcpyDeviceToDevice, s->xstream));
+    }
+    CU(cudaEventRecord(s->xevents[1], s->xstream));
+    CU(cudaStreamWaitEvent(s->stream, s->xevents[1], 0));
   }
   s->cnt.exchanges += 1;
   s->cnt.bytes_exchanged += half_bytes;
@@ -534,6 +553,8 @@ int qb_state_destroy(qb_state *s) {
     if (nc) nc->CommDestroy(s->comm);
   }
   if (s->xbuf) cudaFree(s->xbuf);
+  for (auto e : s->xevents) cudaEventDestroy(e);
+  if (s->xstream) cudaStreamDestroy(s->xstream);
   if (s->psi) cudaFree(s->psi);
   if (s->d_scalar) cudaFree(s->d_scalar);
   if (s->d_counter) cudaFree(s->d_counter);

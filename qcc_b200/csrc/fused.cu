@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_consta
           if (k == QB_K_ULADDER || k == QB_K_LADDER) {
             const double2 *tb = s_tab + op->table_off;
             n_sp = s_pout[op->flags];
-            n_lo = tb[jb & 63u];
+            n_lo = tb[(jb & 63u) ^ ((jb >> 3) & 7u)];
             if (hi_bits) n_hi = tb[64 + (jb >> QB_LADDER_CHUNK)];
           }
         };
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_consta
           const bool real = (code >> 16) & QB_MF_REAL;
           const double2 *mp = reinterpret_cast<const double2 *>(op->m);
           if (kind == QB_K_ULADDER) {  // uncontrolled by construction
-            const double2 *F = s_tab + op->table_off + 64 + (1 << hi_bits);
+            const double2 *F = reinterpret_cast<const double2 *>(op->F);  // constant bank
             double2 c = cmul(sp, tlo);
             if (hi_bits) c = cmul(c, thi);
             if (real) {
@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_consta
               break;
             }
             case QB_K_LADDER: {
-              const double2 *F = s_tab + op->table_off + 64 + (1 << hi_bits);
+              const double2 *F = reinterpret_cast<const double2 *>(op->F);
               double2 c = cmul(sp, tlo);
               if (hi_bits) c = cmul(c, thi);
 #pragma unroll
@@ -449,7 +449,7 @@ int g_sms = 0;
 }  // namespace
 
 cudaError_t fused_configure(int device) {
-  static_assert(sizeof(QbOp) == 128, "QbOp is read as 16-byte pieces");
+  static_assert(sizeof(QbOp) == 256, "QbOp layout");
   static_assert(sizeof(QbRound) % 4 == 0 && (QB_MAX_PASS_OPS * sizeof(QbOp)) % 16 == 0, "smem layout");
   cudaError_t err = cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, device);
   if (err != cudaSuccess) return err;

@@ -288,20 +288,22 @@ void build_ladder_tables(const TileMap &tm, const QbRound &r, const Item &it, in
     self_out = Cplx{1.0, 0.0};
   }
   // Table layout (double2 units from table_off):
-  //   [0, 64)            T_lo[j & 63]
+  //   [0, 64)            T_lo[j & 63], stored at slot v ^ ((v >> 3) & 7) so that lanes whose
+  //                      base indices differ in bits 3..5 hit different 16-byte bank groups
   //   [64, 64 + 2^hi)    T_hi[j >> 6]
-  //   next 8             F[e]   product over round bits set in e
-  // T_lo / T_hi are evaluated on the group base (round bits zero), F covers the round bits.
+  // T_lo / T_hi are evaluated on the group base (round bits zero); the 8 combinations of the
+  // round's own bits, F[e], travel inside the op descriptor (constant bank).
   // The per-tile constant lives in a second array (outph, from outph_off): the constant
   // factor (self phase when the pivot is outside the tile), then one phase per outside bit.
   op->table_off = int32_t(pp->tables.size());
   bool is_round[QB_MAX_TILE_BITS] = {false};
   for (int k = 0; k < r.nbits; ++k) is_round[r.rbit[k]] = true;
+  pp->tables.resize(pp->tables.size() + 64);
   for (int v = 0; v < 64; ++v) {
     Cplx p{1.0, 0.0};
     for (int k = 0; k < lo_bits; ++k)
       if ((v >> k & 1) && !is_round[k]) p = cmulh(p, per[k]);
-    pp->tables.push_back(p);
+    pp->tables[size_t(op->table_off) + size_t(v ^ ((v >> 3) & 7))] = p;
   }
   for (int v = 0; v < (1 << hi_bits); ++v) {
     Cplx p{1.0, 0.0};
@@ -313,7 +315,8 @@ void build_ladder_tables(const TileMap &tm, const QbRound &r, const Item &it, in
     Cplx p{1.0, 0.0};
     for (int k = 0; k < r.nbits; ++k)
       if (e >> k & 1) p = cmulh(p, per[r.rbit[k]]);
-    pp->tables.push_back(p);
+    op->F[2 * e] = p.x;
+    op->F[2 * e + 1] = p.y;
   }
   op->outph_off = int32_t(pp->outph.size());
   pp->outph.push_back(self_out);
@@ -662,6 +665,11 @@ std::string Plan::to_json() const {
       s += buf;
       for (int k = 0; k < 8; ++k) {
         snprintf(buf, sizeof buf, "%s%.17g", k ? "," : "", O.m[k]);
+        s += buf;
+      }
+      s += "],\"F\":[";
+      for (int k = 0; k < 16; ++k) {
+        snprintf(buf, sizeof buf, "%s%.17g", k ? "," : "", O.F[k]);
         s += buf;
       }
       s += "]}";

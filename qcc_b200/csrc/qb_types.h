@@ -58,13 +58,13 @@ struct QbGate {
 #define QB_MAX_TILE_BITS 13  // 2^13 * 16 B = 128 KiB
 #define QB_ROUND_BITS 3      // 8 amplitudes = 16 doubles in registers per thread
 #define QB_LADDER_CHUNK 6    // ladder lookup tables are indexed by 6 tile-local bits
-#define QB_MAX_PASS_OPS 48   // ops of one pass are staged in shared memory (48 * 128 B)
+#define QB_MAX_PASS_OPS 48   // ops of one pass travel as kernel parameters (48 * 256 B)
 #define QB_MAX_PASS_ROUNDS 16
 #define QB_MAX_SEGS 6
 #define QB_MAX_PASS_LADDERS 12  // their lookup tables (<= 200 x 16 B each) are staged in shared memory too
 #define QB_MF_REAL 1         // all four entries of m are real: 8 instead of 20 flops per pair
 
-struct alignas(16) QbOp {   // 128 bytes, read by the kernel as 16-byte pieces
+struct alignas(16) QbOp {   // 256 bytes; lives in the kernel parameters (constant bank)
   int32_t kind;      // QbKind (never DIAG/NOP: the planner lowers those) | tpos << 8 | mflags << 16
   int32_t tpos;      // U/PERM/SWAP: target position inside rbit[]
   uint32_t lmask, lwant;
@@ -77,6 +77,7 @@ struct alignas(16) QbOp {   // 128 bytes, read by the kernel as 16-byte pieces
   int32_t out_off;   // LADDER: first entry in the pass's outside-bit array
   int32_t mflags;    // QB_MF_* properties of m
   int32_t outph_off; // LADDER: first entry in the pass's outside-phase array ([0] = constant factor)
+  double F[16];      // LADDER: phase of the round's own bits for each of the 8 registers (re, im)
 };
 
 struct QbRound {

@@ -178,10 +178,11 @@ def interpret_plan(plan_json: str, n: int, gates, psi: np.ndarray) -> np.ndarray
           for k in range(op["nout"]):
             bit = outbits[op["out_off"] + k]
             pout = np.where((base >> bit) & 1 == 1, pout * outph[cbase + 1 + k], pout)
-          c = pout[:, None] * tables[t0 + (jb & 63)][None, :]
+          lo = jb & 63
+          c = pout[:, None] * tables[t0 + (lo ^ ((lo >> 3) & 7))][None, :]   # T_lo is stored bank-swizzled
           if hi_bits:
             c = c * tables[t0 + 64 + (jb >> 6)][None, :]
-          F = tables[t0 + 64 + (1 << hi_bits): t0 + 64 + (1 << hi_bits) + 8]
+          F = np.array([complex(op["F"][2 * e], op["F"][2 * e + 1]) for e in range(8)])
           for e in range(8):
             if (e & lad_rmask) == lad_rwant:
               A[:, :, e] = np.where(ok, c * F[e] * A[:, :, e], A[:, :, e])
