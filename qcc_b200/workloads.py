@@ -143,3 +143,36 @@ def grover_circuit(nbits: int, marked: int = None, *, device: int = 0, qc_factor
     qc.x(idx)
     qc.h(idx)
   return qc, bits
+
+
+def qft_adder(n: int, init_a: int, init_b: int, factor: float = 1.0, *, eager: bool = True, qc_factory=None):
+  """a + factor * b with the QFT adder of arith_quantum.py:43-75 on two (n+1)-qubit registers
+  (n = 12, a = 2, b = 3 is the 26-qubit circuit behind src/libq/libq_arith_test.cc).
+  Returns (qc, a_register, b_register); the sum is read from the a register, least
+  significant bit first (arith_quantum.py:36)."""
+  from qcc_b200 import circuit, helper
+  qc = qc_factory("qadd") if qc_factory else circuit.qc("qadd", eager=eager)
+  a = qc.reg(n + 1, helper.val2bits(init_a, n)[::-1], name="a")
+  b = qc.reg(n + 1, helper.val2bits(init_b, n)[::-1], name="b")
+
+  def qft_step(reg, k):                       # arith_quantum.py:43-46
+    qc.h(reg[k])
+    for i in range(k):
+      qc.cu1(reg[k - (i + 1)], reg[k], math.pi / float(2 ** (i + 1)))
+
+  def evolve(k):                              # arith_quantum.py:49-52
+    for i in range(k + 1):
+      qc.cu1(b[k - i], a[k], factor * math.pi / float(2 ** i))
+
+  def inverse_qft_step(reg, k):               # arith_quantum.py:55-58
+    for i in range(k):
+      qc.cu1(reg[i], reg[k], -1 * math.pi / float(2 ** (k - i)))
+    qc.h(reg[k])
+
+  for i in range(n + 1):
+    qft_step(a, n - i)
+  for i in range(n + 1):
+    evolve(n - i)
+  for i in range(n + 1):
+    inverse_qft_step(a, i)
+  return qc, a, b

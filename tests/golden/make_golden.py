@@ -316,6 +316,12 @@ def libq_cases():
     with open(os.path.join(HERE, t + ".out"), "w") as f:
       f.write(out)
     print("wrote", t + ".out")
+  # fingerprint of the libq:: call sequence of the reference's generated adder test (the file
+  # itself is reference source and is not copied): our transpiler must reproduce it exactly
+  import hashlib
+  lines = [l.strip() for l in open(os.path.join(REF, "src/libq/libq_arith_test.cc")) if l.strip().startswith("libq::")]
+  with open(os.path.join(HERE, "libq_arith_test.calls.sha256"), "w") as f:
+    f.write(f"{hashlib.sha256(chr(10).join(lines).encode()).hexdigest()} {len(lines)}\n")
 
 
 if __name__ == "__main__":

@@ -135,3 +135,16 @@ def test_libq_programs_compile_against_our_header(src, tmp_path):
          "-Wl,-rpath," + os.path.join(ROOT, "qcc_b200", "lib"), "-o", str(exe)]
   subprocess.run(cmd, check=True, capture_output=True)
   assert exe.exists()
+
+
+def test_transpiled_adder_reproduces_the_reference_test_program():
+  """arith_quantum.py's 12-bit adder on our surface, transpiled, gives exactly the
+  libq:: call sequence of the reference's generated src/libq/libq_arith_test.cc (fingerprint
+  recorded by make_golden.py; 280 calls)."""
+  import hashlib
+  from qcc_b200 import workloads
+  qc, _, _ = workloads.qft_adder(12, 2, 3, eager=False)
+  lines = [l.strip() for l in qc.libq().splitlines() if l.strip().startswith("libq::")]
+  want, count = open(os.path.join(GOLDEN, "libq_arith_test.calls.sha256")).read().split()
+  assert len(lines) == int(count)
+  assert hashlib.sha256("\n".join(lines).encode()).hexdigest() == want

@@ -285,3 +285,48 @@ def test_libxgates_shim_is_a_drop_in():
     libxgates.apply1(np.zeros(4, dtype=np.complex64), np.eye(2).reshape(4), 2, 0, 128)
   with pytest.raises(ValueError):
     libxgates.apply1(np.zeros(4, dtype=np.complex128), np.eye(2, dtype=np.complex128).reshape(4) * 1j, 2, 2, 128)
+
+
+# ---------------------------------------------------------------------------------------
+# the QFT adder behind src/libq/libq_arith_test.cc, end to end on both faces
+# ---------------------------------------------------------------------------------------
+def _arith_golden_label():
+  text = open(os.path.join(GOLDEN, "libq_arith_test.out")).read()
+  got = parse_print_qureg(text)
+  assert len(got) == 1
+  return next(iter(got))                      # 24581
+
+
+def test_qft_adder_26_qubits_python_face():
+  from qcc_b200 import helper
+  n = 12
+  qc, a, _ = workloads.qft_adder(n, 2, 3)
+  assert qc.nbits == 26
+  maxbits, p = qc.psi.maxprob()
+  assert abs(p - 1.0) < 1e-9
+  assert helper.bits2val(maxbits[0:n + 1][::-1]) == 5          # arith_quantum.py:34-39
+  # same basis state as the reference's libq run of this circuit, up to the bit reversal between faces
+  label = sum(bit << q for q, bit in enumerate(maxbits))       # python qubit q == libq bit q
+  assert label == _arith_golden_label()
+  labels, amps, total = qc.psi.nonzero(1e-9)
+  assert total == 1 and abs(amps[0] - 1.0) < 1e-9
+
+
+def test_qft_adder_transpiled_to_libq(tmp_path):
+  """circuit.qc (non-eager) -> qc.libq() -> g++ against our libq.h -> run: prints the same single
+  basis state the reference's own libq build prints for src/libq/libq_arith_test.cc."""
+  qc, _, _ = workloads.qft_adder(12, 2, 3, eager=False)
+  src = tmp_path / "adder.cc"
+  src.write_text(qc.libq())
+  exe = tmp_path / "adder"
+  lib = os.path.join(ROOT, "qcc_b200", "lib")
+  subprocess.run(["g++", "-O1", "-I" + os.path.join(ROOT, "qcc_b200", "libq"), str(src), "-L" + lib,
+                  "-lqcc_libq", "-lqcc_b200", "-Wl,-rpath," + lib, "-o", str(exe)], check=True, capture_output=True)
+  out = subprocess.run([str(exe)], check=True, capture_output=True, text=True, timeout=300).stdout
+  got = parse_print_qureg(out)
+  assert list(got) == [_arith_golden_label()]
+  amp, prob, bits = got[_arith_golden_label()]
+  assert abs(amp - 1.0) < 1e-5 and abs(prob - 1.0) < 1e-5
+  ref = parse_print_qureg(open(os.path.join(GOLDEN, "libq_arith_test.out")).read())
+  assert bits == ref[_arith_golden_label()][2]
+  assert "# of qubits        : 26" in out
