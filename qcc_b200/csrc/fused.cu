@@ -177,6 +177,24 @@ __device__ __forceinline__ void uladder(double2 (&a)[8], const Mat &m, double2 c
   }
 }
 
+// The QFT case: U = r * [[1, 1], [1, -1]] (Hadamard) on the pivot, then the ladder.  The scale r
+// is folded into the phase, so a pair costs 14 fp64 instructions instead of 16:
+//   x' = r (x + y),   y' = (x - y) * (r * cf * F[e1]);  F[pivot only] is exactly 1 by construction
+// (the planner moves the pivot's own phase into the per-tile constant).
+template <int TP>
+__device__ __forceinline__ void hladder(double2 (&a)[8], double r, double2 cf, const double2 *F) {
+  const double2 cr = make_double2(r * cf.x, r * cf.y);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    if (e & (1 << TP)) continue;
+    const double2 x = a[e], y = a[e | (1 << TP)];
+    const double2 ph = (e == 0) ? cr : cmul(cr, F[e | (1 << TP)]);
+    const double2 d = make_double2(x.x - y.x, x.y - y.y);
+    a[e] = make_double2(r * (x.x + y.x), r * (x.y + y.y));
+    a[e | (1 << TP)] = cmul(d, ph);
+  }
+}
+
 #define QB_DISPATCH_TP(tp, CALL0, CALL1, CALL2) \
   do {                                          \
     if ((tp) == 0) { CALL0; }                   \
@@ -194,6 +212,13 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+// FULL: the tile has a multiple of 256 groups (K >= 11), so the group loop has a trip count that
+// is uniform across the CTA and needs no bounds test.  That matters beyond the saved compare: with a
+// thread-dependent loop condition the compiler must treat the op loop inside as divergent and keeps
+// the op index -- and with it every descriptor load -- in vector registers (vector-indexed LDC,
+// vector compares and branches per op); with a uniform trip count the decode runs on the uniform
+// datapath.
+template <bool FULL>
 __global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_constant__ FusedParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int K = P.desc.K;
@@ -318,7 +343,10 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_consta
       const uint32_t d2 = swz(1u << R->rbit[2]);
       const int ob = R->op_begin, oe = (P.debug & 1) ? R->op_begin : R->op_end;
       const uint32_t *jbt = P.jbtab + (size_t(r) << P.desc.ngroups_log2);
-      for (uint32_t q = tid; q < ngroups; q += kFThreads) {
+      const uint32_t giters = FULL ? (ngroups / kFThreads) : ((ngroups + kFThreads - 1) / kFThreads);
+      for (uint32_t git = 0; git < giters; ++git) {
+        const uint32_t q = git * kFThreads + tid;
+        if (!FULL && q >= ngroups) break;
         const uint32_t w = __ldg(jbt + q);
         const uint32_t jb = w & 0xffffu, pb = w >> 16;
         double2 a[8];
@@ -326,91 +354,74 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_consta
         for (int e = 0; e < 8; ++e)
           a[e] = tile[pb ^ ((e & 1) ? d0 : 0u) ^ ((e & 2) ? d1 : 0u) ^ ((e & 4) ? d2 : 0u)];
 
-        // The op loop is software-pipelined by one op: the code word and, for ladder ops, the
-        // three phase factors (per-tile constant, T_lo, T_hi) of op oi+1 are fetched before the
-        // arithmetic of op oi starts, so their LDC/LDS latency hides behind ~70 fp64 instructions
-        // instead of stalling the 4 warps of the SM sub-partition at the top of every op.
+        // One dense opcode per (kind, target position, matrix class): a single jump-table switch
+        // replaces the chain of compare-and-branch steps a generic (kind, tpos, flags) decode needs.
         const uint64_t active = (uint64_t(s_active[1]) << 32) | s_active[0];
-        int ncode = 0;
-        double2 n_sp = make_double2(1.0, 0.0), n_lo = n_sp, n_hi = n_sp;
-        auto prefetch = [&](int oi) {
-          const QbOp *op = s_ops + oi;
-          ncode = op->kind;
-          const int k = ncode & 0xff;
-          if (k == QB_K_ULADDER || k == QB_K_LADDER) {
-            const double2 *tb = s_tab + op->table_off;
-            n_sp = s_pout[op->flags];
-            n_lo = tb[(jb & 63u) ^ ((jb >> 3) & 7u)];
-            if (hi_bits) n_hi = tb[64 + (jb >> QB_LADDER_CHUNK)];
-          }
-        };
-        if (ob < oe) prefetch(ob);
 #pragma unroll 1
         for (int oi = ob; oi < oe; ++oi) {
-          const QbOp *op = s_ops + oi;
-          const int code = ncode;
-          const double2 sp = n_sp, tlo = n_lo, thi = n_hi;
-          if (oi + 1 < oe) prefetch(oi + 1);
           if (!((active >> oi) & 1)) continue;                            // uniform per tile
-          const int kind = code & 0xff, tp = (code >> 8) & 0xff;
-          const bool real = (code >> 16) & QB_MF_REAL;
+          const QbOp *op = s_ops + oi;
           const double2 *mp = reinterpret_cast<const double2 *>(op->m);
-          if (kind == QB_K_ULADDER) {  // uncontrolled by construction
+          const int opc = int(uint32_t(op->kind) >> 24);
+          if (opc < QB_OPC_U_ALL) {
+            // ULADDER family: uncontrolled butterfly on the pivot + the pivot's phase ladder
+            const double2 *tb = s_tab + op->table_off;
             const double2 *F = reinterpret_cast<const double2 *>(op->F);  // constant bank
-            double2 c = cmul(sp, tlo);
-            if (hi_bits) c = cmul(c, thi);
-            if (real) {
-              Mat m;
-              m.a.x = mp[0].x; m.b.x = mp[1].x; m.c.x = mp[2].x; m.d.x = mp[3].x;
-              QB_DISPATCH_TP(tp, (uladder<0, true>(a, m, c, F)), (uladder<1, true>(a, m, c, F)),
-                             (uladder<2, true>(a, m, c, F)));
-            } else {
-              const Mat m{mp[0], mp[1], mp[2], mp[3]};
-              QB_DISPATCH_TP(tp, (uladder<0, false>(a, m, c, F)), (uladder<1, false>(a, m, c, F)),
-                             (uladder<2, false>(a, m, c, F)));
+            double2 c = cmul(s_pout[op->flags], tb[(jb & 63u) ^ ((jb >> 3) & 7u)]);
+            if (hi_bits) c = cmul(c, tb[64 + (jb >> QB_LADDER_CHUNK)]);
+            switch (opc) {
+              case 0: { const Mat m{mp[0], mp[1], mp[2], mp[3]}; uladder<0, false>(a, m, c, F); break; }
+              case 1: { const Mat m{mp[0], mp[1], mp[2], mp[3]}; uladder<1, false>(a, m, c, F); break; }
+              case 2: { const Mat m{mp[0], mp[1], mp[2], mp[3]}; uladder<2, false>(a, m, c, F); break; }
+              case 3: case 4: case 5: {
+                Mat m;
+                m.a.x = mp[0].x; m.b.x = mp[1].x; m.c.x = mp[2].x; m.d.x = mp[3].x;
+                if (opc == 3) uladder<0, true>(a, m, c, F);
+                else if (opc == 4) uladder<1, true>(a, m, c, F);
+                else uladder<2, true>(a, m, c, F);
+                break;
+              }
+              case 6: hladder<0>(a, mp[0].x, c, F); break;
+              case 7: hladder<1>(a, mp[0].x, c, F); break;
+              default: hladder<2>(a, mp[0].x, c, F); break;
             }
             continue;
           }
           const uint32_t rmask = op->rmask, rwant = op->rwant;
-          const int4 h0 = make_int4(0, 0, int(op->lmask), int(op->lwant));
-          if ((jb & uint32_t(h0.z)) != uint32_t(h0.w)) continue;         // per group
-          switch (kind) {
-            case QB_K_U: {
-              const Mat m{mp[0], mp[1], mp[2], mp[3]};
-              if (rmask == 0) {
-                if (real)
-                  QB_DISPATCH_TP(tp, (bfly_all<0, true>(a, m)), (bfly_all<1, true>(a, m)), (bfly_all<2, true>(a, m)));
-                else
-                  QB_DISPATCH_TP(tp, (bfly_all<0, false>(a, m)), (bfly_all<1, false>(a, m)),
-                                 (bfly_all<2, false>(a, m)));
-              } else {
-                QB_DISPATCH_TP(tp, (bfly_masked<0>(a, m, rmask, rwant)), (bfly_masked<1>(a, m, rmask, rwant)),
-                               (bfly_masked<2>(a, m, rmask, rwant)));
-              }
+          if ((jb & op->lmask) != op->lwant) continue;                   // per group
+          switch (opc) {
+            case QB_OPC_U_ALL + 0: { const Mat m{mp[0], mp[1], mp[2], mp[3]}; bfly_all<0, false>(a, m); break; }
+            case QB_OPC_U_ALL + 1: { const Mat m{mp[0], mp[1], mp[2], mp[3]}; bfly_all<1, false>(a, m); break; }
+            case QB_OPC_U_ALL + 2: { const Mat m{mp[0], mp[1], mp[2], mp[3]}; bfly_all<2, false>(a, m); break; }
+            case QB_OPC_U_ALL + 3: case QB_OPC_U_ALL + 4: case QB_OPC_U_ALL + 5: {
+              Mat m;
+              m.a.x = mp[0].x; m.b.x = mp[1].x; m.c.x = mp[2].x; m.d.x = mp[3].x;
+              if (opc == QB_OPC_U_ALL + 3) bfly_all<0, true>(a, m);
+              else if (opc == QB_OPC_U_ALL + 4) bfly_all<1, true>(a, m);
+              else bfly_all<2, true>(a, m);
               break;
             }
-            case QB_K_PERM: {
-              const double2 mb = mp[1], mc = mp[2];
-              QB_DISPATCH_TP(tp, (perm_masked<0>(a, mb, mc, rmask, rwant)), (perm_masked<1>(a, mb, mc, rmask, rwant)),
-                             (perm_masked<2>(a, mb, mc, rmask, rwant)));
-              break;
-            }
-            case QB_K_SWAP: {
-              QB_DISPATCH_TP(tp, (swap_masked<0>(a, rmask, rwant)), (swap_masked<1>(a, rmask, rwant)),
-                             (swap_masked<2>(a, rmask, rwant)));
-              break;
-            }
-            case QB_K_PHASE: {
+            case QB_OPC_U_MASKED + 0: { const Mat m{mp[0], mp[1], mp[2], mp[3]}; bfly_masked<0>(a, m, rmask, rwant); break; }
+            case QB_OPC_U_MASKED + 1: { const Mat m{mp[0], mp[1], mp[2], mp[3]}; bfly_masked<1>(a, m, rmask, rwant); break; }
+            case QB_OPC_U_MASKED + 2: { const Mat m{mp[0], mp[1], mp[2], mp[3]}; bfly_masked<2>(a, m, rmask, rwant); break; }
+            case QB_OPC_PERM + 0: perm_masked<0>(a, mp[1], mp[2], rmask, rwant); break;
+            case QB_OPC_PERM + 1: perm_masked<1>(a, mp[1], mp[2], rmask, rwant); break;
+            case QB_OPC_PERM + 2: perm_masked<2>(a, mp[1], mp[2], rmask, rwant); break;
+            case QB_OPC_SWAP + 0: swap_masked<0>(a, rmask, rwant); break;
+            case QB_OPC_SWAP + 1: swap_masked<1>(a, rmask, rwant); break;
+            case QB_OPC_SWAP + 2: swap_masked<2>(a, rmask, rwant); break;
+            case QB_OPC_PHASE: {
               const double2 ph = mp[0];
 #pragma unroll
               for (int e = 0; e < 8; ++e)
                 if ((uint32_t(e) & rmask) == rwant) a[e] = cmul(ph, a[e]);
               break;
             }
-            case QB_K_LADDER: {
+            case QB_OPC_LADDER: {
+              const double2 *tb = s_tab + op->table_off;
               const double2 *F = reinterpret_cast<const double2 *>(op->F);
-              double2 c = cmul(sp, tlo);
-              if (hi_bits) c = cmul(c, thi);
+              double2 c = cmul(s_pout[op->flags], tb[(jb & 63u) ^ ((jb >> 3) & 7u)]);
+              if (hi_bits) c = cmul(c, tb[64 + (jb >> QB_LADDER_CHUNK)]);
 #pragma unroll
               for (int e = 0; e < 8; ++e)
                 if ((uint32_t(e) & rmask) == rwant) a[e] = cmul(cmul(c, F[e]), a[e]);
@@ -453,7 +464,9 @@ cudaError_t fused_configure(int device) {
   static_assert(sizeof(QbRound) % 4 == 0 && (QB_MAX_PASS_OPS * sizeof(QbOp)) % 16 == 0, "smem layout");
   cudaError_t err = cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, device);
   if (err != cudaSuccess) return err;
-  return cudaFuncSetAttribute(k_fused_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemLimit));
+  err = cudaFuncSetAttribute(k_fused_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemLimit));
+  if (err != cudaSuccess) return err;
+  return cudaFuncSetAttribute(k_fused_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemLimit));
 }
 
 cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cudaStream_t st) {
@@ -495,7 +508,10 @@ cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cuda
   unsigned blocks = ntiles;
   if (persist > 0 && ntiles > unsigned(persist * g_sms)) blocks = unsigned(persist * g_sms);
   if (nbuf == 2) blocks = ntiles < unsigned(g_sms) ? ntiles : unsigned(g_sms);
-  k_fused_pass<<<blocks, kFThreads, smem, st>>>(P);
+  if (((1u << (K - 3)) % kFThreads) == 0)
+    k_fused_pass<true><<<blocks, kFThreads, smem, st>>>(P);
+  else
+    k_fused_pass<false><<<blocks, kFThreads, smem, st>>>(P);
   return cudaGetLastError();
 }
 

@@ -282,8 +282,15 @@ void build_ladder_tables(const TileMap &tm, const QbRound &r, const Item &it, in
     }
   }
   int plp = tm.lpos[it.pivot];
-  Cplx self_out = it.self;  // pivot outside the tile: folded into the per-tile constant
-  if (plp >= 0) {
+  // The pivot's own phase (a u1 merged into the ladder) applies to every touched amplitude.  It
+  // goes into the lookup tables only when the pivot is a tile bit outside the round; otherwise
+  // (pivot outside the tile, or a round bit) it is folded into the per-tile constant, which keeps
+  // F[pivot bit only] exactly 1 -- the Hadamard+ladder op relies on that.
+  Cplx self_out = it.self;
+  bool pivot_in_round = false;
+  for (int k = 0; k < r.nbits; ++k)
+    if (plp >= 0 && r.rbit[k] == plp) pivot_in_round = true;
+  if (plp >= 0 && !pivot_in_round) {
     per[plp] = cmulh(per[plp], it.self);
     self_out = Cplx{1.0, 0.0};
   }
@@ -415,8 +422,25 @@ void close_round(const TileMap &tm, std::vector<int> &rset, std::vector<PendingO
     if ((op.kind == QB_K_U || op.kind == QB_K_ULADDER || op.kind == QB_K_PERM) && op.m[1] == 0.0 &&
         op.m[3] == 0.0 && op.m[5] == 0.0 && op.m[7] == 0.0)
       op.mflags |= QB_MF_REAL;
-    // the kernel decodes one word per op: kind | tpos << 8 | mflags << 16
-    op.kind = (op.kind & 0xff) | ((op.tpos & 0xff) << 8) | ((op.mflags & 0xff) << 16);
+    if ((op.mflags & QB_MF_REAL) && op.m[0] == op.m[2] && op.m[0] == op.m[4] && op.m[0] == -op.m[6])
+      op.mflags |= QB_MF_HADAMARD;
+    // the kernel decodes one word per op: kind | tpos << 8 | mflags << 16 | dense opcode << 24
+    int opc = 0;
+    const bool real = op.mflags & QB_MF_REAL;
+    const bool unmasked = op.lmask == 0 && op.rmask == 0;
+    switch (op.kind & 0xff) {
+      case QB_K_ULADDER:
+        opc = QB_OPC_ULADDER + op.tpos + ((op.mflags & QB_MF_HADAMARD) ? 6 : (real ? 3 : 0));
+        break;
+      case QB_K_U:
+        opc = unmasked ? QB_OPC_U_ALL + op.tpos + (real ? 3 : 0) : QB_OPC_U_MASKED + op.tpos;
+        break;
+      case QB_K_PERM: opc = QB_OPC_PERM + op.tpos; break;
+      case QB_K_SWAP: opc = QB_OPC_SWAP + op.tpos; break;
+      case QB_K_PHASE: opc = QB_OPC_PHASE; break;
+      default: opc = QB_OPC_LADDER; break;
+    }
+    op.kind = (op.kind & 0xff) | ((op.tpos & 0xff) << 8) | ((op.mflags & 0xff) << 16) | (opc << 24);
     pp->ops.push_back(op);
   }
   r.op_end = int32_t(pp->ops.size());

@@ -63,9 +63,18 @@ struct QbGate {
 #define QB_MAX_SEGS 6
 #define QB_MAX_PASS_LADDERS 12  // their lookup tables (<= 200 x 16 B each) are staged in shared memory too
 #define QB_MF_REAL 1         // all four entries of m are real: 8 instead of 20 flops per pair
+#define QB_MF_HADAMARD 2     // m = r * [[1, 1], [1, -1]] with real r
+// Dense opcodes (bits 24..31 of QbOp::kind): one jump-table switch in the kernel.
+#define QB_OPC_ULADDER 0     // +tpos complex, +3+tpos real, +6+tpos Hadamard
+#define QB_OPC_U_ALL 9       // uncontrolled U: +tpos complex, +3+tpos real
+#define QB_OPC_U_MASKED 15   // U with controls inside the tile: +tpos
+#define QB_OPC_PERM 18       // +tpos
+#define QB_OPC_SWAP 21       // +tpos
+#define QB_OPC_PHASE 24
+#define QB_OPC_LADDER 25
 
 struct alignas(16) QbOp {   // 256 bytes; lives in the kernel parameters (constant bank)
-  int32_t kind;      // QbKind (never DIAG/NOP: the planner lowers those) | tpos << 8 | mflags << 16
+  int32_t kind;      // QbKind (never DIAG/NOP: the planner lowers those) | tpos << 8 | mflags << 16 | opcode << 24
   int32_t tpos;      // U/PERM/SWAP: target position inside rbit[]
   uint32_t lmask, lwant;
   uint32_t rmask, rwant;

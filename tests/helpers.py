@@ -136,6 +136,8 @@ def interpret_plan(plan_json: str, n: int, gates, psi: np.ndarray) -> np.ndarray
             [complex(op["m"][2 * i], op["m"][2 * i + 1]) for i in range(4)])
         kind = op["kind"] & 0xFF
         assert (op["kind"] >> 8) & 0xFF == op["tpos"] and (op["kind"] >> 16) & 0xFF == op["mflags"]
+        if kind == K_ULADDER:
+          assert op["F"][2 * (1 << op["tpos"])] == 1.0 and op["F"][2 * (1 << op["tpos"]) + 1] == 0.0
         if kind in (K_U, K_PERM, K_SWAP):
           tp = op["tpos"]
           for e in range(8):
