@@ -37,9 +37,9 @@
 // h followed by its cu1 ladder is ONE op (ULADDER): y' = (c x + d y) * phase.
 //
 // Phase ladders: the phase of an amplitude is C_tile * T_lo[j & 63] * T_hi[j >> 6] * F[e];
-// C_tile = product over partner bits outside the tile (computed once per CTA into shared
-// memory), T_* = host-built 64-entry tables over the tile-local partner bits, F = the 8
-// combinations of the round's own bits.
+// C_tile = product over partner bits outside the tile (one warp per ladder, once per tile,
+// folded into that tile's copy of T_lo), T_* = host-built 64-entry tables over the tile-local
+// partner bits, F = the 8 combinations of the round's own bits (constant bank).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -328,7 +328,12 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_consta
           d.y = __shfl_xor_sync(0xffffffffu, c.y, o);
           c = cmul(c, d);
         }
-        if (lane == 0) s_pout[op->flags] = c;
+        // Fold the per-tile constant into this tile's copy of T_lo (64 entries, 2 per lane), so
+        // the hot loop needs one multiply less and one dependent shared-memory read less per op.
+        const double2 *t0 = P.tables + op->table_off;
+        double2 *t1 = s_tab + op->table_off;
+        t1[lane] = cmul(__ldg(t0 + lane), c);
+        t1[lane + 32] = cmul(__ldg(t0 + lane + 32), c);
       }
     }
     if (nbuf == 2 && more) cp_async_wait<1>();
@@ -367,7 +372,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_consta
             // ULADDER family: uncontrolled butterfly on the pivot + the pivot's phase ladder
             const double2 *tb = s_tab + op->table_off;
             const double2 *F = reinterpret_cast<const double2 *>(op->F);  // constant bank
-            double2 c = cmul(s_pout[op->flags], tb[(jb & 63u) ^ ((jb >> 3) & 7u)]);
+            double2 c = tb[(jb & 63u) ^ ((jb >> 3) & 7u)];   // already carries the per-tile constant
             if (hi_bits) c = cmul(c, tb[64 + (jb >> QB_LADDER_CHUNK)]);
             switch (opc) {
               case 0: { const Mat m{mp[0], mp[1], mp[2], mp[3]}; uladder<0, false>(a, m, c, F); break; }
@@ -420,7 +425,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_consta
             case QB_OPC_LADDER: {
               const double2 *tb = s_tab + op->table_off;
               const double2 *F = reinterpret_cast<const double2 *>(op->F);
-              double2 c = cmul(s_pout[op->flags], tb[(jb & 63u) ^ ((jb >> 3) & 7u)]);
+              double2 c = tb[(jb & 63u) ^ ((jb >> 3) & 7u)];
               if (hi_bits) c = cmul(c, tb[64 + (jb >> QB_LADDER_CHUNK)]);
 #pragma unroll
               for (int e = 0; e < 8; ++e)
