@@ -52,7 +52,16 @@ namespace qb {
 namespace {
 
 constexpr int kFThreads = 256;
-constexpr int kMaxLadders = 64;
+
+// Host-precomputed per-round constants of the round programs (all derivable from QbRound / QbOp;
+// kept out of the hot loop's uniform-datapath instruction stream).
+struct RoundAux {
+  uint32_t b[3];     // byte XOR that sets round bit k in a swizzled slot
+  uint32_t pbi[(1 << (QB_MAX_TILE_BITS - 3)) / kFThreads];  // byte slot of group 256 * git
+  uint32_t ta[3];    // byte offset of the three ladders' tables
+  uint32_t pad_;
+  double s;          // product of the three Hadamard scales
+};
 
 struct FusedParams {
   double2 *psi;
@@ -62,11 +71,12 @@ struct FusedParams {
   const double2 *outph;
   const int32_t *outbits;
   const uint32_t *jbtab;
-  int debug;  // timing experiments only -- 1: skip the op loop, 2: skip the rounds, 4: skip the store, 8: skip the load
-  int nbuf;   // tile buffers in the shared-memory ring (1 or 2)
-  int stagger_ns;  // first-wave start offset between the CTA slots of an SM (see launch_fused_pass)
-  int sms;
-  int nbits_out;  // entries in outbits
+  int debug;  // timing experiments only -- 1: skip the op loop, 2: skip the rounds, 4: skip the store, 8: skip the load, 16: no round programs, 32: round programs read the group table
+  // per copy iteration i (thread t moves tile-local index t + 256 i): global offset of index 256 i
+  // in units of 8 amplitudes, and the XOR that takes the byte slot of t to the byte slot of t + 256 i
+  uint32_t io_goff[(1 << QB_MAX_TILE_BITS) / kFThreads];
+  uint32_t io_sxor[(1 << QB_MAX_TILE_BITS) / kFThreads];
+  RoundAux aux[QB_MAX_PASS_ROUNDS];
   // Pass descriptors travel as kernel parameters (7 KiB of the 32 KiB parameter space): the
   // per-op decode in the hot loop is then LDC from the constant bank (warp-uniform index), which
   // costs neither shared-memory wavefronts nor LSU issue slots.
@@ -99,6 +109,16 @@ __device__ __forceinline__ double2 mad2r(double m0, double2 x, double m1, double
 struct Mat {
   double2 a, b, c, d;
 };
+
+// shared-memory accesses by 32-bit shared address (base in a uniform register + per-thread offset)
+__device__ __forceinline__ double2 lds128(uint32_t sa) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];\n" : "=d"(v.x), "=d"(v.y) : "r"(sa));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t sa, double2 v) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};\n" ::"r"(sa), "d"(v.x), "d"(v.y) : "memory");
+}
 
 // ---- butterflies on the 8 registers of one group ------------------------------------
 template <int TP, bool REAL>
@@ -195,6 +215,117 @@ __device__ __forceinline__ void hladder(double2 (&a)[8], double r, double2 cf, c
   }
 }
 
+// ---- round program HL3: three Hadamard+ladder stages on round positions 0, 1, 2 ---------------
+// The shape of every round of a QFT (circuit.py:320-328): h(b0) + ladder(b0), h(b1) + ladder(b1),
+// h(b2) + ladder(b2).  Fully unrolled, no op decode: per group 8 LDS.128, three table lookups (two
+// reads each: one per lane, one broadcast), ~130 fp64 instructions, 8 STS.128.  The three
+// 1/sqrt(2) factors are applied once (s = r0 r1 r2: the y' path of stage 0 takes it inside its
+// phase, the x' path as one multiply).
+// UPPER: the ladder partners inside the round are all above their pivot, so stage 1 has one
+// non-trivial in-round phase and stage 2 none (true for the QFT; otherwise all of F is used).
+template <bool UPPER, bool FULL>
+__device__ __forceinline__ void round_hl3(const uint32_t tile_sa, const uint32_t tab_sa,
+                                          const uint32_t *__restrict__ jbt, const QbOp *__restrict__ o,
+                                          const QbRound *__restrict__ R, const RoundAux *__restrict__ X,
+                                          const uint32_t ngroups, const uint32_t tid) {
+  const double s = X->s;
+  const double2 *F0 = reinterpret_cast<const double2 *>(o[0].F);
+  const double2 *F1 = reinterpret_cast<const double2 *>(o[1].F);
+  const double2 *F2 = reinterpret_cast<const double2 *>(o[2].F);
+  const uint32_t giters = FULL ? (ngroups / kFThreads) : ((ngroups + kFThreads - 1) / kFThreads);
+  const uint32_t b0 = X->b[0], b1 = X->b[1], b2 = X->b[2];
+  // ladder tables: T_a[lane] (fixed per thread), T_b[q >> 5] (uniform per warp)
+  const uint32_t lane16 = (tid & 31u) << 4;
+  const uint32_t ta0 = tab_sa + X->ta[0] + lane16;
+  const uint32_t ta1 = tab_sa + X->ta[1] + lane16;
+  const uint32_t ta2 = tab_sa + X->ta[2] + lane16;
+  // Group q = tid + 256 git -> swizzled byte slot of its base index (the bits of q scattered to
+  // qmap[]).  The slot is linear over XOR in q, so the per-thread part is built once per round
+  // from tid and the per-iteration part is uniform: no table load at the head of the dependency
+  // chain of every group.
+  uint32_t jb_t = 0;
+  if (FULL) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) jb_t |= ((tid >> k) & 1u) << R->qmap[k];
+  }
+  const uint32_t pb_t = swz(jb_t) << 4;
+#pragma unroll 1
+  for (uint32_t git = 0; git < giters; ++git) {
+    const uint32_t q = git * kFThreads + tid;
+    uint32_t pb;  // base slot in bytes
+    if (FULL) {
+      pb = pb_t ^ X->pbi[git];
+    } else {
+      if (q >= ngroups) break;
+      pb = (__ldg(jbt + q) >> 12) & 0xffff0u;
+    }
+    double2 a[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      a[e] = lds128(tile_sa + (pb ^ ((e & 1) ? b0 : 0u) ^ ((e & 2) ? b1 : 0u) ^ ((e & 4) ? b2 : 0u)));
+    const uint32_t tboff = (32u + (q >> 5)) << 4;
+    // stage 0: pairs (e, e|1)
+    {
+      double2 c0 = cmul(lds128(ta0), lds128(ta0 - lane16 + tboff));
+      c0.x *= s;
+      c0.y *= s;
+      const double2 p3 = cmul(c0, F0[3]), p5 = cmul(c0, F0[5]), p7 = cmul(c0, F0[7]);
+#pragma unroll
+      for (int e = 0; e < 8; e += 2) {
+        const double2 x = a[e], y = a[e | 1];
+        const double2 ph = e == 0 ? c0 : (e == 2 ? p3 : (e == 4 ? p5 : p7));
+        const double2 d = make_double2(x.x - y.x, x.y - y.y);
+        a[e] = make_double2(s * (x.x + y.x), s * (x.y + y.y));
+        a[e | 1] = cmul(d, ph);
+      }
+    }
+    // stage 1: pairs (e, e|2)
+    {
+      const double2 c1 = cmul(lds128(ta1), lds128(ta1 - lane16 + tboff));
+      double2 p2 = c1, p3, p6, p7;
+      if (UPPER) {
+        p3 = c1;
+        p6 = cmul(c1, F1[6]);
+        p7 = p6;
+      } else {
+        p3 = cmul(c1, F1[3]);
+        p6 = cmul(c1, F1[6]);
+        p7 = cmul(c1, F1[7]);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e = (k & 1) | ((k & 2) << 1);
+        const double2 x = a[e], y = a[e | 2];
+        const double2 ph = k == 0 ? p2 : (k == 1 ? p3 : (k == 2 ? p6 : p7));
+        const double2 d = make_double2(x.x - y.x, x.y - y.y);
+        a[e] = make_double2(x.x + y.x, x.y + y.y);
+        a[e | 2] = cmul(d, ph);
+      }
+    }
+    // stage 2: pairs (e, e|4)
+    {
+      const double2 c2 = cmul(lds128(ta2), lds128(ta2 - lane16 + tboff));
+      double2 p4 = c2, p5 = c2, p6 = c2, p7 = c2;
+      if (!UPPER) {
+        p5 = cmul(c2, F2[5]);
+        p6 = cmul(c2, F2[6]);
+        p7 = cmul(c2, F2[7]);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const double2 x = a[e], y = a[e | 4];
+        const double2 ph = e == 0 ? p4 : (e == 1 ? p5 : (e == 2 ? p6 : p7));
+        const double2 d = make_double2(x.x - y.x, x.y - y.y);
+        a[e] = make_double2(x.x + y.x, x.y + y.y);
+        a[e | 4] = cmul(d, ph);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      sts128(tile_sa + (pb ^ ((e & 1) ? b0 : 0u) ^ ((e & 2) ? b1 : 0u) ^ ((e & 4) ? b2 : 0u)), a[e]);
+  }
+}
+
 #define QB_DISPATCH_TP(tp, CALL0, CALL1, CALL2) \
   do {                                          \
     if ((tp) == 0) { CALL0; }                   \
@@ -202,8 +333,7 @@ __device__ __forceinline__ void hladder(double2 (&a)[8], double r, double2 cf, c
     else { CALL2; }                             \
   } while (0)
 
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
-  const uint32_t sa = uint32_t(__cvta_generic_to_shared(smem));
+__device__ __forceinline__ void cp_async16(uint32_t sa, const void *gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
@@ -218,48 +348,40 @@ __device__ __forceinline__ void cp_async_wait() {
 // the op index -- and with it every descriptor load -- in vector registers (vector-indexed LDC,
 // vector compares and branches per op); with a uniform trip count the decode runs on the uniform
 // datapath.
-template <bool FULL>
-__global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_constant__ FusedParams P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+// FAST: every round of the pass has a round program, so the op interpreter is not compiled in; the
+// kernel then fits 80 registers and a third CTA per SM (24 instead of 16 warps to hide the
+// shared-memory and fp64 latencies of the rounds).
+template <bool FULL, bool FAST>
+__global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __grid_constant__ FusedParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int K = P.desc.K;
   const uint32_t tileN = 1u << K;
-  const int nbuf = P.nbuf;
-  double2 *tiles = reinterpret_cast<double2 *>(smem_raw);               // nbuf x 2^K
-  double2 *s_pout = tiles + size_t(nbuf) * tileN;                       // kMaxLadders
-  uint32_t *s_active = reinterpret_cast<uint32_t *>(s_pout + kMaxLadders);  // 4 words: ops whose
+  double2 *tile = reinterpret_cast<double2 *>(smem_raw);                // 2^K
+  double2 *s_tab = tile + tileN;                                        // ntable
+  uint32_t *s_active = reinterpret_cast<uint32_t *>(s_tab + P.desc.ntable);  // 4 words: ops whose
                                                                         // outside-tile predicate holds for this tile
-  double2 *s_tab = s_pout + kMaxLadders + 1;                            // ntable
-  double2 *s_outph = s_tab + P.desc.ntable;                             // nout_total (+1 pad)
-  uint32_t *hi_off = reinterpret_cast<uint32_t *>(s_outph + P.desc.nout_total + 1);  // 2^(K-3)
-  int32_t *s_outbits = reinterpret_cast<int32_t *>(hi_off + (tileN >> 3));  // nout_total
   const QbOp *s_ops = P.ops;        // constant bank
   const QbRound *s_rounds = P.rounds;
   const uint32_t tid = threadIdx.x;
   double2 *__restrict__ psi = P.psi;
 
-  // De-phase the CTAs that share an SM.  All CTAs do identical work, so the ones launched
-  // together stay in lockstep for the whole kernel -- every resident CTA loading, then every
-  // one computing -- and HBM, shared memory and the fp64 pipe are used one after the other
-  // instead of concurrently.  Delaying the 2nd / 3rd CTA slot of each SM once, in the first
-  // wave only, keeps the slots a third of a tile apart from then on.
-  if (P.stagger_ns && blockIdx.x < 3u * uint32_t(P.sms)) {
-    const uint32_t slot = blockIdx.x / uint32_t(P.sms);
-    for (uint32_t k = 0; k < slot; ++k) __nanosleep(uint32_t(P.stagger_ns));
-  }
+  // ---- STAGE (once per CTA): ladder tables -> shared memory ---------------------------------
+  for (int i = tid; i < P.desc.ntable; i += kFThreads) s_tab[i] = __ldg(P.tables + i);
 
-  // ---- STAGE (once per CTA): ladder tables, run offsets -> shared memory --------------------
-  {
-    for (int i = tid; i < P.desc.ntable; i += kFThreads) s_tab[i] = __ldg(P.tables + i);
-    // ladder constants: per-tile factors are rebuilt from these for every tile
-    for (int i = tid; i < P.desc.nout_total; i += kFThreads) s_outph[i] = __ldg(P.outph + i);
-    for (int i = tid; i < P.nbits_out; i += kFThreads) s_outbits[i] = __ldg(P.outbits + i);
-    // offset of every 8-amplitude run of a tile, in units of 8 amplitudes
-    for (uint32_t h = tid; h < (tileN >> 3); h += kFThreads) {
-      uint64_t off = 0;
-      for (int k = 3; k < K; ++k) off |= uint64_t((h >> (k - 3)) & 1u) << P.desc.tile_bits[k];
-      hi_off[h] = uint32_t(off >> 3);
-    }
-  }
+  // Tile <-> HBM addressing.  Thread t moves tile-local indices j = t + 256 i.  Both the global
+  // offset of j (its bits scattered to tile_bits[]) and its swizzled slot are linear over XOR and
+  // t, 256 i have no bit in common, so address(j) = address(t) (+ or ^) address(256 i): one
+  // per-thread term computed here, one per-iteration term from the kernel parameters -- an add, an
+  // XOR and the copy itself per 16 bytes.
+  uint64_t g_tid = tid & 7u;
+#pragma unroll
+  for (int k = 3; k < 8; ++k)
+    if (k < K) g_tid |= uint64_t((tid >> k) & 1u) << P.desc.tile_bits[k];
+  const uint32_t s_tid = swz(tid) << 4;
+  const uint32_t io_iters = tileN > kFThreads ? tileN / kFThreads : 1u;
+  const bool io_on = tid < tileN;
+  const uint32_t tile_sa = uint32_t(__cvta_generic_to_shared(tile));
+  const uint32_t tab_sa = uint32_t(__cvta_generic_to_shared(s_tab));
   __syncthreads();
 
   const uint32_t ntiles = 1u << (P.nbits - K);
@@ -286,26 +408,32 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_consta
     }
     return b;
   };
-  auto issue_load = [&](uint32_t t, double2 *buf) {
-    const uint64_t b = tile_base(t);
-    if (!(P.debug & 8))
-      for (uint32_t j = tid; j < tileN; j += kFThreads)
-        cp_async16(buf + swz(j), psi + (b | (uint64_t(hi_off[j >> 3]) << 3) | (j & 7u)));
+  auto issue_load = [&](uint64_t b) {
+    if (!(P.debug & 8) && io_on) {
+      const double2 *src = psi + (b | g_tid);
+      if (io_iters == 16) {  // K = 12: constant-bank operands with immediate addresses
+#pragma unroll
+        for (uint32_t i = 0; i < 16; ++i)
+          cp_async16(tile_sa + (s_tid ^ P.io_sxor[i]), src + (uint64_t(P.io_goff[i]) << 3));
+      } else {
+#pragma unroll 4
+        for (uint32_t i = 0; i < io_iters; ++i)
+          cp_async16(tile_sa + (s_tid ^ P.io_sxor[i]), src + (uint64_t(P.io_goff[i]) << 3));
+      }
+    }
     cp_async_commit();
   };
 
-  const int hi_bits = K > QB_LADDER_CHUNK ? K - QB_LADDER_CHUNK : 0;
   const uint32_t ngroups = tileN >> 3;
-  int cur = 0;
-  if (blockIdx.x < ntiles) issue_load(blockIdx.x, tiles);
+  const int gbits = K - QB_ROUND_BITS;
+  const int nb_tab = gbits > QB_LADDER_LANE_BITS ? 1 << (gbits - QB_LADDER_LANE_BITS) : 1;  // entries of T_b
+  uint64_t base = blockIdx.x < ntiles ? tile_base(blockIdx.x) : 0;
+  if (blockIdx.x < ntiles) issue_load(base);
   for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const uint32_t tn = t + gridDim.x;
     const bool more = tn < ntiles;
-    double2 *tile = tiles + size_t(cur) * tileN;
-    if (nbuf == 2 && more) issue_load(tn, tiles + size_t(cur ^ 1) * tileN);  // prefetch
-    const uint64_t base = tile_base(t);
     // which ops apply to this tile at all (their controls outside the tile): one bit per op
-    if (tid < 64) {
+    if (!FAST && tid < 64) {
       const bool on = int(tid) < P.desc.nops && (base & s_ops[tid].gmask) == s_ops[tid].gwant;
       const uint32_t bal = __ballot_sync(0xffffffffu, on);
       if ((tid & 31u) == 0) s_active[tid >> 5] = bal;
@@ -317,10 +445,10 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_consta
       const int k8 = op->kind & 0xff;
       if (k8 == QB_K_LADDER || k8 == QB_K_ULADDER) {
         const int lane = int(tid & 31u);
-        const double2 *ph = s_outph + op->outph_off;
+        const double2 *ph = P.outph + op->outph_off;
         double2 c = make_double2(1.0, 0.0);
-        if (lane < op->nout && ((base >> s_outbits[op->out_off + lane]) & 1)) c = ph[1 + lane];
-        if (lane == 0) c = cmul(c, ph[0]);
+        if (lane < op->nout && ((base >> __ldg(P.outbits + op->out_off + lane)) & 1)) c = __ldg(ph + 1 + lane);
+        if (lane == 0) c = cmul(c, __ldg(ph));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           double2 d;
@@ -328,26 +456,32 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_consta
           d.y = __shfl_xor_sync(0xffffffffu, c.y, o);
           c = cmul(c, d);
         }
-        // Fold the per-tile constant into this tile's copy of T_lo (64 entries, 2 per lane), so
-        // the hot loop needs one multiply less and one dependent shared-memory read less per op.
-        const double2 *t0 = P.tables + op->table_off;
-        double2 *t1 = s_tab + op->table_off;
-        t1[lane] = cmul(__ldg(t0 + lane), c);
-        t1[lane + 32] = cmul(__ldg(t0 + lane + 32), c);
+        // Fold the per-tile constant into this tile's copy of T_b (<= 32 entries), so the hot
+        // loop needs one multiply less and one dependent shared-memory read less per op.
+        if (lane < nb_tab) {
+          const int e = op->table_off + (1 << QB_LADDER_LANE_BITS) + lane;
+          s_tab[e] = cmul(__ldg(P.tables + e), c);
+        }
       }
     }
-    if (nbuf == 2 && more) cp_async_wait<1>();
-    else cp_async_wait<0>();
+    cp_async_wait<0>();
     __syncthreads();
 
     // ---- ROUNDS ------------------------------------------------------------------------
     for (int r = 0; r < ((P.debug & 2) ? 0 : P.desc.nrounds); ++r) {
       const QbRound *R = s_rounds + r;
+      const int ob = R->op_begin, oe = (P.debug & 1) ? R->op_begin : R->op_end;
+      const uint32_t *jbt = P.jbtab + (size_t(r) << P.desc.ngroups_log2);
+      if (FAST || (R->prog != QB_PROG_GENERIC && !(P.debug & (1 | 16)))) {
+        if (R->prog == QB_PROG_HL3U) round_hl3<true, FULL>(tile_sa, tab_sa, jbt, s_ops + ob, R, P.aux + r, ngroups, tid);
+        else round_hl3<false, FULL>(tile_sa, tab_sa, jbt, s_ops + ob, R, P.aux + r, ngroups, tid);
+        __syncthreads();
+        continue;
+      }
+      if (!FAST) {
       const uint32_t d0 = swz(1u << R->rbit[0]);
       const uint32_t d1 = swz(1u << R->rbit[1]);
       const uint32_t d2 = swz(1u << R->rbit[2]);
-      const int ob = R->op_begin, oe = (P.debug & 1) ? R->op_begin : R->op_end;
-      const uint32_t *jbt = P.jbtab + (size_t(r) << P.desc.ngroups_log2);
       const uint32_t giters = FULL ? (ngroups / kFThreads) : ((ngroups + kFThreads - 1) / kFThreads);
       for (uint32_t git = 0; git < giters; ++git) {
         const uint32_t q = git * kFThreads + tid;
@@ -372,8 +506,8 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_consta
             // ULADDER family: uncontrolled butterfly on the pivot + the pivot's phase ladder
             const double2 *tb = s_tab + op->table_off;
             const double2 *F = reinterpret_cast<const double2 *>(op->F);  // constant bank
-            double2 c = tb[(jb & 63u) ^ ((jb >> 3) & 7u)];   // already carries the per-tile constant
-            if (hi_bits) c = cmul(c, tb[64 + (jb >> QB_LADDER_CHUNK)]);
+            // T_b already carries the per-tile constant
+            const double2 c = cmul(tb[q & 31u], tb[32u + (q >> QB_LADDER_LANE_BITS)]);
             switch (opc) {
               case 0: { const Mat m{mp[0], mp[1], mp[2], mp[3]}; uladder<0, false>(a, m, c, F); break; }
               case 1: { const Mat m{mp[0], mp[1], mp[2], mp[3]}; uladder<1, false>(a, m, c, F); break; }
@@ -425,8 +559,7 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_consta
             case QB_OPC_LADDER: {
               const double2 *tb = s_tab + op->table_off;
               const double2 *F = reinterpret_cast<const double2 *>(op->F);
-              double2 c = tb[(jb & 63u) ^ ((jb >> 3) & 7u)];
-              if (hi_bits) c = cmul(c, tb[64 + (jb >> QB_LADDER_CHUNK)]);
+              const double2 c = cmul(tb[q & 31u], tb[32u + (q >> QB_LADDER_LANE_BITS)]);
 #pragma unroll
               for (int e = 0; e < 8; ++e)
                 if ((uint32_t(e) & rmask) == rwant) a[e] = cmul(cmul(c, F[e]), a[e]);
@@ -441,26 +574,44 @@ __global__ void __launch_bounds__(kFThreads, 2) k_fused_pass(const __grid_consta
           tile[pb ^ ((e & 1) ? d0 : 0u) ^ ((e & 2) ? d1 : 0u) ^ ((e & 4) ? d2 : 0u)] = a[e];
       }
       __syncthreads();
+      }
     }
 
     // ---- STORE ---------------------------------------------------------------------------
-    if (!(P.debug & 4))
-    for (uint32_t j = tid; j < tileN; j += kFThreads)
-      __stcs(psi + (base | (uint64_t(hi_off[j >> 3]) << 3) | (j & 7u)), tile[swz(j)]);
-    __syncthreads();  // every read of this buffer is done before a later copy lands in it
-    if (nbuf == 1 && more) issue_load(tn, tiles);
-    if (nbuf == 2) cur ^= 1;
+    if (!(P.debug & 4) && io_on) {
+      double2 *dst = psi + (base | g_tid);
+      if (io_iters == 16) {
+#pragma unroll
+        for (uint32_t i = 0; i < 16; ++i)
+          __stcs(dst + (uint64_t(P.io_goff[i]) << 3), lds128(tile_sa + (s_tid ^ P.io_sxor[i])));
+      } else {
+#pragma unroll 4
+        for (uint32_t i = 0; i < io_iters; ++i)
+          __stcs(dst + (uint64_t(P.io_goff[i]) << 3), lds128(tile_sa + (s_tid ^ P.io_sxor[i])));
+      }
+    }
+    if (more) base = tile_base(tn);
+    __syncthreads();  // every read of the tile is done before the next copy lands in it
+    if (more) issue_load(base);
   }
 }
 
-size_t fused_smem_bytes(int K, int ntable, int nbuf, int nout_total) {
-  return size_t(nbuf) * (size_t(1) << K) * sizeof(double2) + (kMaxLadders + 1) * sizeof(double2) +
-         size_t(ntable) * sizeof(double2) + (size_t(1) << (K - 3)) * sizeof(uint32_t) +
-         size_t(nout_total + 1) * sizeof(double2) + size_t(nout_total + 4) * sizeof(int32_t);
+size_t fused_smem_bytes(int K, int ntable) {
+  return (size_t(1) << K) * sizeof(double2) + size_t(ntable) * sizeof(double2) + 4 * sizeof(uint32_t);
 }
 
 constexpr size_t kSmemLimit = 227 * 1024;
+constexpr size_t kSmemSM = 228 * 1024;  // per SM, shared by the resident CTAs (+ 1 KiB reserved each)
 int g_sms = 0;
+
+template <bool FULL, bool FAST>
+cudaError_t configure_one() {
+  cudaError_t err = cudaFuncSetAttribute(k_fused_pass<FULL, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         int(kSmemLimit));
+  if (err != cudaSuccess) return err;
+  return cudaFuncSetAttribute(k_fused_pass<FULL, FAST>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                              cudaSharedmemCarveoutMaxShared);
+}
 
 }  // namespace
 
@@ -469,9 +620,10 @@ cudaError_t fused_configure(int device) {
   static_assert(sizeof(QbRound) % 4 == 0 && (QB_MAX_PASS_OPS * sizeof(QbOp)) % 16 == 0, "smem layout");
   cudaError_t err = cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, device);
   if (err != cudaSuccess) return err;
-  err = cudaFuncSetAttribute(k_fused_pass<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemLimit));
-  if (err != cudaSuccess) return err;
-  return cudaFuncSetAttribute(k_fused_pass<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemLimit));
+  if ((err = configure_one<true, true>()) != cudaSuccess) return err;
+  if ((err = configure_one<true, false>()) != cudaSuccess) return err;
+  if ((err = configure_one<false, true>()) != cudaSuccess) return err;
+  return configure_one<false, false>();
 }
 
 cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cudaStream_t st) {
@@ -486,37 +638,67 @@ cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cuda
   P.outph = p.outph;
   P.outbits = p.outbits;
   P.jbtab = p.jbtab;
-  P.nbits_out = p.noutbits;
   static const int dbg = getenv("QCC_B200_FUSED_DEBUG") ? atoi(getenv("QCC_B200_FUSED_DEBUG")) : 0;
-  static const int force_nbuf = getenv("QCC_B200_FUSED_NBUF") ? atoi(getenv("QCC_B200_FUSED_NBUF")) : 0;
   P.debug = dbg;
-  static const int stagger = getenv("QCC_B200_FUSED_STAGGER_NS") ? atoi(getenv("QCC_B200_FUSED_STAGGER_NS")) : 0;
-  P.stagger_ns = stagger;
-  P.sms = g_sms;
   const int K = p.desc.K;
   if (K < 4 || K > QB_MAX_TILE_BITS || K > nbits) return cudaErrorInvalidValue;
-  if (p.desc.nops > QB_MAX_PASS_OPS || p.desc.nrounds > QB_MAX_PASS_ROUNDS) return cudaErrorInvalidValue;
   const unsigned ntiles = 1u << (nbits - K);
-  // Default: one CTA per tile, single buffer, two CTAs of 256 threads resident per SM (register
-  // budget 128/thread: the 16 fp64 amplitude registers plus a complex 2x2 and ladder phases fit
-  // without spilling; at 3 CTAs / 80 registers the spills and ladder-table misses cost more
-  // than the extra CTA gains).  QCC_B200_FUSED_NBUF=2 selects the persistent two-deep cp.async
-  // ring instead (one CTA per SM); measured slower (profiles/r01_fused_experiments.md).
-  int nbuf = force_nbuf == 2 && fused_smem_bytes(K, p.desc.ntable, 2, p.desc.nout_total) <= kSmemLimit ? 2 : 1;
-  const size_t smem = fused_smem_bytes(K, p.desc.ntable, nbuf, p.desc.nout_total);
+  const size_t smem = fused_smem_bytes(K, p.desc.ntable);
   if (smem > kSmemLimit) return cudaErrorInvalidValue;
-  P.nbuf = nbuf;
-  // Persistent CTAs: 2 per SM, each walking tiles blockIdx.x, +grid, ... so that the per-CTA
-  // staging (26 KiB of ladder tables, run offsets) is paid once per SM slot, not once per tile
-  // (it was 3.5 of 16 ms per pass when every tile had its own CTA).
-  static const int persist = getenv("QCC_B200_FUSED_PERSIST") ? atoi(getenv("QCC_B200_FUSED_PERSIST")) : 2;
+  // copy-loop address terms of tile-local index 256 i (see the kernel)
+  for (uint32_t i = 0; i < (1u << K) / kFThreads; ++i) {
+    const uint32_t j = i * kFThreads, h = j >> 3;
+    uint64_t off = 0;
+    for (int k = 3; k < K; ++k) off |= uint64_t((h >> (k - 3)) & 1u) << p.desc.tile_bits[k];
+    uint32_t x = j >> 3;
+    x ^= x >> 3;
+    x ^= x >> 6;
+    P.io_goff[i] = uint32_t(off >> 3);
+    P.io_sxor[i] = (j ^ (x & 7u)) << 4;
+  }
+  if ((1u << K) <= kFThreads) P.io_goff[0] = P.io_sxor[0] = 0;
+  auto swz_h = [](uint32_t j) {
+    uint32_t x = j >> 3;
+    x ^= x >> 3;
+    x ^= x >> 6;
+    return j ^ (x & 7u);
+  };
+  for (int r = 0; r < p.desc.nrounds; ++r) {
+    const QbRound &R = p.rounds[r];
+    RoundAux &X = P.aux[r];
+    memset(&X, 0, sizeof X);
+    if (R.prog == QB_PROG_GENERIC) continue;
+    X.s = 1.0;
+    for (int k = 0; k < 3; ++k) {
+      X.b[k] = swz_h(1u << R.rbit[k]) << 4;
+      X.ta[k] = uint32_t(p.ops[R.op_begin + k].table_off) << 4;
+      X.s *= p.ops[R.op_begin + k].m[0];
+    }
+    for (uint32_t git = 0; git < (1u << (K - 3)) / kFThreads; ++git) {
+      uint32_t jb = 0;
+      for (int k = 8; k < K - 3; ++k) jb |= ((git >> (k - 8)) & 1u) << R.qmap[k];
+      X.pbi[git] = swz_h(jb) << 4;
+    }
+  }
+  // FAST: no round needs the op interpreter (and the debug switches that fall back to it are off)
+  bool fast = !(dbg & (1 | 16));
+  for (int r = 0; r < p.desc.nrounds; ++r)
+    if (p.rounds[r].prog == QB_PROG_GENERIC) fast = false;
+  // Persistent CTAs, as many as fit an SM (3 for FAST passes at K = 12: 64 KiB tile + 9 KiB of
+  // tables each; else 2), each walking tiles blockIdx.x, +grid, ... so that the per-CTA staging
+  // (ladder tables) is paid once per SM slot, not once per tile.  The CTAs of an SM drift out of
+  // phase, so one streams its tile while the others compute.
+  int per_sm = int(kSmemSM / (smem + 1024));
+  per_sm = per_sm < 1 ? 1 : (per_sm > (fast ? 3 : 2) ? (fast ? 3 : 2) : per_sm);
+  static const int persist = getenv("QCC_B200_FUSED_PERSIST") ? atoi(getenv("QCC_B200_FUSED_PERSIST")) : -1;
+  if (persist >= 0) per_sm = persist;
   unsigned blocks = ntiles;
-  if (persist > 0 && ntiles > unsigned(persist * g_sms)) blocks = unsigned(persist * g_sms);
-  if (nbuf == 2) blocks = ntiles < unsigned(g_sms) ? ntiles : unsigned(g_sms);
-  if (((1u << (K - 3)) % kFThreads) == 0)
-    k_fused_pass<true><<<blocks, kFThreads, smem, st>>>(P);
-  else
-    k_fused_pass<false><<<blocks, kFThreads, smem, st>>>(P);
+  if (per_sm > 0 && ntiles > unsigned(per_sm * g_sms)) blocks = unsigned(per_sm * g_sms);
+  const bool full = ((1u << (K - 3)) % kFThreads) == 0;
+  if (full && fast) k_fused_pass<true, true><<<blocks, kFThreads, smem, st>>>(P);
+  else if (full) k_fused_pass<true, false><<<blocks, kFThreads, smem, st>>>(P);
+  else if (fast) k_fused_pass<false, true><<<blocks, kFThreads, smem, st>>>(P);
+  else k_fused_pass<false, false><<<blocks, kFThreads, smem, st>>>(P);
   return cudaGetLastError();
 }
 

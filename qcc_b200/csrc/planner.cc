@@ -11,7 +11,7 @@
 //     one "pivot" bit are merged into a LADDER item: for every index with the pivot
 //     set, multiply by the product of the partner phases whose bit is set.  This is the
 //     controlled-phase ladder that follows each h in circuit.py:320-328 (qft): up to
-//     n-1 cu1 gates become one op whose phase is looked up in two 64-entry tables.
+//     n-1 cu1 gates become one op whose phase is looked up in two small tables.
 //  2. Pass cut.  Only U / PERM / SWAP items need their target inside the tile (they mix
 //     two amplitudes); PHASE / DIAG / LADDER items are diagonal and can run in any tile.
 //     A pass greedily collects items until it would need more than K-3 distinct targets
@@ -266,8 +266,6 @@ void split_pred(const TileMap &tm, const int *rbit, int nr, uint64_t mask, uint6
 
 void build_ladder_tables(const TileMap &tm, const QbRound &r, const Item &it, int slot, PlannedPass *pp, QbOp *op) {
   const int K = tm.K;
-  const int lo_bits = std::min(K, QB_LADDER_CHUNK);
-  const int hi_bits = K - lo_bits;
   // per tile-local position phase (1 where the position is not a partner / the pivot)
   Cplx per[QB_MAX_TILE_BITS];
   for (int k = 0; k < K; ++k) per[k] = Cplx{1.0, 0.0};
@@ -294,28 +292,29 @@ void build_ladder_tables(const TileMap &tm, const QbRound &r, const Item &it, in
     per[plp] = cmulh(per[plp], it.self);
     self_out = Cplx{1.0, 0.0};
   }
-  // Table layout (double2 units from table_off):
-  //   [0, 64)            T_lo[j & 63], stored at slot v ^ ((v >> 3) & 7) so that lanes whose
-  //                      base indices differ in bits 3..5 hit different 16-byte bank groups
-  //   [64, 64 + 2^hi)    T_hi[j >> 6]
-  // T_lo / T_hi are evaluated on the group base (round bits zero); the 8 combinations of the
-  // round's own bits, F[e], travel inside the op descriptor (constant bank).
-  // The per-tile constant lives in a second array (outph, from outph_off): the constant
+  // Table layout (double2 units from table_off), indexed by the GROUP number q of the op's round
+  // (group-index bit k drives tile-local position r.qmap[k]; the round's own bits are not group
+  // bits, so no entry is wasted on them):
+  //   [0, 32)                     T_a[q & 31]  -- one entry per lane: conflict-free reads
+  //   [32, 32 + 2^(K-3-5))        T_b[q >> 5]  -- uniform per warp: broadcast reads; the kernel
+  //                                               folds the per-tile constant into its copy
+  // The 8 combinations of the round's own bits, F[e], travel inside the op descriptor (constant
+  // bank).  The per-tile constant lives in a second array (outph, from outph_off): the constant
   // factor (self phase when the pivot is outside the tile), then one phase per outside bit.
   op->table_off = int32_t(pp->tables.size());
-  bool is_round[QB_MAX_TILE_BITS] = {false};
-  for (int k = 0; k < r.nbits; ++k) is_round[r.rbit[k]] = true;
-  pp->tables.resize(pp->tables.size() + 64);
-  for (int v = 0; v < 64; ++v) {
+  const int gbits = K - r.nbits;                       // group-index bits
+  const int a_bits = std::min(gbits, QB_LADDER_LANE_BITS);
+  const int b_bits = gbits - a_bits;
+  for (int v = 0; v < (1 << QB_LADDER_LANE_BITS); ++v) {
     Cplx p{1.0, 0.0};
-    for (int k = 0; k < lo_bits; ++k)
-      if ((v >> k & 1) && !is_round[k]) p = cmulh(p, per[k]);
-    pp->tables[size_t(op->table_off) + size_t(v ^ ((v >> 3) & 7))] = p;
+    for (int k = 0; k < a_bits; ++k)
+      if (v >> k & 1) p = cmulh(p, per[r.qmap[k]]);
+    pp->tables.push_back(p);
   }
-  for (int v = 0; v < (1 << hi_bits); ++v) {
+  for (int v = 0; v < (1 << b_bits); ++v) {
     Cplx p{1.0, 0.0};
-    for (int k = 0; k < hi_bits; ++k)
-      if ((v >> k & 1) && !is_round[lo_bits + k]) p = cmulh(p, per[lo_bits + k]);
+    for (int k = 0; k < b_bits; ++k)
+      if (v >> k & 1) p = cmulh(p, per[r.qmap[a_bits + k]]);
     pp->tables.push_back(p);
   }
   for (int e = 0; e < 8; ++e) {
@@ -444,6 +443,23 @@ void close_round(const TileMap &tm, std::vector<int> &rset, std::vector<PendingO
     pp->ops.push_back(op);
   }
   r.op_end = int32_t(pp->ops.size());
+  // Round program: three Hadamard+ladder ops on round positions 0, 1, 2 (what every round of a QFT
+  // looks like) run through a fully unrolled path in the kernel.
+  r.prog = QB_PROG_GENERIC;
+  if (nr == QB_ROUND_BITS && r.op_end - r.op_begin == 3) {
+    bool hl3 = true;
+    for (int k = 0; k < 3; ++k) {
+      const QbOp &o = pp->ops[size_t(r.op_begin + k)];
+      if (int(uint32_t(o.kind) >> 24) != QB_OPC_ULADDER + 6 + k || o.gmask != 0) hl3 = false;
+    }
+    if (hl3) {
+      const QbOp &o1 = pp->ops[size_t(r.op_begin + 1)], &o2 = pp->ops[size_t(r.op_begin + 2)];
+      auto isone = [](const double *F, int e) { return F[2 * e] == 1.0 && F[2 * e + 1] == 0.0; };
+      const bool upper = isone(o1.F, 3) && o1.F[14] == o1.F[12] && o1.F[15] == o1.F[13] && isone(o2.F, 5) &&
+                         isone(o2.F, 6) && isone(o2.F, 7);
+      r.prog = upper ? QB_PROG_HL3U : QB_PROG_HL3;
+    }
+  }
   pp->rounds.push_back(r);
   rset.clear();
   pend.clear();
@@ -668,8 +684,8 @@ std::string Plan::to_json() const {
     s += "],\"rounds\":[";
     for (size_t r = 0; r < p.rounds.size(); ++r) {
       const QbRound &R = p.rounds[r];
-      snprintf(buf, sizeof buf, "%s{\"nbits\":%d,\"rbit\":[%d,%d,%d],\"op_begin\":%d,\"op_end\":%d,\"qmap\":[",
-               r ? "," : "", R.nbits, R.rbit[0], R.rbit[1], R.rbit[2], R.op_begin, R.op_end);
+      snprintf(buf, sizeof buf, "%s{\"nbits\":%d,\"rbit\":[%d,%d,%d],\"op_begin\":%d,\"op_end\":%d,\"prog\":%d,\"qmap\":[",
+               r ? "," : "", R.nbits, R.rbit[0], R.rbit[1], R.rbit[2], R.op_begin, R.op_end, R.prog);
       s += buf;
       for (int k = 0; k < p.desc.K - R.nbits; ++k) {
         snprintf(buf, sizeof buf, "%s%d", k ? "," : "", R.qmap[k]);

@@ -26,7 +26,7 @@ struct PlannedPass {
   QbPassDesc desc{};
   std::vector<QbOp> ops;
   std::vector<QbRound> rounds;
-  std::vector<Cplx> tables;      // per ladder: T_lo[64], T_hi[2^(K-6)], F[8]  (staged in smem)
+  std::vector<Cplx> tables;      // per ladder: T_a[32], T_b[2^(K-8)], indexed by group number (staged in smem)
   std::vector<Cplx> outph;       // per ladder: constant factor, then one phase per outside bit
   std::vector<int32_t> outbits;  // per ladder: the outside partner bits
   std::vector<uint32_t> jbtab;   // per round, per group q: jb | swizzled slot(jb) << 16

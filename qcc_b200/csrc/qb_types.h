@@ -57,11 +57,11 @@ struct QbGate {
 #define QB_TILE_LOW 3        // bits 0..2 are always tile bits (8 amps = 128 B runs)
 #define QB_MAX_TILE_BITS 13  // 2^13 * 16 B = 128 KiB
 #define QB_ROUND_BITS 3      // 8 amplitudes = 16 doubles in registers per thread
-#define QB_LADDER_CHUNK 6    // ladder lookup tables are indexed by 6 tile-local bits
+#define QB_LADDER_LANE_BITS 5 // ladder lookup tables: T_a over group-index bits 0..4 (the lane), T_b over the rest
 #define QB_MAX_PASS_OPS 48   // ops of one pass travel as kernel parameters (48 * 256 B)
 #define QB_MAX_PASS_ROUNDS 16
 #define QB_MAX_SEGS 6
-#define QB_MAX_PASS_LADDERS 12  // their lookup tables (<= 200 x 16 B each) are staged in shared memory too
+#define QB_MAX_PASS_LADDERS 12  // their lookup tables (48 x 16 B each at K = 12) are staged in shared memory too
 #define QB_MF_REAL 1         // all four entries of m are real: 8 instead of 20 flops per pair
 #define QB_MF_HADAMARD 2     // m = r * [[1, 1], [1, -1]] with real r
 // Dense opcodes (bits 24..31 of QbOp::kind): one jump-table switch in the kernel.
@@ -72,6 +72,12 @@ struct QbGate {
 #define QB_OPC_SWAP 21       // +tpos
 #define QB_OPC_PHASE 24
 #define QB_OPC_LADDER 25
+
+// Round programs (QbRound::prog).  The op list stays the definition of what a round computes;
+// prog only names a fully unrolled code path in fused.cu for op lists of a known shape.
+#define QB_PROG_GENERIC 0    // interpret the op list
+#define QB_PROG_HL3 1        // exactly three Hadamard+ladder ops on round positions 0, 1, 2 in that order
+#define QB_PROG_HL3U 2       // HL3 whose in-round ladder partners are all above their pivot (the QFT shape)
 
 struct alignas(16) QbOp {   // 256 bytes; lives in the kernel parameters (constant bank)
   int32_t kind;      // QbKind (never DIAG/NOP: the planner lowers those) | tpos << 8 | mflags << 16 | opcode << 24
@@ -94,6 +100,7 @@ struct QbRound {
   int32_t rbit[QB_ROUND_BITS];       // tile-local positions, ascending
   int32_t qmap[QB_MAX_TILE_BITS];    // local position driven by group-index bit k
   int32_t op_begin, op_end;          // range in the pass's op array
+  int32_t prog;                      // QB_PROG_*: the kernel's specialised code path for this round's op list
 };
 
 struct QbPassDesc {

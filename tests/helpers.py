@@ -110,7 +110,6 @@ def interpret_plan(plan_json: str, n: int, gates, psi: np.ndarray) -> np.ndarray
     outph = np.array([complex(x, y) for x, y in p["outph"]], dtype=np.complex128)
     jbtab = np.array(p["jbtab"], dtype=np.int64).reshape(len(p["rounds"]), 1 << (K - 3))
     outbits = p["outbits"]
-    hi_bits = max(K - 6, 0)
     for ri, R in enumerate(p["rounds"]):
       assert R["nbits"] == 3
       rbit = R["rbit"]
@@ -180,10 +179,8 @@ def interpret_plan(plan_json: str, n: int, gates, psi: np.ndarray) -> np.ndarray
           for k in range(op["nout"]):
             bit = outbits[op["out_off"] + k]
             pout = np.where((base >> bit) & 1 == 1, pout * outph[cbase + 1 + k], pout)
-          lo = jb & 63
-          c = pout[:, None] * tables[t0 + (lo ^ ((lo >> 3) & 7))][None, :]   # T_lo is stored bank-swizzled
-          if hi_bits:
-            c = c * tables[t0 + 64 + (jb >> 6)][None, :]
+          # tables are indexed by the group number: T_a[q & 31] (the lane), T_b[q >> 5]
+          c = pout[:, None] * tables[t0 + (q & 31)][None, :] * tables[t0 + 32 + (q >> 5)][None, :]
           F = np.array([complex(op["F"][2 * e], op["F"][2 * e + 1]) for e in range(8)])
           for e in range(8):
             if (e & lad_rmask) == lad_rwant:
