@@ -71,7 +71,7 @@ struct FusedParams {
   const double2 *outph;
   const int32_t *outbits;
   const uint32_t *jbtab;
-  int debug;  // timing experiments only -- 1: skip the op loop, 2: skip the rounds, 4: skip the store, 8: skip the load, 16: no round programs, 32: round programs read the group table
+  int debug;  // timing experiments only -- 1: skip the op loop, 2: skip the rounds, 4: skip the store, 8: skip the load, 16: no round programs, 32: (unused), 64: CTA barrier after every round
   // per copy iteration i (thread t moves tile-local index t + 256 i): global offset of index 256 i
   // in units of 8 amplitudes, and the XOR that takes the byte slot of t to the byte slot of t + 256 i
   uint32_t io_goff[(1 << QB_MAX_TILE_BITS) / kFThreads];
@@ -223,7 +223,7 @@ __device__ __forceinline__ void hladder(double2 (&a)[8], double r, double2 cf, c
 // phase, the x' path as one multiply).
 // UPPER: the ladder partners inside the round are all above their pivot, so stage 1 has one
 // non-trivial in-round phase and stage 2 none (true for the QFT; otherwise all of F is used).
-template <bool UPPER, bool FULL>
+template <bool UPPER, bool FULL, bool SCALED>
 __device__ __forceinline__ void round_hl3(const uint32_t tile_sa, const uint32_t tab_sa,
                                           const uint32_t *__restrict__ jbt, const QbOp *__restrict__ o,
                                           const QbRound *__restrict__ R, const RoundAux *__restrict__ X,
@@ -267,15 +267,17 @@ __device__ __forceinline__ void round_hl3(const uint32_t tile_sa, const uint32_t
     // stage 0: pairs (e, e|1)
     {
       double2 c0 = cmul(lds128(ta0), lds128(ta0 - lane16 + tboff));
-      c0.x *= s;
-      c0.y *= s;
+      if (SCALED) {
+        c0.x *= s;
+        c0.y *= s;
+      }
       const double2 p3 = cmul(c0, F0[3]), p5 = cmul(c0, F0[5]), p7 = cmul(c0, F0[7]);
 #pragma unroll
       for (int e = 0; e < 8; e += 2) {
         const double2 x = a[e], y = a[e | 1];
         const double2 ph = e == 0 ? c0 : (e == 2 ? p3 : (e == 4 ? p5 : p7));
         const double2 d = make_double2(x.x - y.x, x.y - y.y);
-        a[e] = make_double2(s * (x.x + y.x), s * (x.y + y.y));
+        a[e] = SCALED ? make_double2(s * (x.x + y.x), s * (x.y + y.y)) : make_double2(x.x + y.x, x.y + y.y);
         a[e | 1] = cmul(d, ph);
       }
     }
@@ -342,6 +344,14 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+// Between two rounds.  Rounds of one run (QbRound::nobar, planner.cc assign_group_maps) keep every
+// warp inside its own sub-cube of the tile, so only the lanes of a warp have to see each other's
+// stores; otherwise the whole CTA meets.
+__device__ __forceinline__ void round_sync(bool warp_only) {
+  if (warp_only) __syncwarp();
+  else __syncthreads();
+}
+
 // FULL: the tile has a multiple of 256 groups (K >= 11), so the group loop has a trip count that
 // is uniform across the CTA and needs no bounds test.  That matters beyond the saved compare: with a
 // thread-dependent loop condition the compiler must treat the op loop inside as divergent and keeps
@@ -365,8 +375,6 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
   const uint32_t tid = threadIdx.x;
   double2 *__restrict__ psi = P.psi;
 
-  // ---- STAGE (once per CTA): ladder tables -> shared memory ---------------------------------
-  for (int i = tid; i < P.desc.ntable; i += kFThreads) s_tab[i] = __ldg(P.tables + i);
 
   // Tile <-> HBM addressing.  Thread t moves tile-local indices j = t + 256 i.  Both the global
   // offset of j (its bits scattered to tile_bits[]) and its swizzled slot are linear over XOR and
@@ -382,7 +390,6 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
   const bool io_on = tid < tileN;
   const uint32_t tile_sa = uint32_t(__cvta_generic_to_shared(tile));
   const uint32_t tab_sa = uint32_t(__cvta_generic_to_shared(s_tab));
-  __syncthreads();
 
   const uint32_t ntiles = 1u << (P.nbits - K);
   const uint64_t tmask = P.desc.tile_mask;
@@ -429,6 +436,9 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
   const int nb_tab = gbits > QB_LADDER_LANE_BITS ? 1 << (gbits - QB_LADDER_LANE_BITS) : 1;  // entries of T_b
   uint64_t base = blockIdx.x < ntiles ? tile_base(blockIdx.x) : 0;
   if (blockIdx.x < ntiles) issue_load(base);
+  // ---- STAGE (once per CTA, behind the first tile's copy): ladder tables -> shared memory ----
+  for (int i = tid; i < P.desc.ntable; i += kFThreads) s_tab[i] = __ldg(P.tables + i);
+  __syncthreads();
   for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const uint32_t tn = t + gridDim.x;
     const bool more = tn < ntiles;
@@ -473,9 +483,16 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
       const int ob = R->op_begin, oe = (P.debug & 1) ? R->op_begin : R->op_end;
       const uint32_t *jbt = P.jbtab + (size_t(r) << P.desc.ngroups_log2);
       if (FAST || (R->prog != QB_PROG_GENERIC && !(P.debug & (1 | 16)))) {
-        if (R->prog == QB_PROG_HL3U) round_hl3<true, FULL>(tile_sa, tab_sa, jbt, s_ops + ob, R, P.aux + r, ngroups, tid);
-        else round_hl3<false, FULL>(tile_sa, tab_sa, jbt, s_ops + ob, R, P.aux + r, ngroups, tid);
-        __syncthreads();
+        const RoundAux *X = P.aux + r;
+        const bool upper = R->prog == QB_PROG_HL3U;
+        if (X->s != 1.0) {
+          if (upper) round_hl3<true, FULL, true>(tile_sa, tab_sa, jbt, s_ops + ob, R, X, ngroups, tid);
+          else round_hl3<false, FULL, true>(tile_sa, tab_sa, jbt, s_ops + ob, R, X, ngroups, tid);
+        } else {
+          if (upper) round_hl3<true, FULL, false>(tile_sa, tab_sa, jbt, s_ops + ob, R, X, ngroups, tid);
+          else round_hl3<false, FULL, false>(tile_sa, tab_sa, jbt, s_ops + ob, R, X, ngroups, tid);
+        }
+        round_sync(R->nobar && !(P.debug & 64));
         continue;
       }
       if (!FAST) {
@@ -573,7 +590,7 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
         for (int e = 0; e < 8; ++e)
           tile[pb ^ ((e & 1) ? d0 : 0u) ^ ((e & 2) ? d1 : 0u) ^ ((e & 4) ? d2 : 0u)] = a[e];
       }
-      __syncthreads();
+      round_sync(R->nobar && !(P.debug & 64));
       }
     }
 
@@ -680,20 +697,38 @@ cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cuda
       X.pbi[git] = swz_h(jb) << 4;
     }
   }
+  // The Hadamard scales are plain scalars: collect those of all program rounds of the pass in the
+  // first one (a round with s == 1 skips the multiplies).
+  {
+    int first = -1;
+    double prod = 1.0;
+    for (int r = 0; r < p.desc.nrounds; ++r)
+      if (p.rounds[r].prog != QB_PROG_GENERIC) {
+        if (first < 0) first = r;
+        prod *= P.aux[r].s;
+        P.aux[r].s = 1.0;
+      }
+    static const bool no_hoist = getenv("QCC_B200_NO_SCALE_HOIST") != nullptr;
+    if (first >= 0 && !no_hoist) P.aux[first].s = prod;
+    else if (no_hoist)
+      for (int r = 0; r < p.desc.nrounds; ++r)
+        if (p.rounds[r].prog != QB_PROG_GENERIC) {
+          P.aux[r].s = 1.0;
+          for (int k = 0; k < 3; ++k) P.aux[r].s *= p.ops[p.rounds[r].op_begin + k].m[0];
+        }
+  }
   // FAST: no round needs the op interpreter (and the debug switches that fall back to it are off)
   bool fast = !(dbg & (1 | 16));
   for (int r = 0; r < p.desc.nrounds; ++r)
     if (p.rounds[r].prog == QB_PROG_GENERIC) fast = false;
-  // Persistent CTAs, as many as fit an SM (3 for FAST passes at K = 12: 64 KiB tile + 9 KiB of
-  // tables each; else 2), each walking tiles blockIdx.x, +grid, ... so that the per-CTA staging
-  // (ladder tables) is paid once per SM slot, not once per tile.  The CTAs of an SM drift out of
-  // phase, so one streams its tile while the others compute.
-  int per_sm = int(kSmemSM / (smem + 1024));
-  per_sm = per_sm < 1 ? 1 : (per_sm > (fast ? 3 : 2) ? (fast ? 3 : 2) : per_sm);
-  static const int persist = getenv("QCC_B200_FUSED_PERSIST") ? atoi(getenv("QCC_B200_FUSED_PERSIST")) : -1;
-  if (persist >= 0) per_sm = persist;
+  // One CTA per tile by default: up to 3 CTAs (FAST passes at K = 12: 64 KiB tile + 9 KiB of tables
+  // each; else 2) are resident per SM, and because they start and finish at different times one
+  // streams its tile while the others compute.  QCC_B200_FUSED_PERSIST=n instead launches n
+  // persistent CTAs per SM that walk the tiles (measured 4 % slower on QFT-30: the per-CTA table
+  // staging it saves is small, and the hardware scheduler balances the SMs better).
+  static const int persist = getenv("QCC_B200_FUSED_PERSIST") ? atoi(getenv("QCC_B200_FUSED_PERSIST")) : 0;
   unsigned blocks = ntiles;
-  if (per_sm > 0 && ntiles > unsigned(per_sm * g_sms)) blocks = unsigned(per_sm * g_sms);
+  if (persist > 0 && ntiles > unsigned(persist * g_sms)) blocks = unsigned(persist * g_sms);
   const bool full = ((1u << (K - 3)) % kFThreads) == 0;
   if (full && fast) k_fused_pass<true, true><<<blocks, kFThreads, smem, st>>>(P);
   else if (full) k_fused_pass<true, false><<<blocks, kFThreads, smem, st>>>(P);

@@ -333,39 +333,108 @@ void build_ladder_tables(const TileMap &tm, const QbRound &r, const Item &it, in
   op->flags = slot;
 }
 
-void close_round(const TileMap &tm, std::vector<int> &rset, std::vector<PendingOp> &pend, int *nladders,
-                 PlannedPass *pp) {
-  if (pend.empty()) {
-    rset.clear();
-    return;
+// One round as collected by emit_pass before the group maps are assigned.
+struct RoundPlan {
+  std::vector<int> rset;        // round bits (tile-local positions), padded to nr and sorted
+  std::vector<PendingOp> pend;
+  std::vector<int> order;       // group-index bit k -> tile-local position (qmap)
+  bool nobar = false;           // the next round works on the same per-warp sub-cube: no CTA barrier after
+};
+
+void pad_round_bits(const TileMap &tm, std::vector<int> *rset) {
+  const int nr = std::min(tm.K, QB_ROUND_BITS);
+  // pad the round's bit set with the lowest unused local positions
+  for (int k = 0; k < tm.K && int(rset->size()) < nr; ++k)
+    if (std::find(rset->begin(), rset->end(), k) == rset->end()) rset->push_back(k);
+  std::sort(rset->begin(), rset->end());
+}
+
+// `cand` in the order they should be used, except that the first three are one bit of each
+// swizzle class when available.  The tile is stored swizzled (fused.cu): the 16-byte bank group of
+// local index j is (j ^ j>>3 ^ j>>6 ^ j>>9 ...) & 7, so local bit b feeds bank-group bit b % 3;
+// giving group-index bits 0,1,2 one bit of each class makes 8 consecutive lanes land in 8 distinct
+// bank groups.
+std::vector<int> class_first(std::vector<int> cand) {
+  std::vector<int> order;
+  for (int cls = 0; cls < 3; ++cls)
+    for (size_t k = 0; k < cand.size(); ++k)
+      if (cand[k] >= 0 && cand[k] % 3 == cls) {
+        order.push_back(cand[k]);
+        cand[k] = -1;
+        break;
+      }
+  for (int b : cand)
+    if (b >= 0) order.push_back(b);
+  return order;
+}
+
+// Group maps.  Default: the free local bits in class-first order.  For tiles with >= 256 groups
+// (K >= 11) consecutive rounds are collected into RUNS that share one (K-3)-bit sub-cube S of the
+// tile containing all their round bits: the group-index bits that enumerate a warp's work (lane
+// bits 0..4 and the iteration bits 8..) are mapped into S, the warp number (bits 5..7) to the 3
+// tile bits outside S.  Every warp then reads and writes the same 2^(K-3) amplitudes in every round
+// of the run, so the rounds of a run are separated by a warp-level sync only and the warps of a
+// CTA drift apart instead of meeting at a barrier after every round.
+void assign_group_maps(const TileMap &tm, std::vector<RoundPlan> *rounds) {
+  const int K = tm.K;
+  const int nr = std::min(K, QB_ROUND_BITS);
+  const int gbits = K - nr;
+  for (RoundPlan &rp : *rounds) {
+    std::vector<int> freeb;
+    for (int k = 0; k < K; ++k)
+      if (std::find(rp.rset.begin(), rp.rset.end(), k) == rp.rset.end()) freeb.push_back(k);
+    rp.order = class_first(freeb);
+    rp.nobar = false;
   }
+  if (gbits < 8) return;  // fewer than 256 groups: one barrier per round
+  for (size_t i = 0; i < rounds->size();) {
+    std::vector<int> S = (*rounds)[i].rset;
+    size_t j = i + 1;
+    for (; j < rounds->size(); ++j) {
+      std::vector<int> U = S;
+      for (int b : (*rounds)[j].rset)
+        if (std::find(U.begin(), U.end(), b) == U.end()) U.push_back(b);
+      if (int(U.size()) > gbits) break;
+      S = U;
+    }
+    if (j - i >= 2) {
+      // pad S to gbits bits, preferring the lowest tile bits
+      for (int k = 0; k < K && int(S.size()) < gbits; ++k)
+        if (std::find(S.begin(), S.end(), k) == S.end()) S.push_back(k);
+      std::sort(S.begin(), S.end());
+      std::vector<int> W;
+      for (int k = 0; k < K; ++k)
+        if (std::find(S.begin(), S.end(), k) == S.end()) W.push_back(k);
+      for (size_t r = i; r < j; ++r) {
+        RoundPlan &rp = (*rounds)[r];
+        std::vector<int> in_s;
+        for (int b : S)
+          if (std::find(rp.rset.begin(), rp.rset.end(), b) == rp.rset.end()) in_s.push_back(b);
+        in_s = class_first(in_s);  // gbits - 3 bits: 5 lane bits, then the iteration bits
+        std::vector<int> order(size_t(gbits), -1);
+        size_t u = 0;
+        for (int k = 0; k < 5; ++k) order[size_t(k)] = in_s[u++];
+        for (int k = 8; k < gbits; ++k) order[size_t(k)] = in_s[u++];
+        for (int k = 5; k < 8; ++k) order[size_t(k)] = W[size_t(k - 5)];
+        rp.order = order;
+        rp.nobar = r + 1 < j;
+      }
+    }
+    i = j;
+  }
+}
+
+void close_round(const TileMap &tm, RoundPlan &rp, int *nladders, PlannedPass *pp) {
+  std::vector<int> &rset = rp.rset;
+  std::vector<PendingOp> &pend = rp.pend;
+  const std::vector<int> &order = rp.order;
   QbRound r{};
   const int K = tm.K;
   const int nr = std::min(K, QB_ROUND_BITS);
-  // pad the round's bit set with the lowest unused local positions
-  for (int k = 0; k < K && int(rset.size()) < nr; ++k)
-    if (std::find(rset.begin(), rset.end(), k) == rset.end()) rset.push_back(k);
-  std::sort(rset.begin(), rset.end());
   r.nbits = nr;
   for (int k = 0; k < nr; ++k) r.rbit[k] = rset[k];
-  // group-index bit -> local position.  The tile is stored swizzled (fused.cu): the
-  // 16-byte bank group of local index j is (j ^ j>>3 ^ j>>6 ^ j>>9 ...) & 7, so local bit
-  // b feeds bank-group bit b % 3.  Give group-index bits 0,1,2 one free local bit of each
-  // class so 8 consecutive lanes land in 8 distinct bank groups.
-  std::vector<int> freeb;
-  for (int k = 0; k < K; ++k)
-    if (std::find(rset.begin(), rset.end(), k) == rset.end()) freeb.push_back(k);
-  std::vector<int> order;
-  for (int cls = 0; cls < 3; ++cls)
-    for (size_t k = 0; k < freeb.size(); ++k)
-      if (freeb[k] >= 0 && freeb[k] % 3 == cls) {
-        order.push_back(freeb[k]);
-        freeb[k] = -1;
-        break;
-      }
-  for (int b : freeb)
-    if (b >= 0) order.push_back(b);
   for (size_t k = 0; k < order.size(); ++k) r.qmap[k] = order[k];
+  r.nobar = rp.nobar ? 1 : 0;
   // per-group base index and its swizzled shared-memory slot, so the kernel does one load
   // instead of a K-3 step bit scatter per group per round
   for (uint32_t q = 0; q < (1u << (K - 3)); ++q) {
@@ -377,23 +446,75 @@ void close_round(const TileMap &tm, std::vector<int> &rset, std::vector<PendingO
     pp->jbtab.push_back(jb | ((jb ^ (x & 7u)) << 16));
   }
   r.op_begin = int32_t(pp->ops.size());
+  // The tail of a QFT: "h + one cu1" and a bare h are not ladders, but when the whole round is three
+  // Hadamards on round positions 0, 1, 2, each followed by at most one ladder / two-bit phase on its
+  // own target, giving the short ones a one-partner / empty ladder lets the round run as the
+  // unrolled Hadamard+ladder program instead of through the op interpreter.
+  std::vector<Item> synth;
+  synth.reserve(pend.size());
+  std::vector<const Item *> lad_of(pend.size(), nullptr);  // per U op: its (possibly synthesized) ladder
+  std::vector<char> skip(pend.size(), 0);
+  {
+    bool ok = nr == QB_ROUND_BITS;
+    size_t idx = 0;
+    std::vector<std::pair<size_t, size_t>> found;  // (U index, follower index or npos)
+    for (int k = 0; ok && k < 3; ++k) {
+      if (idx >= pend.size()) { ok = false; break; }
+      const Item &u = *pend[idx].it;
+      const double *m = u.g.m;
+      const bool had = u.kind == QB_K_U && u.g.ctl_mask == 0 && m[1] == 0.0 && m[3] == 0.0 && m[5] == 0.0 &&
+                       m[7] == 0.0 && m[0] == m[2] && m[0] == m[4] && m[0] == -m[6];
+      if (!had || tm.lpos[u.g.target] != r.rbit[k]) { ok = false; break; }
+      size_t fol = size_t(-1);
+      if (idx + 1 < pend.size()) {
+        const Item &f = *pend[idx + 1].it;
+        const uint64_t fb = f.g.ctl_mask | (uint64_t(1) << f.g.target);
+        if (f.kind == QB_K_LADDER && f.pivot == u.g.target) fol = idx + 1;
+        else if (f.kind == QB_K_PHASE && __builtin_popcountll(fb) == 2 && (fb >> u.g.target & 1)) fol = idx + 1;
+      }
+      found.push_back({idx, fol});
+      idx += fol == size_t(-1) ? 1 : 2;
+    }
+    if (ok && idx == pend.size()) {
+      for (auto &uf : found) {
+        const Item &u = *pend[uf.first].it;
+        if (uf.second != size_t(-1) && pend[uf.second].it->kind == QB_K_LADDER) {
+          lad_of[uf.first] = pend[uf.second].it;
+        } else {
+          Item lad;
+          lad.kind = QB_K_LADDER;
+          lad.pivot = u.g.target;
+          if (uf.second != size_t(-1)) {
+            const Item &f = *pend[uf.second].it;
+            const uint64_t fb = (f.g.ctl_mask | (uint64_t(1) << f.g.target)) & ~(uint64_t(1) << u.g.target);
+            lad.pbits.push_back(__builtin_ctzll(fb));
+            lad.pphase.push_back(Cplx{f.g.m[6], f.g.m[7]});
+          }
+          synth.push_back(lad);
+          lad_of[uf.first] = &synth.back();
+        }
+        if (uf.second != size_t(-1)) skip[uf.second] = 1;
+      }
+    }
+  }
   for (size_t pi = 0; pi < pend.size(); ++pi) {
+    if (skip[pi]) continue;
     const PendingOp &po = pend[pi];
     const Item &it = *po.it;
     QbOp op{};
     op.kind = it.kind;
     op.tpos = 0;
-    if (it.kind == QB_K_U && it.g.ctl_mask == 0 && pi + 1 < pend.size() &&
-        pend[pi + 1].it->kind == QB_K_LADDER && pend[pi + 1].it->pivot == it.g.target) {
+    if (lad_of[pi] || (it.kind == QB_K_U && it.g.ctl_mask == 0 && pi + 1 < pend.size() &&
+                       pend[pi + 1].it->kind == QB_K_LADDER && pend[pi + 1].it->pivot == it.g.target)) {
       // h(q) + the cu1 ladder hanging off q (circuit.py:323-326): one op, y' = (c x + d y) * phase
-      const Item &lad = *pend[pi + 1].it;
+      const Item &lad = lad_of[pi] ? *lad_of[pi] : *pend[pi + 1].it;
       op.kind = QB_K_ULADDER;
       int lp = tm.lpos[it.g.target];
       for (int k = 0; k < nr; ++k)
         if (r.rbit[k] == lp) op.tpos = k;
       memcpy(op.m, it.g.m, sizeof op.m);
       build_ladder_tables(tm, r, lad, (*nladders)++, pp, &op);
-      ++pi;
+      if (!lad_of[pi]) ++pi;
     } else if (it.kind == QB_K_LADDER) {
       op.kind = QB_K_LADDER;
       split_pred(tm, r.rbit, nr, uint64_t(1) << it.pivot, uint64_t(1) << it.pivot, &op);
@@ -461,8 +582,6 @@ void close_round(const TileMap &tm, std::vector<int> &rset, std::vector<PendingO
     }
   }
   pp->rounds.push_back(r);
-  rset.clear();
-  pend.clear();
 }
 
 void emit_pass(int nbits, int K, const std::vector<const Item *> &items, const std::vector<int> &targets_hi,
@@ -496,25 +615,34 @@ void emit_pass(int nbits, int K, const std::vector<const Item *> &items, const s
   pp.desc.K = tm.K;
   pp.desc.tile_mask = tm.mask;
   for (int k = 0; k < tm.K; ++k) pp.desc.tile_bits[k] = tm.bits[k];
-  std::vector<int> rset;
-  std::vector<PendingOp> pend;
+  std::vector<RoundPlan> rplans;
+  RoundPlan cur;
   int nlad = 0;
   const int nr = std::min(tm.K, QB_ROUND_BITS);
+  auto flush_round = [&]() {
+    if (!cur.pend.empty()) {
+      pad_round_bits(tm, &cur.rset);
+      rplans.push_back(cur);
+    }
+    cur = RoundPlan();
+  };
   for (const Item *it : items) {
     pp.ngates += it->ngates;
     pp.bytes_algorithmic_per_amp += it->bytes_per_amp;
     if (it->kind == QB_K_NOP) continue;
     if (needs_target(it->kind)) {
       int lp = tm.lpos[it->g.target];
-      if (std::find(rset.begin(), rset.end(), lp) == rset.end()) {
-        if (int(rset.size()) == nr) close_round(tm, rset, pend, &nlad, &pp);
-        rset.push_back(lp);
+      if (std::find(cur.rset.begin(), cur.rset.end(), lp) == cur.rset.end()) {
+        if (int(cur.rset.size()) == nr) flush_round();
+        cur.rset.push_back(lp);
       }
     }
-    pend.push_back(PendingOp{it, 0});
-    if (it->kind == QB_K_DIAG) pend.push_back(PendingOp{it, 1});
+    cur.pend.push_back(PendingOp{it, 0});
+    if (it->kind == QB_K_DIAG) cur.pend.push_back(PendingOp{it, 1});
   }
-  close_round(tm, rset, pend, &nlad, &pp);
+  flush_round();
+  assign_group_maps(tm, &rplans);
+  for (RoundPlan &rp : rplans) close_round(tm, rp, &nlad, &pp);
   pp.desc.nrounds = int32_t(pp.rounds.size());
   pp.desc.nops = int32_t(pp.ops.size());
   pp.desc.ntable = int32_t(pp.tables.size());
@@ -684,8 +812,8 @@ std::string Plan::to_json() const {
     s += "],\"rounds\":[";
     for (size_t r = 0; r < p.rounds.size(); ++r) {
       const QbRound &R = p.rounds[r];
-      snprintf(buf, sizeof buf, "%s{\"nbits\":%d,\"rbit\":[%d,%d,%d],\"op_begin\":%d,\"op_end\":%d,\"prog\":%d,\"qmap\":[",
-               r ? "," : "", R.nbits, R.rbit[0], R.rbit[1], R.rbit[2], R.op_begin, R.op_end, R.prog);
+      snprintf(buf, sizeof buf, "%s{\"nbits\":%d,\"rbit\":[%d,%d,%d],\"op_begin\":%d,\"op_end\":%d,\"prog\":%d,\"nobar\":%d,\"qmap\":[",
+               r ? "," : "", R.nbits, R.rbit[0], R.rbit[1], R.rbit[2], R.op_begin, R.op_end, R.prog, R.nobar);
       s += buf;
       for (int k = 0; k < p.desc.K - R.nbits; ++k) {
         snprintf(buf, sizeof buf, "%s%d", k ? "," : "", R.qmap[k]);

@@ -100,6 +100,7 @@ struct QbRound {
   int32_t rbit[QB_ROUND_BITS];       // tile-local positions, ascending
   int32_t qmap[QB_MAX_TILE_BITS];    // local position driven by group-index bit k
   int32_t op_begin, op_end;          // range in the pass's op array
+  int32_t nobar;                     // 1: the next round stays inside each warp's sub-cube (warp sync, no CTA barrier)
   int32_t prog;                      // QB_PROG_*: the kernel's specialised code path for this round's op list
 };
 

@@ -126,6 +126,21 @@ def interpret_plan(plan_json: str, n: int, gates, psi: np.ndarray) -> np.ndarray
       assert np.array_equal(jbtab[ri] >> 16, jb ^ (fold & 7))
       spread = np.array([sum(((e >> k) & 1) << rbit[k] for k in range(3)) for e in range(8)])
       je = jb[:, None] | spread[None, :]        # [group, e]
+      # rounds of one barrier-free run: warp w (groups with (q >> 5) & 7 == w) must own the same
+      # amplitudes in this round and in the next one -- the kernel only syncs the warp between them
+      if R.get("nobar"):
+        assert ng >= 256 and ri + 1 < len(p["rounds"])
+        Rn = p["rounds"][ri + 1]
+        jbn = np.zeros(ng, dtype=np.int64)
+        for k, lp in enumerate(Rn["qmap"]):
+          jbn |= ((q >> k) & 1) << lp
+        spn = np.array([sum(((e >> k) & 1) << Rn["rbit"][k] for k in range(3)) for e in range(8)])
+        jen = jbn[:, None] | spn[None, :]
+        for w in range(8):
+          mine = ((q >> 5) & 7) == w
+          assert np.array_equal(np.sort(je[mine].ravel()), np.sort(jen[mine].ravel())), "warp sub-cube changes inside a run"
+      else:
+        assert ri + 1 == len(p["rounds"]) or not R.get("nobar")
       A = T[:, je]                              # [tile, group, e]
       for op in p["ops"][R["op_begin"]:R["op_end"]]:
         tile_ok = (base & op["gmask"]) == op["gwant"]

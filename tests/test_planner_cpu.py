@@ -114,9 +114,15 @@ def test_qft30_plans_into_three_passes():
   assert len(gates) == 465
   s = plan_summary(_cabi.plan_json(30, gates, 12))
   assert s["fused"] == 3 and s["singles"] == 0
-  assert s["ladders"] == 28 and s["ops"] == 31  # 28 h+ladder, h+cu1, h, (last cu1 is a PHASE)
+  # 28 h+ladder; the h + single cu1 and the bare h of the tail get a one-partner / empty ladder so
+  # that every round is the unrolled Hadamard+ladder program (QB_PROG_HL3U == 2)
+  assert s["ladders"] == 30 and s["ops"] == 30
   plan = json.loads(_cabi.plan_json(30, gates, 12))
   assert sum(p["ngates"] for p in plan["passes"]) == 465
+  assert [len(p["rounds"]) for p in plan["passes"]] == [4, 3, 3]
+  assert all(R["prog"] == 2 for p in plan["passes"] for R in p["rounds"])
+  # rounds that share a per-warp sub-cube need no CTA barrier between them: 3 per run at K = 12
+  assert [[R["nobar"] for R in p["rounds"]] for p in plan["passes"]] == [[1, 1, 0, 0], [1, 1, 0], [1, 1, 0]]
 
 
 def test_larose_plan_is_much_shorter_than_the_gate_list():
