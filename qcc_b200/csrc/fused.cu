@@ -58,9 +58,9 @@ constexpr int kFThreads = 256;
 struct RoundAux {
   uint32_t b[3];     // byte XOR that sets round bit k in a swizzled slot
   uint32_t pbi[(1 << (QB_MAX_TILE_BITS - 3)) / kFThreads];  // byte slot of group 256 * git
-  uint32_t ta[3];    // byte offset of the three ladders' tables
-  uint32_t pad_;
-  double s;          // product of the three Hadamard scales
+  uint32_t jbi[(1 << (QB_MAX_TILE_BITS - 3)) / kFThreads];  // tile-local base index of group 256 * git
+  uint32_t ta[3];    // HL3: byte offset of the three ladders' tables
+  double s;          // HL3: product of the three Hadamard scales
 };
 
 struct FusedParams {
@@ -174,6 +174,21 @@ __device__ __forceinline__ void swap_masked(double2 (&a)[8], uint32_t rmask, uin
       a[e] = a[e | (1 << TP)];
       a[e | (1 << TP)] = x;
     }
+  }
+}
+
+// Parity-controlled swap (QB_K_PARSWAP): pair e of position TP is swapped when bit e of sel is set
+// (sel = parity table of the round's own control bits, complemented when the parity of the control
+// bits outside the round -- tile-local and outside-tile -- xor the constant flip is odd).
+template <int TP>
+__device__ __forceinline__ void parswap(double2 (&a)[8], uint32_t sel) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    if (e & (1 << TP)) continue;
+    const bool sw = (sel >> e) & 1u;
+    const double2 x = a[e], y = a[e | (1 << TP)];
+    a[e] = make_double2(sw ? y.x : x.x, sw ? y.y : x.y);
+    a[e | (1 << TP)] = make_double2(sw ? x.x : y.x, sw ? x.y : y.y);
   }
 }
 
@@ -328,6 +343,74 @@ __device__ __forceinline__ void round_hl3(const uint32_t tile_sa, const uint32_t
   }
 }
 
+// ---- round program UX: uncontrolled butterflies and parity swaps only ------------------------
+// Every round of larose_benchmark.py:47-54 after scheduling (h.v on three qubits; the cx fan-in onto
+// qubit 0 as ONE parity swap), and the single-qubit layers of supremacy-style circuits.  No
+// predicates to evaluate, 9 opcodes, matrices straight from the constant bank: the interpretive
+// overhead per op is a uniform load and one indexed branch against 32-64 fp64 instructions of work.
+template <bool FULL>
+__device__ __forceinline__ void round_ux(const uint32_t tile_sa, const uint32_t *__restrict__ jbt,
+                                         const QbOp *__restrict__ o, const int nops,
+                                         const QbRound *__restrict__ R, const RoundAux *__restrict__ X,
+                                         const uint32_t ngroups, const uint32_t tid, const uint64_t base) {
+  const uint32_t giters = FULL ? (ngroups / kFThreads) : ((ngroups + kFThreads - 1) / kFThreads);
+  const uint32_t b0 = X->b[0], b1 = X->b[1], b2 = X->b[2];
+  uint32_t jb_t = 0;
+  if (FULL) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) jb_t |= ((tid >> k) & 1u) << R->qmap[k];
+  }
+  const uint32_t pb_t = swz(jb_t) << 4;
+#pragma unroll 1
+  for (uint32_t git = 0; git < giters; ++git) {
+    const uint32_t q = git * kFThreads + tid;
+    uint32_t pb, jb;
+    if (FULL) {
+      pb = pb_t ^ X->pbi[git];
+      jb = jb_t | X->jbi[git];
+    } else {
+      if (q >= ngroups) break;
+      const uint32_t w = __ldg(jbt + q);
+      jb = w & 0xffffu;
+      pb = (w >> 12) & 0xffff0u;
+    }
+    double2 a[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      a[e] = lds128(tile_sa + (pb ^ ((e & 1) ? b0 : 0u) ^ ((e & 2) ? b1 : 0u) ^ ((e & 4) ? b2 : 0u)));
+#pragma unroll 1
+    for (int oi = 0; oi < nops; ++oi) {
+      const QbOp *op = o + oi;
+      const double2 *mp = reinterpret_cast<const double2 *>(op->m);
+      const int opc = int(uint32_t(op->kind) >> 24);
+      switch (opc) {
+        case QB_OPC_U_ALL + 0: { const Mat m{mp[0], mp[1], mp[2], mp[3]}; bfly_all<0, false>(a, m); break; }
+        case QB_OPC_U_ALL + 1: { const Mat m{mp[0], mp[1], mp[2], mp[3]}; bfly_all<1, false>(a, m); break; }
+        case QB_OPC_U_ALL + 2: { const Mat m{mp[0], mp[1], mp[2], mp[3]}; bfly_all<2, false>(a, m); break; }
+        case QB_OPC_U_ALL + 3: case QB_OPC_U_ALL + 4: case QB_OPC_U_ALL + 5: {
+          Mat m;
+          m.a.x = mp[0].x; m.b.x = mp[1].x; m.c.x = mp[2].x; m.d.x = mp[3].x;
+          if (opc == QB_OPC_U_ALL + 3) bfly_all<0, true>(a, m);
+          else if (opc == QB_OPC_U_ALL + 4) bfly_all<1, true>(a, m);
+          else bfly_all<2, true>(a, m);
+          break;
+        }
+        default: {  // QB_OPC_PARSWAP + tpos
+          const uint32_t odd = (uint32_t(__popcll(base & op->gmask)) + uint32_t(__popc(jb & op->lmask)) + op->rwant) & 1u;
+          const uint32_t sel = op->lwant ^ (0u - odd);
+          if (opc == QB_OPC_PARSWAP + 0) parswap<0>(a, sel);
+          else if (opc == QB_OPC_PARSWAP + 1) parswap<1>(a, sel);
+          else parswap<2>(a, sel);
+          break;
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      sts128(tile_sa + (pb ^ ((e & 1) ? b0 : 0u) ^ ((e & 2) ? b1 : 0u) ^ ((e & 4) ? b2 : 0u)), a[e]);
+  }
+}
+
 #define QB_DISPATCH_TP(tp, CALL0, CALL1, CALL2) \
   do {                                          \
     if ((tp) == 0) { CALL0; }                   \
@@ -444,7 +527,8 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
     const bool more = tn < ntiles;
     // which ops apply to this tile at all (their controls outside the tile): one bit per op
     if (!FAST && tid < 64) {
-      const bool on = int(tid) < P.desc.nops && (base & s_ops[tid].gmask) == s_ops[tid].gwant;
+      const bool on = int(tid) < P.desc.nops && ((s_ops[tid].kind & 0xff) == QB_K_PARSWAP ||  // its gmask is a parity
+                                                  (base & s_ops[tid].gmask) == s_ops[tid].gwant);
       const uint32_t bal = __ballot_sync(0xffffffffu, on);
       if ((tid & 31u) == 0) s_active[tid >> 5] = bal;
     }
@@ -485,7 +569,9 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
       if (FAST || (R->prog != QB_PROG_GENERIC && !(P.debug & (1 | 16)))) {
         const RoundAux *X = P.aux + r;
         const bool upper = R->prog == QB_PROG_HL3U;
-        if (X->s != 1.0) {
+        if (R->prog == QB_PROG_UX) {
+          round_ux<FULL>(tile_sa, jbt, s_ops + ob, oe - ob, R, X, ngroups, tid, base);
+        } else if (X->s != 1.0) {
           if (upper) round_hl3<true, FULL, true>(tile_sa, tab_sa, jbt, s_ops + ob, R, X, ngroups, tid);
           else round_hl3<false, FULL, true>(tile_sa, tab_sa, jbt, s_ops + ob, R, X, ngroups, tid);
         } else {
@@ -541,6 +627,14 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
               case 7: hladder<1>(a, mp[0].x, c, F); break;
               default: hladder<2>(a, mp[0].x, c, F); break;
             }
+            continue;
+          }
+          if (opc >= QB_OPC_PARSWAP) {
+            const uint32_t odd = (uint32_t(__popcll(base & op->gmask)) + uint32_t(__popc(jb & op->lmask)) + op->rwant) & 1u;
+            const uint32_t sel = op->lwant ^ (0u - odd);
+            if (opc == QB_OPC_PARSWAP + 0) parswap<0>(a, sel);
+            else if (opc == QB_OPC_PARSWAP + 1) parswap<1>(a, sel);
+            else parswap<2>(a, sel);
             continue;
           }
           const uint32_t rmask = op->rmask, rwant = op->rwant;
@@ -618,7 +712,6 @@ size_t fused_smem_bytes(int K, int ntable) {
 }
 
 constexpr size_t kSmemLimit = 227 * 1024;
-constexpr size_t kSmemSM = 228 * 1024;  // per SM, shared by the resident CTAs (+ 1 KiB reserved each)
 int g_sms = 0;
 
 template <bool FULL, bool FAST>
@@ -686,24 +779,29 @@ cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cuda
     memset(&X, 0, sizeof X);
     if (R.prog == QB_PROG_GENERIC) continue;
     X.s = 1.0;
+    const bool hl = R.prog == QB_PROG_HL3 || R.prog == QB_PROG_HL3U;
     for (int k = 0; k < 3; ++k) {
       X.b[k] = swz_h(1u << R.rbit[k]) << 4;
-      X.ta[k] = uint32_t(p.ops[R.op_begin + k].table_off) << 4;
-      X.s *= p.ops[R.op_begin + k].m[0];
+      if (hl) {
+        X.ta[k] = uint32_t(p.ops[R.op_begin + k].table_off) << 4;
+        X.s *= p.ops[R.op_begin + k].m[0];
+      }
     }
     for (uint32_t git = 0; git < (1u << (K - 3)) / kFThreads; ++git) {
       uint32_t jb = 0;
       for (int k = 8; k < K - 3; ++k) jb |= ((git >> (k - 8)) & 1u) << R.qmap[k];
       X.pbi[git] = swz_h(jb) << 4;
+      X.jbi[git] = jb;
     }
   }
+  auto is_hl = [&](int r) { return p.rounds[r].prog == QB_PROG_HL3 || p.rounds[r].prog == QB_PROG_HL3U; };
   // The Hadamard scales are plain scalars: collect those of all program rounds of the pass in the
   // first one (a round with s == 1 skips the multiplies).
   {
     int first = -1;
     double prod = 1.0;
     for (int r = 0; r < p.desc.nrounds; ++r)
-      if (p.rounds[r].prog != QB_PROG_GENERIC) {
+      if (is_hl(r)) {
         if (first < 0) first = r;
         prod *= P.aux[r].s;
         P.aux[r].s = 1.0;
@@ -712,7 +810,7 @@ cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cuda
     if (first >= 0 && !no_hoist) P.aux[first].s = prod;
     else if (no_hoist)
       for (int r = 0; r < p.desc.nrounds; ++r)
-        if (p.rounds[r].prog != QB_PROG_GENERIC) {
+        if (is_hl(r)) {
           P.aux[r].s = 1.0;
           for (int k = 0; k < 3; ++k) P.aux[r].s *= p.ops[p.rounds[r].op_begin + k].m[0];
         }

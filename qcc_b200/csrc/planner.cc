@@ -17,12 +17,20 @@
 //     A pass greedily collects items until it would need more than K-3 distinct targets
 //     above bit 2.  Tile bits = {0,1,2} + targets, padded with the lowest unused bits so
 //     that tiles are as contiguous in memory as possible.
-//  3. Round cut.  Inside a pass, ops are greedily grouped while their targets fit in 3
-//     tile-local bits (8 amplitudes per thread in registers).
+//  3. Round cut.  Inside a pass, ops are grouped while their targets fit in 3 tile-local bits
+//     (8 amplitudes per thread in registers).  The items of a pass are list-scheduled over
+//     their commutation DAG (schedule_rounds): uncontrolled U's on distinct bits are collected
+//     three to a round (the predicate-free UX round program of fused.cu), diagonal items ride along
+//     wherever they are ready, and a bit that many later gates target (the cx fan-in of
+//     larose_benchmark.py:52-53) is taken into a round only when that work can finish there.
+//     x / cx gates onto one target that end up adjacent become ONE parity-controlled swap
+//     (PARSWAP).  The in-order cut is kept as the fallback whenever scheduling does not
+//     need fewer rounds.
 #include "planner.h"
 
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -48,6 +56,30 @@ struct Item {
 };
 
 bool needs_target(int kind) { return kind == QB_K_U || kind == QB_K_PERM || kind == QB_K_SWAP; }
+
+uint64_t item_bits(const Item &it) {
+  if (it.kind == QB_K_LADDER) {
+    uint64_t b = uint64_t(1) << it.pivot;
+    for (int p : it.pbits) b |= uint64_t(1) << p;
+    return b;
+  }
+  return it.g.ctl_mask | (uint64_t(1) << it.g.target);
+}
+
+// Sufficient test.  An item is diagonal in every bit it touches except the target of a
+// U / PERM / SWAP ("mix" bit).  Two items commute when neither mixes a bit the other touches; two
+// pure X-type gates on the same target (x, cx, ccx) commute as well: X^f X^g = X^(f xor g).
+bool items_commute(const Item &a, const Item &b) {
+  const uint64_t ba = item_bits(a), bb = item_bits(b);
+  const uint64_t ma = needs_target(a.kind) ? uint64_t(1) << a.g.target : 0;
+  const uint64_t mb = needs_target(b.kind) ? uint64_t(1) << b.g.target : 0;
+  if (!(ma & bb) && !(mb & ba)) return true;
+  if (a.kind == QB_K_SWAP && b.kind == QB_K_SWAP && a.g.target == b.g.target) return true;
+  return false;
+}
+
+// x / cx: a pure swap with at most one control -- the building block of a PARSWAP op
+bool is_parity_x(const Item &it) { return it.kind == QB_K_SWAP && __builtin_popcountll(it.g.ctl_mask) <= 1; }
 
 struct Merged {
   QbGate g;
@@ -424,6 +456,146 @@ void assign_group_maps(const TileMap &tm, std::vector<RoundPlan> *rounds) {
   }
 }
 
+// Round cut in program order: a new round whenever a fourth target bit shows up.
+std::vector<RoundPlan> inorder_rounds(const TileMap &tm, const std::vector<const Item *> &items) {
+  std::vector<RoundPlan> out;
+  RoundPlan cur;
+  const int nr = std::min(tm.K, QB_ROUND_BITS);
+  auto flush_round = [&]() {
+    if (!cur.pend.empty()) {
+      pad_round_bits(tm, &cur.rset);
+      out.push_back(cur);
+    }
+    cur = RoundPlan();
+  };
+  for (const Item *it : items) {
+    if (needs_target(it->kind)) {
+      int lp = tm.lpos[it->g.target];
+      if (std::find(cur.rset.begin(), cur.rset.end(), lp) == cur.rset.end()) {
+        if (int(cur.rset.size()) == nr) flush_round();
+        cur.rset.push_back(lp);
+      }
+    }
+    cur.pend.push_back(PendingOp{it, 0});
+    if (it->kind == QB_K_DIAG) cur.pend.push_back(PendingOp{it, 1});
+  }
+  flush_round();
+  return out;
+}
+
+// List scheduling over the commutation DAG of the pass's items.  A round is grown from the ready
+// items: everything ready that fits the round's bits is absorbed (diagonal items always fit); a new
+// round bit is taken from the ready item whose bit strands the least work -- items on that bit that
+// could not finish inside this round and would force the bit into a later round again -- with
+// uncontrolled U's preferred (they are what the predicate-free UX round program runs) and program order as the
+// tie break, so a stream without freedom (the QFT) comes out exactly as written.
+std::vector<RoundPlan> schedule_rounds(const TileMap &tm, const std::vector<const Item *> &items) {
+  const int n = int(items.size());
+  const int nr = std::min(tm.K, QB_ROUND_BITS);
+  std::vector<std::vector<int>> preds;
+  preds.resize(size_t(n));
+  for (int j = 0; j < n; ++j)
+    for (int i = 0; i < j; ++i)
+      if (!items_commute(*items[size_t(i)], *items[size_t(j)])) preds[size_t(j)].push_back(i);
+  std::vector<char> done(static_cast<size_t>(n), 0);
+  std::vector<int> lp_of(static_cast<size_t>(n), -1);
+  for (int j = 0; j < n; ++j)
+    if (needs_target(items[size_t(j)]->kind)) lp_of[size_t(j)] = tm.lpos[items[size_t(j)]->g.target];
+  int left = n;
+  std::vector<RoundPlan> out;
+  while (left > 0) {
+    std::vector<int> rset, picked;
+    std::vector<char> in_round(static_cast<size_t>(n), 0);
+    auto in_rset = [&](const std::vector<int> &rs, int lp) { return std::find(rs.begin(), rs.end(), lp) != rs.end(); };
+    auto ready = [&](int j) {
+      for (int i : preds[size_t(j)])
+        if (!done[size_t(i)]) return false;
+      return true;
+    };
+    auto take = [&](int j) {
+      done[size_t(j)] = 1;
+      in_round[size_t(j)] = 1;
+      picked.push_back(j);
+      --left;
+    };
+    for (;;) {
+      // absorb everything ready that fits, in program order, until nothing moves
+      for (bool moved = true; moved;) {
+        moved = false;
+        for (int j = 0; j < n; ++j) {
+          if (done[size_t(j)] || !ready(j)) continue;
+          if (lp_of[size_t(j)] >= 0 && !in_rset(rset, lp_of[size_t(j)])) continue;
+          take(j);
+          moved = true;
+        }
+      }
+      if (int(rset.size()) == nr) break;
+      // candidates for a new round bit
+      int best = -1, best_stranded = 0, best_cls = 0;
+      for (int j = 0; j < n; ++j) {
+        if (done[size_t(j)] || lp_of[size_t(j)] < 0 || !ready(j)) continue;
+        const int lp = lp_of[size_t(j)];
+        std::vector<int> rs = rset;
+        rs.push_back(lp);
+        // which undone items could finish in a round with bits rs (program order == topological)
+        std::vector<char> can(static_cast<size_t>(n), 0);
+        int stranded = 0;
+        for (int k = 0; k < n; ++k) {
+          if (done[size_t(k)]) continue;
+          bool ok = lp_of[size_t(k)] < 0 || in_rset(rs, lp_of[size_t(k)]);
+          for (int i : preds[size_t(k)])
+            if (!done[size_t(i)] && !can[size_t(i)]) ok = false;
+          can[size_t(k)] = ok;
+          if (!ok && lp_of[size_t(k)] == lp) ++stranded;
+        }
+        const Item &it = *items[size_t(j)];
+        const int cls = (it.kind == QB_K_U && it.g.ctl_mask == 0) ? 0 : 1;
+        if (best < 0 || stranded < best_stranded || (stranded == best_stranded && cls < best_cls)) {
+          best = j;
+          best_stranded = stranded;
+          best_cls = cls;
+        }
+      }
+      if (best < 0) break;
+      rset.push_back(lp_of[size_t(best)]);
+      take(best);
+    }
+    if (picked.empty()) break;  // cannot happen: the first undone item is always ready
+    // Uncontrolled U's with no predecessor inside the round commute with everything scheduled
+    // before them here: move them to the front, ascending by bit.  Rounds holding
+    // ladders keep their order (a U must stay next to its ladder to fuse into one ULADDER op).
+    bool has_ladder = false;
+    for (int j : picked)
+      if (items[size_t(j)]->kind == QB_K_LADDER) has_ladder = true;
+    std::vector<int> order;
+    if (!has_ladder) {
+      std::vector<int> front;
+      for (int j : picked) {
+        const Item &it = *items[size_t(j)];
+        bool free_u = it.kind == QB_K_U && it.g.ctl_mask == 0;
+        for (int i : preds[size_t(j)])
+          if (in_round[size_t(i)]) free_u = false;
+        if (free_u) front.push_back(j);
+      }
+      std::sort(front.begin(), front.end(), [&](int a, int b) { return lp_of[size_t(a)] < lp_of[size_t(b)]; });
+      order = front;
+      for (int j : picked)
+        if (std::find(front.begin(), front.end(), j) == front.end()) order.push_back(j);
+    } else {
+      order = picked;
+    }
+    RoundPlan rp;
+    rp.rset = rset;
+    for (int j : order) {
+      rp.pend.push_back(PendingOp{items[size_t(j)], 0});
+      if (items[size_t(j)]->kind == QB_K_DIAG) rp.pend.push_back(PendingOp{items[size_t(j)], 1});
+    }
+    pad_round_bits(tm, &rp.rset);
+    out.push_back(std::move(rp));
+  }
+  return out;
+}
+
 void close_round(const TileMap &tm, RoundPlan &rp, int *nladders, PlannedPass *pp) {
   std::vector<int> &rset = rp.rset;
   std::vector<PendingOp> &pend = rp.pend;
@@ -497,14 +669,77 @@ void close_round(const TileMap &tm, RoundPlan &rp, int *nladders, PlannedPass *p
       }
     }
   }
+  // x / cx gates onto one target: each is merged into an earlier PARSWAP of this round on the same
+  // target when it commutes with everything in between (larose_benchmark.py:52-53 -- after
+  // scheduling, all cx(bit, 0) of a pass sit next to each other).
+  struct Par {
+    bool leader = false;
+    uint64_t mask = 0;
+    int flip = 0;
+  };
+  std::vector<Par> par(pend.size());
+  {
+    std::vector<size_t> emitted;
+    for (size_t pi = 0; pi < pend.size(); ++pi) {
+      if (skip[pi]) continue;
+      const Item &it = *pend[pi].it;
+      if (is_parity_x(it)) {
+        bool merged = false;
+        for (size_t k = emitted.size(); k-- > 0;) {
+          const size_t e = emitted[k];
+          const Item &ei = *pend[e].it;
+          if (par[e].leader && ei.g.target == it.g.target) {
+            par[e].mask ^= it.g.ctl_mask;
+            par[e].flip ^= it.g.ctl_mask ? 0 : 1;
+            skip[pi] = 1;
+            merged = true;
+            break;
+          }
+          if (par[e].leader) {
+            // against the merged op, not just its first gate: X_te^(parity of mask)
+            if ((par[e].mask >> it.g.target & 1) || (it.g.ctl_mask >> ei.g.target & 1)) break;
+          } else if (!items_commute(ei, it)) {
+            break;
+          }
+        }
+        if (merged) continue;
+        par[pi].leader = true;
+        par[pi].mask = it.g.ctl_mask;
+        par[pi].flip = it.g.ctl_mask ? 0 : 1;
+      }
+      emitted.push_back(pi);
+    }
+  }
   for (size_t pi = 0; pi < pend.size(); ++pi) {
     if (skip[pi]) continue;
+    if (par[pi].leader && par[pi].mask == 0 && par[pi].flip == 0) continue;  // the x's cancelled
     const PendingOp &po = pend[pi];
     const Item &it = *po.it;
     QbOp op{};
     op.kind = it.kind;
     op.tpos = 0;
-    if (lad_of[pi] || (it.kind == QB_K_U && it.g.ctl_mask == 0 && pi + 1 < pend.size() &&
+    if (par[pi].leader) {
+      op.kind = QB_K_PARSWAP;
+      int lp = tm.lpos[it.g.target];
+      for (int k = 0; k < nr; ++k)
+        if (r.rbit[k] == lp) op.tpos = k;
+      for (int b = 0; b < 64; ++b) {
+        if (!(par[pi].mask >> b & 1)) continue;
+        int blp = tm.lpos[b];
+        if (blp < 0) {
+          op.gmask |= uint64_t(1) << b;
+          continue;
+        }
+        int rp = -1;
+        for (int k = 0; k < nr; ++k)
+          if (r.rbit[k] == blp) rp = k;
+        if (rp >= 0) op.rmask |= 1u << rp;
+        else op.lmask |= 1u << blp;
+      }
+      op.rwant = uint32_t(par[pi].flip);
+      for (int e = 0; e < 8; ++e)
+        if (__builtin_popcount(uint32_t(e) & op.rmask) & 1) op.lwant |= 1u << e;
+    } else if (lad_of[pi] || (it.kind == QB_K_U && it.g.ctl_mask == 0 && pi + 1 < pend.size() &&
                        pend[pi + 1].it->kind == QB_K_LADDER && pend[pi + 1].it->pivot == it.g.target)) {
       // h(q) + the cu1 ladder hanging off q (circuit.py:323-326): one op, y' = (c x + d y) * phase
       const Item &lad = lad_of[pi] ? *lad_of[pi] : *pend[pi + 1].it;
@@ -557,6 +792,7 @@ void close_round(const TileMap &tm, RoundPlan &rp, int *nladders, PlannedPass *p
         break;
       case QB_K_PERM: opc = QB_OPC_PERM + op.tpos; break;
       case QB_K_SWAP: opc = QB_OPC_SWAP + op.tpos; break;
+      case QB_K_PARSWAP: opc = QB_OPC_PARSWAP + op.tpos; break;
       case QB_K_PHASE: opc = QB_OPC_PHASE; break;
       default: opc = QB_OPC_LADDER; break;
     }
@@ -580,6 +816,18 @@ void close_round(const TileMap &tm, RoundPlan &rp, int *nladders, PlannedPass *p
                          isone(o2.F, 6) && isone(o2.F, 7);
       r.prog = upper ? QB_PROG_HL3U : QB_PROG_HL3;
     }
+  }
+  // Round program UX: nothing but uncontrolled U's and parity swaps (every round of larose_benchmark).
+  if (r.prog == QB_PROG_GENERIC && nr == QB_ROUND_BITS && r.op_end > r.op_begin) {
+    bool ux = true;
+    for (int k = r.op_begin; k < r.op_end; ++k) {
+      const QbOp &o = pp->ops[size_t(k)];
+      const int opc = int(uint32_t(o.kind) >> 24);
+      const bool u_all = opc >= QB_OPC_U_ALL && opc < QB_OPC_U_ALL + 6 && o.gmask == 0;
+      const bool psw = opc >= QB_OPC_PARSWAP && opc < QB_OPC_PARSWAP + 3;
+      if (!u_all && !psw) ux = false;
+    }
+    if (ux) r.prog = QB_PROG_UX;
   }
   pp->rounds.push_back(r);
 }
@@ -615,32 +863,19 @@ void emit_pass(int nbits, int K, const std::vector<const Item *> &items, const s
   pp.desc.K = tm.K;
   pp.desc.tile_mask = tm.mask;
   for (int k = 0; k < tm.K; ++k) pp.desc.tile_bits[k] = tm.bits[k];
-  std::vector<RoundPlan> rplans;
-  RoundPlan cur;
   int nlad = 0;
-  const int nr = std::min(tm.K, QB_ROUND_BITS);
-  auto flush_round = [&]() {
-    if (!cur.pend.empty()) {
-      pad_round_bits(tm, &cur.rset);
-      rplans.push_back(cur);
-    }
-    cur = RoundPlan();
-  };
+  std::vector<const Item *> live;
   for (const Item *it : items) {
     pp.ngates += it->ngates;
     pp.bytes_algorithmic_per_amp += it->bytes_per_amp;
-    if (it->kind == QB_K_NOP) continue;
-    if (needs_target(it->kind)) {
-      int lp = tm.lpos[it->g.target];
-      if (std::find(cur.rset.begin(), cur.rset.end(), lp) == cur.rset.end()) {
-        if (int(cur.rset.size()) == nr) flush_round();
-        cur.rset.push_back(lp);
-      }
-    }
-    cur.pend.push_back(PendingOp{it, 0});
-    if (it->kind == QB_K_DIAG) cur.pend.push_back(PendingOp{it, 1});
+    if (it->kind != QB_K_NOP) live.push_back(it);
   }
-  flush_round();
+  std::vector<RoundPlan> rplans = inorder_rounds(tm, live);
+  static const bool no_sched = getenv("QCC_B200_NO_SCHED") != nullptr;
+  if (!no_sched && tm.K >= QB_ROUND_BITS) {
+    std::vector<RoundPlan> sched = schedule_rounds(tm, live);
+    if (sched.size() <= rplans.size()) rplans.swap(sched);
+  }
   assign_group_maps(tm, &rplans);
   for (RoundPlan &rp : rplans) close_round(tm, rp, &nlad, &pp);
   pp.desc.nrounds = int32_t(pp.rounds.size());

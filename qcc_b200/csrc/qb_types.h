@@ -21,6 +21,8 @@ enum QbKind : int32_t {
   QB_K_NOP = 5,
   QB_K_SWAP = 6,    // PERM with b = c = 1: moves amplitudes, no arithmetic
   QB_K_ULADDER = 7, // uncontrolled U on the pivot immediately followed by that pivot's LADDER
+  QB_K_PARSWAP = 8, // product of x / cx gates sharing one target: swap the pair where the PARITY of the
+                    // control bits (xor a constant) is odd -- cx(a,t) cx(b,t) ... = X_t^(a xor b xor ...)
 };
 
 // A gate in physical index-bit terms, as queued by the engine.
@@ -72,21 +74,24 @@ struct QbGate {
 #define QB_OPC_SWAP 21       // +tpos
 #define QB_OPC_PHASE 24
 #define QB_OPC_LADDER 25
+#define QB_OPC_PARSWAP 26    // +tpos
 
 // Round programs (QbRound::prog).  The op list stays the definition of what a round computes;
 // prog only names a fully unrolled code path in fused.cu for op lists of a known shape.
 #define QB_PROG_GENERIC 0    // interpret the op list
 #define QB_PROG_HL3 1        // exactly three Hadamard+ladder ops on round positions 0, 1, 2 in that order
 #define QB_PROG_HL3U 2       // HL3 whose in-round ladder partners are all above their pivot (the QFT shape)
+#define QB_PROG_UX 3         // every op is an uncontrolled U (any round position, complex or real) or a PARSWAP:
+                             // a lean interpreter without predicates (9 opcodes), no registers spent on masks
 
 struct alignas(16) QbOp {   // 256 bytes; lives in the kernel parameters (constant bank)
   int32_t kind;      // QbKind (never DIAG/NOP: the planner lowers those) | tpos << 8 | mflags << 16 | opcode << 24
   int32_t tpos;      // U/PERM/SWAP: target position inside rbit[]
-  uint32_t lmask, lwant;
-  uint32_t rmask, rwant;
+  uint32_t lmask, lwant;   // PARSWAP: lmask = tile-local control bits (parity), lwant = 8-bit table, bit e = parity(e & rmask)
+  uint32_t rmask, rwant;   // PARSWAP: rmask = round-position control bits (parity), rwant = constant flip (0 / 1)
   int32_t table_off; // LADDER: first double2 of this op's tables in the pass table buffer
   int32_t flags;     // LADDER: slot (0..63) of its per-tile constant in shared memory
-  uint64_t gmask, gwant;
+  uint64_t gmask, gwant;   // PARSWAP: gmask = control bits outside the tile (parity), gwant unused
   double m[8];       // U/PERM: a b c d; PHASE: p in m[0..1]
   int32_t nout;      // LADDER: number of partner bits outside the tile
   int32_t out_off;   // LADDER: first entry in the pass's outside-bit array

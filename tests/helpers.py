@@ -16,7 +16,7 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 from oracle import oracle  # noqa: E402
 
-K_U, K_PHASE, K_DIAG, K_PERM, K_LADDER, K_NOP, K_SWAP, K_ULADDER = range(8)
+K_U, K_PHASE, K_DIAG, K_PERM, K_LADDER, K_NOP, K_SWAP, K_ULADDER, K_PARSWAP = range(9)
 
 
 def load_golden(name):
@@ -142,7 +142,36 @@ def interpret_plan(plan_json: str, n: int, gates, psi: np.ndarray) -> np.ndarray
       else:
         assert ri + 1 == len(p["rounds"]) or not R.get("nobar")
       A = T[:, je]                              # [tile, group, e]
-      for op in p["ops"][R["op_begin"]:R["op_end"]]:
+      rops = p["ops"][R["op_begin"]:R["op_end"]]
+      if R.get("prog") == 3:
+        # UX program: uncontrolled U's and parity swaps only (the kernel's predicate-free interpreter)
+        for o in rops:
+          k8 = o["kind"] & 0xFF
+          assert k8 in (K_U, K_PARSWAP) and len(rops) >= 1
+          if k8 == K_U:
+            assert o["lmask"] == 0 and o["rmask"] == 0 and o["gmask"] == 0
+            real = all(o["m"][2 * i + 1] == 0.0 for i in range(4))
+            assert (o["kind"] >> 24) == 9 + o["tpos"] + (3 if real else 0)
+      for op in rops:
+        if op["kind"] & 0xFF == K_PARSWAP:
+          # swap the pair on tpos where parity(control bits) ^ flip is odd
+          tp = op["tpos"]
+          assert not (op["rmask"] >> tp) & 1 and (op["kind"] >> 24) == 26 + tp
+          par_t = np.array([bin(int(b) & op["gmask"]).count("1") & 1 for b in base])
+          par_g = np.array([bin(int(x) & op["lmask"]).count("1") & 1 for x in jb])
+          par = par_t[:, None] ^ par_g[None, :] ^ (op["rwant"] & 1)
+          for e in range(8):
+            if e & (1 << tp):
+              continue
+            pe = bin(e & op["rmask"]).count("1") & 1
+            assert (op["lwant"] >> e) & 1 == pe
+            sw = (par ^ pe) == 1
+            e1 = e | (1 << tp)
+            x = A[:, :, e].copy()
+            y = A[:, :, e1].copy()
+            A[:, :, e] = np.where(sw, y, x)
+            A[:, :, e1] = np.where(sw, x, y)
+          continue
         tile_ok = (base & op["gmask"]) == op["gwant"]
         grp_ok = (jb & op["lmask"]) == op["lwant"]
         ok = tile_ok[:, None] & grp_ok[None, :]                        # [tile, group]
@@ -218,4 +247,5 @@ def plan_summary(plan_json: str):
       "rounds": sum(len(p["rounds"]) for p in fused),
       "ops": sum(len(p["ops"]) for p in fused),
       "ladders": sum(1 for p in fused for o in p["ops"] if o["kind"] & 0xFF in (K_LADDER, K_ULADDER)),
+      "progs": [R["prog"] for p in fused for R in p["rounds"]],
   }

@@ -102,6 +102,52 @@ def test_random_circuit_multi_tile(n, tile_bits):
   assert cnt_f["passes"] < cnt_s["passes"] / 3
 
 
+@pytest.mark.parametrize("n,tile_bits,depth", [(12, 12, 3), (15, 12, 3), (18, 12, 2), (16, 13, 2), (14, 8, 2), (20, 11, 2)])
+def test_larose_ux_rounds(n, tile_bits, depth):
+  """larose_benchmark.py:47-54 at several sizes: every round is the UX program (uncontrolled
+  butterflies + one parity swap for the cx fan-in), FULL and non-FULL tiles, several tiles per pass."""
+  stream = []
+  for _ in range(depth):
+    for bit in range(n):
+      stream.append((1, 0, bit, oracle.GATES["h"]))
+      stream.append((1, 0, bit, oracle.GATES["v"]))
+      if bit > 0:
+        stream.append((2, bit, 0, oracle.GATES["x"]))
+  psi0 = random_state(n, n + 1)
+  want = oracle.c_run(psi0.copy(), n, stream)
+  got, cnt = run_device(n, psi0, stream, True, tile_bits)
+  assert np.abs(got - want).max() <= TOL
+  assert cnt["passes"] * 8 < len(stream)
+
+
+@pytest.mark.parametrize("n,tile_bits,seed", [(6, 5, 11), (10, 7, 12), (13, 12, 13), (14, 11, 14), (17, 12, 15), (19, 13, 16)])
+def test_cx_fan_in_and_scheduling(n, tile_bits, seed):
+  """x / cx chains onto shared targets between 1-qubit gates and controlled phases: PARSWAP ops with
+  control bits in the round, in the tile and outside the tile, in UX rounds and in generic rounds."""
+  rng = np.random.default_rng(seed)
+  names = ["h", "v", "yroot", "t", "x", "z", "s"]
+  stream = []
+  for _ in range(260):
+    r = rng.random()
+    t = int(rng.integers(n))
+    if r < 0.45:
+      tgt = int(rng.integers(2))
+      c = int(rng.integers(n))
+      if c == tgt or rng.random() < 0.1:
+        stream.append((1, 0, tgt, oracle.GATES["x"]))
+      else:
+        stream.append((2, c, tgt, oracle.GATES["x"]))
+    elif r < 0.55:
+      c = int((t + 1 + rng.integers(n - 1)) % n)
+      stream.append((2, c, t, oracle.u1(float(rng.uniform(-3, 3)))))
+    else:
+      stream.append((1, 0, t, oracle.GATES[names[rng.integers(len(names))]]))
+  psi0 = random_state(n, seed)
+  want = oracle.c_run(psi0.copy(), n, stream)
+  got, _ = run_device(n, psi0, stream, True, tile_bits)
+  assert np.abs(got - want).max() <= TOL
+
+
 @pytest.mark.parametrize("n", [10, 16, 21])
 def test_qft_matches_oracle(n):
   stream = []

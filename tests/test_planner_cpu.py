@@ -140,6 +140,66 @@ def test_larose_plan_is_much_shorter_than_the_gate_list():
   assert s["passes"] <= 10 and s["passes"] * 10 < len(gates)
 
 
+def _larose_bits(n, depth):
+  gates = []
+  for _ in range(depth):
+    for bit in range(n):
+      b = n - 1 - bit
+      gates.append((0, b, oracle.GATES["h"]))
+      gates.append((0, b, oracle.GATES["v"]))
+      if bit > 0:
+        gates.append((1 << b, n - 1, oracle.GATES["x"]))
+  return gates
+
+
+def test_larose_rounds_are_scheduled_into_ux_programs():
+  """configs[1]: the scheduler collects the h.v butterflies three to a round and turns the cx fan-in
+  onto qubit 0 (larose_benchmark.py:52-53) into one parity swap per pass, so every round runs the
+  predicate-free UX program: 10 rounds per depth instead of the 14 of the in-order cut."""
+  from helpers import K_PARSWAP
+  n = 28
+  plan = json.loads(_cabi.plan_json(n, _larose_bits(n, 2), 12))
+  fused = [p for p in plan["passes"] if p["single_gate"] < 0]
+  assert len(fused) == 6 and len(plan["passes"]) == 6
+  assert sum(len(p["rounds"]) for p in fused) <= 20
+  assert all(R["prog"] == 3 for p in fused for R in p["rounds"])
+  for p in fused:
+    assert sum(1 for o in p["ops"] if o["kind"] & 0xFF == K_PARSWAP) == 1
+
+
+@pytest.mark.parametrize("n,tile_bits,seed", [(6, 5, 11), (10, 7, 12), (13, 12, 13), (14, 11, 14)])
+def test_plan_cx_fan_in_and_scheduling(n, tile_bits, seed):
+  """x / cx chains onto shared targets mixed with 1-qubit gates and controlled phases: exercises the
+  commutation DAG, PARSWAP merging (including x's that cancel) and the UX round program."""
+  from helpers import K_PARSWAP
+  rng = np.random.default_rng(seed)
+  names = ["h", "v", "yroot", "t", "x", "z", "s"]
+  gates = []
+  for _ in range(220):
+    r = rng.random()
+    t = int(rng.integers(n))
+    if r < 0.45:
+      hot = int(rng.integers(2))                      # two popular targets
+      tgt = n - 1 - hot
+      c = int(rng.integers(n))
+      if c == tgt or rng.random() < 0.1:
+        gates.append((0, tgt, oracle.GATES["x"]))
+      else:
+        gates.append((1 << c, tgt, oracle.GATES["x"]))
+    elif r < 0.55:
+      c = int((t + 1 + rng.integers(n - 1)) % n)
+      gates.append((1 << c, t, oracle.u1(float(rng.uniform(-3, 3)))))
+    else:
+      gates.append((0, t, oracle.GATES[names[rng.integers(len(names))]]))
+  psi0 = random_state(n, seed)
+  want = run_bits(psi0.copy(), n, gates)
+  pj = _cabi.plan_json(n, gates, tile_bits)
+  got = interpret_plan(pj, n, gates, psi0.copy())
+  assert np.abs(got - want).max() <= 1e-12
+  plan = json.loads(pj)
+  assert any(o["kind"] & 0xFF == K_PARSWAP for p in plan["passes"] if p["single_gate"] < 0 for o in p["ops"])
+
+
 def test_round_bank_classes():
   """QbRound::qmap gives group-index bits 0..2 one tile-local bit of each class (b % 3),
   which is what makes the swizzled shared-memory accesses of fused.cu conflict free."""
