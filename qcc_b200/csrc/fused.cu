@@ -60,6 +60,9 @@ struct RoundAux {
   uint32_t pbi[(1 << (QB_MAX_TILE_BITS - 3)) / kFThreads];  // byte slot of group 256 * git
   uint32_t jbi[(1 << (QB_MAX_TILE_BITS - 3)) / kFThreads];  // tile-local base index of group 256 * git
   uint32_t ta[3];    // HL3: byte offset of the three ladders' tables
+  uint32_t ux;       // UX: leading uncontrolled U's on ascending round positions, run as straight-line code:
+                     //     bits 0..1 = their number, bits 4+2k..5+2k = class at position k (0 none, 1 complex, 2 real,
+                     //     3 column-imaginary)
   double s;          // HL3: product of the three Hadamard scales
 };
 
@@ -101,6 +104,20 @@ __device__ __forceinline__ double2 mad2(double2 m0, double2 x, double2 m1, doubl
   return make_double2(p.x + q.x, p.y + q.y);
 }
 
+// m0 * x + m1 * y as one multiply and three fused multiply-adds per component (8 fp64 instructions
+// per output instead of 10): the form the uncontrolled butterflies use.
+__device__ __forceinline__ double2 mad2f(double2 m0, double2 x, double2 m1, double2 y) {
+  double re = m0.x * x.x;
+  re = fma(-m0.y, x.y, re);
+  re = fma(m1.x, y.x, re);
+  re = fma(-m1.y, y.y, re);
+  double im = m0.x * x.y;
+  im = fma(m0.y, x.x, im);
+  im = fma(m1.x, y.y, im);
+  im = fma(m1.y, y.x, im);
+  return make_double2(re, im);
+}
+
 // real m0, m1
 __device__ __forceinline__ double2 mad2r(double m0, double2 x, double m1, double2 y) {
   return make_double2(m0 * x.x + m1 * y.x, m0 * x.y + m1 * y.y);
@@ -131,9 +148,21 @@ __device__ __forceinline__ void bfly_all(double2 (&a)[8], const Mat &m) {
       a[e] = mad2r(m.a.x, x, m.b.x, y);
       a[e | (1 << TP)] = mad2r(m.c.x, x, m.d.x, y);
     } else {
-      a[e] = mad2(m.a, x, m.b, y);
-      a[e | (1 << TP)] = mad2(m.c, x, m.d, y);
+      a[e] = mad2f(m.a, x, m.b, y);
+      a[e | (1 << TP)] = mad2f(m.c, x, m.d, y);
     }
+  }
+}
+
+// first column real (a, c), second column imaginary (i b, i d):  x' = a x + i b y,  y' = c x + i d y
+template <int TP>
+__device__ __forceinline__ void bfly_colimag(double2 (&a)[8], double ma, double mb, double mc, double md) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    if (e & (1 << TP)) continue;
+    const double2 x = a[e], y = a[e | (1 << TP)];
+    a[e] = make_double2(fma(-mb, y.y, ma * x.x), fma(mb, y.x, ma * x.y));
+    a[e | (1 << TP)] = make_double2(fma(-md, y.y, mc * x.x), fma(md, y.x, mc * x.y));
   }
 }
 
@@ -345,9 +374,26 @@ __device__ __forceinline__ void round_hl3(const uint32_t tile_sa, const uint32_t
 
 // ---- round program UX: uncontrolled butterflies and parity swaps only ------------------------
 // Every round of larose_benchmark.py:47-54 after scheduling (h.v on three qubits; the cx fan-in onto
-// qubit 0 as ONE parity swap), and the single-qubit layers of supremacy-style circuits.  No
-// predicates to evaluate, 9 opcodes, matrices straight from the constant bank: the interpretive
-// overhead per op is a uniform load and one indexed branch against 32-64 fp64 instructions of work.
+// qubit 0 as ONE parity swap), and the single-qubit layers of supremacy-style circuits.  The leading
+// U's (one per round position, ascending -- the planner's order) are straight-line code selected by
+// uniform branches: no loop-carried register assignment, so no register moves and no decode.  What
+// follows them (the parity swap, a second U on a position) goes through a lean interpreter without
+// predicates, matrices straight from the constant bank through uniform registers.
+template <int TP>
+__device__ __forceinline__ void ux_stage(double2 (&a)[8], const QbOp *__restrict__ op, const uint32_t cls) {
+  const double2 *mp = reinterpret_cast<const double2 *>(op->m);
+  if (cls == 1) {
+    const Mat m{mp[0], mp[1], mp[2], mp[3]};
+    bfly_all<TP, false>(a, m);
+  } else if (cls == 2) {
+    Mat m;
+    m.a.x = mp[0].x; m.b.x = mp[1].x; m.c.x = mp[2].x; m.d.x = mp[3].x;
+    bfly_all<TP, true>(a, m);
+  } else {
+    bfly_colimag<TP>(a, mp[0].x, mp[1].y, mp[2].x, mp[3].y);
+  }
+}
+
 template <bool FULL>
 __device__ __forceinline__ void round_ux(const uint32_t tile_sa, const uint32_t *__restrict__ jbt,
                                          const QbOp *__restrict__ o, const int nops,
@@ -355,6 +401,10 @@ __device__ __forceinline__ void round_ux(const uint32_t tile_sa, const uint32_t 
                                          const uint32_t ngroups, const uint32_t tid, const uint64_t base) {
   const uint32_t giters = FULL ? (ngroups / kFThreads) : ((ngroups + kFThreads - 1) / kFThreads);
   const uint32_t b0 = X->b[0], b1 = X->b[1], b2 = X->b[2];
+  const uint32_t ux = X->ux;
+  const int nu = int(ux & 3u);
+  const uint32_t c0 = (ux >> 4) & 3u, c1 = (ux >> 6) & 3u, c2 = (ux >> 8) & 3u;
+  const QbOp *o0 = o, *o1 = o + (c0 ? 1 : 0), *o2 = o1 + (c1 ? 1 : 0);
   uint32_t jb_t = 0;
   if (FULL) {
 #pragma unroll
@@ -378,31 +428,31 @@ __device__ __forceinline__ void round_ux(const uint32_t tile_sa, const uint32_t 
 #pragma unroll
     for (int e = 0; e < 8; ++e)
       a[e] = lds128(tile_sa + (pb ^ ((e & 1) ? b0 : 0u) ^ ((e & 2) ? b1 : 0u) ^ ((e & 4) ? b2 : 0u)));
+    if (c0) ux_stage<0>(a, o0, c0);
+    if (c1) ux_stage<1>(a, o1, c1);
+    if (c2) ux_stage<2>(a, o2, c2);
 #pragma unroll 1
-    for (int oi = 0; oi < nops; ++oi) {
+    for (int oi = nu; oi < nops; ++oi) {
       const QbOp *op = o + oi;
-      const double2 *mp = reinterpret_cast<const double2 *>(op->m);
       const int opc = int(uint32_t(op->kind) >> 24);
-      switch (opc) {
-        case QB_OPC_U_ALL + 0: { const Mat m{mp[0], mp[1], mp[2], mp[3]}; bfly_all<0, false>(a, m); break; }
-        case QB_OPC_U_ALL + 1: { const Mat m{mp[0], mp[1], mp[2], mp[3]}; bfly_all<1, false>(a, m); break; }
-        case QB_OPC_U_ALL + 2: { const Mat m{mp[0], mp[1], mp[2], mp[3]}; bfly_all<2, false>(a, m); break; }
-        case QB_OPC_U_ALL + 3: case QB_OPC_U_ALL + 4: case QB_OPC_U_ALL + 5: {
-          Mat m;
-          m.a.x = mp[0].x; m.b.x = mp[1].x; m.c.x = mp[2].x; m.d.x = mp[3].x;
-          if (opc == QB_OPC_U_ALL + 3) bfly_all<0, true>(a, m);
-          else if (opc == QB_OPC_U_ALL + 4) bfly_all<1, true>(a, m);
-          else bfly_all<2, true>(a, m);
-          break;
-        }
-        default: {  // QB_OPC_PARSWAP + tpos
-          const uint32_t odd = (uint32_t(__popcll(base & op->gmask)) + uint32_t(__popc(jb & op->lmask)) + op->rwant) & 1u;
-          const uint32_t sel = op->lwant ^ (0u - odd);
-          if (opc == QB_OPC_PARSWAP + 0) parswap<0>(a, sel);
-          else if (opc == QB_OPC_PARSWAP + 1) parswap<1>(a, sel);
-          else parswap<2>(a, sel);
-          break;
-        }
+      if (opc >= QB_OPC_U_CI) {
+        const uint32_t tp = uint32_t(opc - QB_OPC_U_CI);
+        if (tp == 0) ux_stage<0>(a, op, 3);
+        else if (tp == 1) ux_stage<1>(a, op, 3);
+        else ux_stage<2>(a, op, 3);
+      } else if (opc >= QB_OPC_PARSWAP) {
+        const uint32_t odd = (uint32_t(__popcll(base & op->gmask)) + uint32_t(__popc(jb & op->lmask)) + op->rwant) & 1u;
+        const uint32_t sel = op->lwant ^ (0u - odd);
+        if (opc == QB_OPC_PARSWAP + 0) parswap<0>(a, sel);
+        else if (opc == QB_OPC_PARSWAP + 1) parswap<1>(a, sel);
+        else parswap<2>(a, sel);
+      } else {
+        const uint32_t k = uint32_t(opc - QB_OPC_U_ALL);  // 0..2 complex, 3..5 real
+        const uint32_t cls = k < 3 ? 1u : 2u;
+        const uint32_t tp = k < 3 ? k : k - 3;
+        if (tp == 0) ux_stage<0>(a, op, cls);
+        else if (tp == 1) ux_stage<1>(a, op, cls);
+        else ux_stage<2>(a, op, cls);
       }
     }
 #pragma unroll
@@ -629,6 +679,12 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
             }
             continue;
           }
+          if (opc >= QB_OPC_U_CI) {
+            if (opc == QB_OPC_U_CI + 0) bfly_colimag<0>(a, mp[0].x, mp[1].y, mp[2].x, mp[3].y);
+            else if (opc == QB_OPC_U_CI + 1) bfly_colimag<1>(a, mp[0].x, mp[1].y, mp[2].x, mp[3].y);
+            else bfly_colimag<2>(a, mp[0].x, mp[1].y, mp[2].x, mp[3].y);
+            continue;
+          }
           if (opc >= QB_OPC_PARSWAP) {
             const uint32_t odd = (uint32_t(__popcll(base & op->gmask)) + uint32_t(__popc(jb & op->lmask)) + op->rwant) & 1u;
             const uint32_t sel = op->lwant ^ (0u - odd);
@@ -792,6 +848,23 @@ cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cuda
       for (int k = 8; k < K - 3; ++k) jb |= ((git >> (k - 8)) & 1u) << R.qmap[k];
       X.pbi[git] = swz_h(jb) << 4;
       X.jbi[git] = jb;
+    }
+    if (R.prog == QB_PROG_UX) {
+      int prev = -1;
+      uint32_t nu = 0;
+      for (int k = R.op_begin; k < R.op_end && nu < 3; ++k) {
+        const QbOp &o = p.ops[k];
+        const int opc = int(uint32_t(o.kind) >> 24);
+        uint32_t cls = 0;
+        if (opc >= QB_OPC_U_ALL && opc < QB_OPC_U_ALL + 3) cls = 1;
+        else if (opc >= QB_OPC_U_ALL + 3 && opc < QB_OPC_U_ALL + 6) cls = 2;
+        else if (opc >= QB_OPC_U_CI && opc < QB_OPC_U_CI + 3) cls = 3;
+        if (cls == 0 || o.tpos <= prev) break;
+        X.ux |= cls << (4 + 2 * o.tpos);
+        prev = o.tpos;
+        ++nu;
+      }
+      X.ux |= nu;
     }
   }
   auto is_hl = [&](int r) { return p.rounds[r].prog == QB_PROG_HL3 || p.rounds[r].prog == QB_PROG_HL3U; };

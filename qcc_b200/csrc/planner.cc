@@ -779,6 +779,9 @@ void close_round(const TileMap &tm, RoundPlan &rp, int *nladders, PlannedPass *p
       op.mflags |= QB_MF_REAL;
     if ((op.mflags & QB_MF_REAL) && op.m[0] == op.m[2] && op.m[0] == op.m[4] && op.m[0] == -op.m[6])
       op.mflags |= QB_MF_HADAMARD;
+    if (op.kind == QB_K_U && !(op.mflags & QB_MF_REAL) && op.m[1] == 0.0 && op.m[5] == 0.0 && op.m[2] == 0.0 &&
+        op.m[6] == 0.0)
+      op.mflags |= QB_MF_COLIMAG;  // a, c real; b, d imaginary
     // the kernel decodes one word per op: kind | tpos << 8 | mflags << 16 | dense opcode << 24
     int opc = 0;
     const bool real = op.mflags & QB_MF_REAL;
@@ -788,7 +791,8 @@ void close_round(const TileMap &tm, RoundPlan &rp, int *nladders, PlannedPass *p
         opc = QB_OPC_ULADDER + op.tpos + ((op.mflags & QB_MF_HADAMARD) ? 6 : (real ? 3 : 0));
         break;
       case QB_K_U:
-        opc = unmasked ? QB_OPC_U_ALL + op.tpos + (real ? 3 : 0) : QB_OPC_U_MASKED + op.tpos;
+        opc = !unmasked ? QB_OPC_U_MASKED + op.tpos
+                        : ((op.mflags & QB_MF_COLIMAG) ? QB_OPC_U_CI + op.tpos : QB_OPC_U_ALL + op.tpos + (real ? 3 : 0));
         break;
       case QB_K_PERM: opc = QB_OPC_PERM + op.tpos; break;
       case QB_K_SWAP: opc = QB_OPC_SWAP + op.tpos; break;
@@ -823,7 +827,8 @@ void close_round(const TileMap &tm, RoundPlan &rp, int *nladders, PlannedPass *p
     for (int k = r.op_begin; k < r.op_end; ++k) {
       const QbOp &o = pp->ops[size_t(k)];
       const int opc = int(uint32_t(o.kind) >> 24);
-      const bool u_all = opc >= QB_OPC_U_ALL && opc < QB_OPC_U_ALL + 6 && o.gmask == 0;
+      const bool u_all = ((opc >= QB_OPC_U_ALL && opc < QB_OPC_U_ALL + 6) || (opc >= QB_OPC_U_CI && opc < QB_OPC_U_CI + 3)) &&
+                         o.gmask == 0;
       const bool psw = opc >= QB_OPC_PARSWAP && opc < QB_OPC_PARSWAP + 3;
       if (!u_all && !psw) ux = false;
     }

@@ -66,6 +66,7 @@ struct QbGate {
 #define QB_MAX_PASS_LADDERS 12  // their lookup tables (48 x 16 B each at K = 12) are staged in shared memory too
 #define QB_MF_REAL 1         // all four entries of m are real: 8 instead of 20 flops per pair
 #define QB_MF_HADAMARD 2     // m = r * [[1, 1], [1, -1]] with real r
+#define QB_MF_COLIMAG 4      // first column real, second column imaginary (R * diag(1, +-i), e.g. h then v, h then s): 8 flops per pair
 // Dense opcodes (bits 24..31 of QbOp::kind): one jump-table switch in the kernel.
 #define QB_OPC_ULADDER 0     // +tpos complex, +3+tpos real, +6+tpos Hadamard
 #define QB_OPC_U_ALL 9       // uncontrolled U: +tpos complex, +3+tpos real
@@ -75,14 +76,16 @@ struct QbGate {
 #define QB_OPC_PHASE 24
 #define QB_OPC_LADDER 25
 #define QB_OPC_PARSWAP 26    // +tpos
+#define QB_OPC_U_CI 29       // uncontrolled U, QB_MF_COLIMAG matrix: +tpos
 
 // Round programs (QbRound::prog).  The op list stays the definition of what a round computes;
 // prog only names a fully unrolled code path in fused.cu for op lists of a known shape.
 #define QB_PROG_GENERIC 0    // interpret the op list
 #define QB_PROG_HL3 1        // exactly three Hadamard+ladder ops on round positions 0, 1, 2 in that order
 #define QB_PROG_HL3U 2       // HL3 whose in-round ladder partners are all above their pivot (the QFT shape)
-#define QB_PROG_UX 3         // every op is an uncontrolled U (any round position, complex or real) or a PARSWAP:
-                             // a lean interpreter without predicates (9 opcodes), no registers spent on masks
+#define QB_PROG_UX 3         // every op is an uncontrolled U (any round position; complex, real or column-imaginary)
+                             // or a PARSWAP: leading U's on ascending positions run as straight-line code, the rest
+                             // through a lean interpreter without predicates (12 opcodes)
 
 struct alignas(16) QbOp {   // 256 bytes; lives in the kernel parameters (constant bank)
   int32_t kind;      // QbKind (never DIAG/NOP: the planner lowers those) | tpos << 8 | mflags << 16 | opcode << 24

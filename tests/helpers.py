@@ -151,7 +151,8 @@ def interpret_plan(plan_json: str, n: int, gates, psi: np.ndarray) -> np.ndarray
           if k8 == K_U:
             assert o["lmask"] == 0 and o["rmask"] == 0 and o["gmask"] == 0
             real = all(o["m"][2 * i + 1] == 0.0 for i in range(4))
-            assert (o["kind"] >> 24) == 9 + o["tpos"] + (3 if real else 0)
+            colimag = not real and o["m"][1] == 0 and o["m"][5] == 0 and o["m"][2] == 0 and o["m"][6] == 0
+            assert (o["kind"] >> 24) == (29 + o["tpos"] if colimag else 9 + o["tpos"] + (3 if real else 0))
       for op in rops:
         if op["kind"] & 0xFF == K_PARSWAP:
           # swap the pair on tpos where parity(control bits) ^ flip is odd
