@@ -75,10 +75,13 @@ struct FusedParams {
   const int32_t *outbits;
   const uint32_t *jbtab;
   int debug;  // timing experiments only -- 1: skip the op loop, 2: skip the rounds, 4: skip the store, 8: skip the load, 16: no round programs, 32: (unused), 64: CTA barrier after every round
-  // per copy iteration i (thread t moves tile-local index t + 256 i): global offset of index 256 i
-  // in units of 8 amplitudes, and the XOR that takes the byte slot of t to the byte slot of t + 256 i
-  uint32_t io_goff[(1 << QB_MAX_TILE_BITS) / kFThreads];
-  uint32_t io_sxor[(1 << QB_MAX_TILE_BITS) / kFThreads];
+  // per copy iteration i (thread t moves copy index t + 256 i, see QbPassDesc::ld_map / st_map): global
+  // offset of copy index 256 i in units of 8 amplitudes, and the XOR that takes the byte slot of copy
+  // index t to the byte slot of copy index t + 256 i
+  uint32_t ld_goff[(1 << QB_MAX_TILE_BITS) / kFThreads];
+  uint32_t ld_sxor[(1 << QB_MAX_TILE_BITS) / kFThreads];
+  uint32_t st_goff[(1 << QB_MAX_TILE_BITS) / kFThreads];
+  uint32_t st_sxor[(1 << QB_MAX_TILE_BITS) / kFThreads];
   RoundAux aux[QB_MAX_PASS_ROUNDS];
   // Pass descriptors travel as kernel parameters (7 KiB of the 32 KiB parameter space): the
   // per-op decode in the hot loop is then LDC from the constant bank (warp-uniform index), which
@@ -514,11 +517,21 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
   // t, 256 i have no bit in common, so address(j) = address(t) (+ or ^) address(256 i): one
   // per-thread term computed here, one per-iteration term from the kernel parameters -- an add, an
   // XOR and the copy itself per 16 bytes.
-  uint64_t g_tid = tid & 7u;
+  // With warp_io the copy index is not the tile-local index: its warp bits (5..7) select the per-warp
+  // sub-cube of the first (load) / last (store) run of rounds, so a warp moves what it computes on.
+  uint64_t g_ld = tid & 7u, g_st = tid & 7u;
+  uint32_t j_ld = tid & 7u, j_st = tid & 7u;
 #pragma unroll
   for (int k = 3; k < 8; ++k)
-    if (k < K) g_tid |= uint64_t((tid >> k) & 1u) << P.desc.tile_bits[k];
-  const uint32_t s_tid = swz(tid) << 4;
+    if (k < K) {
+      const uint32_t bit = (tid >> k) & 1u;
+      j_ld |= bit << P.desc.ld_map[k];
+      j_st |= bit << P.desc.st_map[k];
+      g_ld |= uint64_t(bit) << P.desc.tile_bits[P.desc.ld_map[k]];
+      g_st |= uint64_t(bit) << P.desc.tile_bits[P.desc.st_map[k]];
+    }
+  const uint32_t s_ld = swz(j_ld) << 4, s_st = swz(j_st) << 4;
+  const bool warp_io = P.desc.warp_io != 0;
   const uint32_t io_iters = tileN > kFThreads ? tileN / kFThreads : 1u;
   const bool io_on = tid < tileN;
   const uint32_t tile_sa = uint32_t(__cvta_generic_to_shared(tile));
@@ -550,15 +563,15 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
   };
   auto issue_load = [&](uint64_t b) {
     if (!(P.debug & 8) && io_on) {
-      const double2 *src = psi + (b | g_tid);
+      const double2 *src = psi + (b | g_ld);
       if (io_iters == 16) {  // K = 12: constant-bank operands with immediate addresses
 #pragma unroll
         for (uint32_t i = 0; i < 16; ++i)
-          cp_async16(tile_sa + (s_tid ^ P.io_sxor[i]), src + (uint64_t(P.io_goff[i]) << 3));
+          cp_async16(tile_sa + (s_ld ^ P.ld_sxor[i]), src + (uint64_t(P.ld_goff[i]) << 3));
       } else {
 #pragma unroll 4
         for (uint32_t i = 0; i < io_iters; ++i)
-          cp_async16(tile_sa + (s_tid ^ P.io_sxor[i]), src + (uint64_t(P.io_goff[i]) << 3));
+          cp_async16(tile_sa + (s_ld ^ P.ld_sxor[i]), src + (uint64_t(P.ld_goff[i]) << 3));
       }
     }
     cp_async_commit();
@@ -608,8 +621,17 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
         }
       }
     }
-    cp_async_wait<0>();
-    __syncthreads();
+    if (warp_io) {
+      // tables, per-tile constants and the active mask are CTA-wide; the tile data is not: every warp
+      // waits for its own copies only (they cover exactly the sub-cube it works on until the first
+      // CTA barrier between rounds)
+      __syncthreads();
+      cp_async_wait<0>();
+      __syncwarp();
+    } else {
+      cp_async_wait<0>();
+      __syncthreads();
+    }
 
     // ---- ROUNDS ------------------------------------------------------------------------
     for (int r = 0; r < ((P.debug & 2) ? 0 : P.desc.nrounds); ++r) {
@@ -628,7 +650,7 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
           if (upper) round_hl3<true, FULL, false>(tile_sa, tab_sa, jbt, s_ops + ob, R, X, ngroups, tid);
           else round_hl3<false, FULL, false>(tile_sa, tab_sa, jbt, s_ops + ob, R, X, ngroups, tid);
         }
-        round_sync(R->nobar && !(P.debug & 64));
+        round_sync((R->nobar || (warp_io && r + 1 == P.desc.nrounds)) && !(P.debug & 64));
         continue;
       }
       if (!FAST) {
@@ -740,21 +762,21 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
         for (int e = 0; e < 8; ++e)
           tile[pb ^ ((e & 1) ? d0 : 0u) ^ ((e & 2) ? d1 : 0u) ^ ((e & 4) ? d2 : 0u)] = a[e];
       }
-      round_sync(R->nobar && !(P.debug & 64));
+      round_sync((R->nobar || (warp_io && r + 1 == P.desc.nrounds)) && !(P.debug & 64));
       }
     }
 
     // ---- STORE ---------------------------------------------------------------------------
     if (!(P.debug & 4) && io_on) {
-      double2 *dst = psi + (base | g_tid);
+      double2 *dst = psi + (base | g_st);
       if (io_iters == 16) {
 #pragma unroll
         for (uint32_t i = 0; i < 16; ++i)
-          __stcs(dst + (uint64_t(P.io_goff[i]) << 3), lds128(tile_sa + (s_tid ^ P.io_sxor[i])));
+          __stcs(dst + (uint64_t(P.st_goff[i]) << 3), lds128(tile_sa + (s_st ^ P.st_sxor[i])));
       } else {
 #pragma unroll 4
         for (uint32_t i = 0; i < io_iters; ++i)
-          __stcs(dst + (uint64_t(P.io_goff[i]) << 3), lds128(tile_sa + (s_tid ^ P.io_sxor[i])));
+          __stcs(dst + (uint64_t(P.st_goff[i]) << 3), lds128(tile_sa + (s_st ^ P.st_sxor[i])));
       }
     }
     if (more) base = tile_base(tn);
@@ -812,23 +834,29 @@ cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cuda
   const size_t smem = fused_smem_bytes(K, p.desc.ntable);
   if (smem > kSmemLimit) return cudaErrorInvalidValue;
   // copy-loop address terms of tile-local index 256 i (see the kernel)
-  for (uint32_t i = 0; i < (1u << K) / kFThreads; ++i) {
-    const uint32_t j = i * kFThreads, h = j >> 3;
-    uint64_t off = 0;
-    for (int k = 3; k < K; ++k) off |= uint64_t((h >> (k - 3)) & 1u) << p.desc.tile_bits[k];
-    uint32_t x = j >> 3;
-    x ^= x >> 3;
-    x ^= x >> 6;
-    P.io_goff[i] = uint32_t(off >> 3);
-    P.io_sxor[i] = (j ^ (x & 7u)) << 4;
-  }
-  if ((1u << K) <= kFThreads) P.io_goff[0] = P.io_sxor[0] = 0;
   auto swz_h = [](uint32_t j) {
     uint32_t x = j >> 3;
     x ^= x >> 3;
     x ^= x >> 6;
     return j ^ (x & 7u);
   };
+  P.ld_goff[0] = P.ld_sxor[0] = P.st_goff[0] = P.st_sxor[0] = 0;
+  for (uint32_t i = 0; i < (1u << K) / kFThreads; ++i) {
+    // copy index 256 i: its bits 8.. drive tile-local positions ld_map[8..] / st_map[8..]
+    uint32_t jl = 0, js = 0;
+    uint64_t gl = 0, gs = 0;
+    for (int k = 8; k < K; ++k) {
+      const uint32_t bit = (i >> (k - 8)) & 1u;
+      jl |= bit << p.desc.ld_map[k];
+      js |= bit << p.desc.st_map[k];
+      gl |= uint64_t(bit) << p.desc.tile_bits[p.desc.ld_map[k]];
+      gs |= uint64_t(bit) << p.desc.tile_bits[p.desc.st_map[k]];
+    }
+    P.ld_goff[i] = uint32_t(gl >> 3);
+    P.ld_sxor[i] = swz_h(jl) << 4;
+    P.st_goff[i] = uint32_t(gs >> 3);
+    P.st_sxor[i] = swz_h(js) << 4;
+  }
   for (int r = 0; r < p.desc.nrounds; ++r) {
     const QbRound &R = p.rounds[r];
     RoundAux &X = P.aux[r];

@@ -407,10 +407,16 @@ std::vector<int> class_first(std::vector<int> cand) {
 // tile bits outside S.  Every warp then reads and writes the same 2^(K-3) amplitudes in every round
 // of the run, so the rounds of a run are separated by a warp-level sync only and the warps of a
 // CTA drift apart instead of meeting at a barrier after every round.
-void assign_group_maps(const TileMap &tm, std::vector<RoundPlan> *rounds) {
+// With >= 512 groups (K >= 12) every S also contains tile bits 0..2, i.e. a warp's sub-cube is made
+// of whole 128-byte runs: the warp itself copies the sub-cube of the first run in from HBM and the
+// sub-cube of the last run out (QbPassDesc::ld_map / st_map, warp_io), waiting only for its own
+// copies -- the load, the rounds and the store of different warps of a CTA overlap.
+void assign_group_maps(const TileMap &tm, std::vector<RoundPlan> *rounds, QbPassDesc *desc) {
   const int K = tm.K;
   const int nr = std::min(K, QB_ROUND_BITS);
   const int gbits = K - nr;
+  desc->warp_io = 0;
+  for (int k = 0; k < QB_MAX_TILE_BITS; ++k) desc->ld_map[k] = desc->st_map[k] = k;
   for (RoundPlan &rp : *rounds) {
     std::vector<int> freeb;
     for (int k = 0; k < K; ++k)
@@ -419,17 +425,26 @@ void assign_group_maps(const TileMap &tm, std::vector<RoundPlan> *rounds) {
     rp.nobar = false;
   }
   if (gbits < 8) return;  // fewer than 256 groups: one barrier per round
+  static const bool no_warp_io = getenv("QCC_B200_NO_WARP_IO") != nullptr;
+  const bool low3 = gbits >= 9 && !no_warp_io && !rounds->empty();
+  std::vector<int> first_S, last_S;
   for (size_t i = 0; i < rounds->size();) {
-    std::vector<int> S = (*rounds)[i].rset;
+    std::vector<int> S;
+    if (low3) S = {0, 1, 2};
+    auto merged = [&](const std::vector<int> &base, const std::vector<int> &add) {
+      std::vector<int> U = base;
+      for (int b : add)
+        if (std::find(U.begin(), U.end(), b) == U.end()) U.push_back(b);
+      return U;
+    };
+    S = merged(S, (*rounds)[i].rset);
     size_t j = i + 1;
     for (; j < rounds->size(); ++j) {
-      std::vector<int> U = S;
-      for (int b : (*rounds)[j].rset)
-        if (std::find(U.begin(), U.end(), b) == U.end()) U.push_back(b);
+      std::vector<int> U = merged(S, (*rounds)[j].rset);
       if (int(U.size()) > gbits) break;
       S = U;
     }
-    if (j - i >= 2) {
+    if (j - i >= 2 || low3) {
       // pad S to gbits bits, preferring the lowest tile bits
       for (int k = 0; k < K && int(S.size()) < gbits; ++k)
         if (std::find(S.begin(), S.end(), k) == S.end()) S.push_back(k);
@@ -451,8 +466,24 @@ void assign_group_maps(const TileMap &tm, std::vector<RoundPlan> *rounds) {
         rp.order = order;
         rp.nobar = r + 1 < j;
       }
+      if (i == 0) first_S = S;
+      if (j == rounds->size()) last_S = S;
     }
     i = j;
+  }
+  if (low3) {
+    // copy index bits: 0..4 (lane) -> S[0..4] (S[0..2] = positions 0..2), 5..7 (warp) -> W, 8.. -> S[5..]
+    auto fill = [&](const std::vector<int> &S, int32_t *map) {
+      std::vector<int> W;
+      for (int k = 0; k < K; ++k)
+        if (std::find(S.begin(), S.end(), k) == S.end()) W.push_back(k);
+      for (int k = 0; k < 5; ++k) map[k] = S[size_t(k)];
+      for (int k = 5; k < 8; ++k) map[k] = W[size_t(k - 5)];
+      for (int k = 8; k < K; ++k) map[k] = S[size_t(k - 3)];
+    };
+    fill(first_S, desc->ld_map);
+    fill(last_S, desc->st_map);
+    desc->warp_io = 1;
   }
 }
 
@@ -881,7 +912,7 @@ void emit_pass(int nbits, int K, const std::vector<const Item *> &items, const s
     std::vector<RoundPlan> sched = schedule_rounds(tm, live);
     if (sched.size() <= rplans.size()) rplans.swap(sched);
   }
-  assign_group_maps(tm, &rplans);
+  assign_group_maps(tm, &rplans, &pp.desc);
   for (RoundPlan &rp : rplans) close_round(tm, rp, &nlad, &pp);
   pp.desc.nrounds = int32_t(pp.rounds.size());
   pp.desc.nops = int32_t(pp.ops.size());
@@ -1042,9 +1073,19 @@ std::string Plan::to_json() const {
       s += "]}";
       continue;
     }
-    snprintf(buf, sizeof buf, "{\"single_gate\":-1,\"ngates\":%lld,\"K\":%d,\"tile_bits\":[", (long long)p.ngates,
-             p.desc.K);
+    snprintf(buf, sizeof buf, "{\"single_gate\":-1,\"ngates\":%lld,\"K\":%d,\"warp_io\":%d,\"ld_map\":[",
+             (long long)p.ngates, p.desc.K, p.desc.warp_io);
     s += buf;
+    for (int k = 0; k < p.desc.K; ++k) {
+      snprintf(buf, sizeof buf, "%s%d", k ? "," : "", p.desc.ld_map[k]);
+      s += buf;
+    }
+    s += "],\"st_map\":[";
+    for (int k = 0; k < p.desc.K; ++k) {
+      snprintf(buf, sizeof buf, "%s%d", k ? "," : "", p.desc.st_map[k]);
+      s += buf;
+    }
+    s += "],\"tile_bits\":[";
     for (int k = 0; k < p.desc.K; ++k) {
       snprintf(buf, sizeof buf, "%s%d", k ? "," : "", p.desc.tile_bits[k]);
       s += buf;

@@ -125,6 +125,15 @@ struct QbPassDesc {
   int32_t pad_;
   int32_t tile_bits[QB_MAX_TILE_BITS + 3];  // index-bit positions, ascending
   uint64_t tile_mask;                  // OR of 1 << tile_bits[k]
+  // Tile <-> HBM copy maps: bit k of the copy index c = tid + 256 * iteration drives tile-local position
+  // ld_map[k] (load) / st_map[k] (store); positions 0..2 always stay with bits 0..2 (8 lanes = one 128-byte run).
+  // warp_io = 1: bits 5..7 of c (the warp number) drive the three positions outside the per-warp sub-cube of the
+  // first (load) / last (store) run of rounds, so a warp copies exactly the amplitudes it computes on and waits
+  // only for its own copies -- no CTA barrier between load and first round or between last round and store.
+  // warp_io = 0: identity maps, CTA barriers.
+  int32_t warp_io;
+  int32_t ld_map[QB_MAX_TILE_BITS];
+  int32_t st_map[QB_MAX_TILE_BITS];
 };
 
 #endif  // QCC_B200_CSRC_QB_TYPES_H_

@@ -141,6 +141,26 @@ def interpret_plan(plan_json: str, n: int, gates, psi: np.ndarray) -> np.ndarray
           assert np.array_equal(np.sort(je[mine].ravel()), np.sort(jen[mine].ravel())), "warp sub-cube changes inside a run"
       else:
         assert ri + 1 == len(p["rounds"]) or not R.get("nobar")
+      # warp-private tile I/O: the amplitudes warp w copies in (ld_map) are exactly the ones it works on
+      # in the first round, the ones it copies out (st_map) exactly those of the last round -- the kernel
+      # has no CTA barrier between the copy and those rounds
+      if p.get("warp_io") and ri in (0, len(p["rounds"]) - 1):
+        assert ng >= 512
+        for name, at in (("ld_map", 0), ("st_map", len(p["rounds"]) - 1)):
+          if ri != at:
+            continue
+          cmap = p[name]
+          assert sorted(cmap) == list(range(K)) and cmap[:3] == [0, 1, 2]
+          c = np.arange(1 << K, dtype=np.int64)
+          jc = np.zeros(1 << K, dtype=np.int64)
+          for k, lp in enumerate(cmap):
+            jc |= ((c >> k) & 1) << lp
+          for w in range(8):
+            mine = ((q >> 5) & 7) == w
+            copied = np.sort(jc[((c >> 5) & 7) == w])
+            assert np.array_equal(copied, np.sort(je[mine].ravel())), f"{name}: warp {w} copies what it does not own"
+      elif not p.get("warp_io"):
+        assert p.get("ld_map", list(range(K))) == list(range(K)) and p.get("st_map", list(range(K))) == list(range(K))
       A = T[:, je]                              # [tile, group, e]
       rops = p["ops"][R["op_begin"]:R["op_end"]]
       if R.get("prog") == 3:

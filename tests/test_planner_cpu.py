@@ -121,8 +121,11 @@ def test_qft30_plans_into_three_passes():
   assert sum(p["ngates"] for p in plan["passes"]) == 465
   assert [len(p["rounds"]) for p in plan["passes"]] == [4, 3, 3]
   assert all(R["prog"] == 2 for p in plan["passes"] for R in p["rounds"])
-  # rounds that share a per-warp sub-cube need no CTA barrier between them: 3 per run at K = 12
-  assert [[R["nobar"] for R in p["rounds"]] for p in plan["passes"]] == [[1, 1, 0, 0], [1, 1, 0], [1, 1, 0]]
+  # rounds that share a per-warp sub-cube need no CTA barrier between them.  Every sub-cube also holds
+  # tile bits 0..2 (whole 128-byte runs, so the warp itself copies it in and out): 9 round bits in the
+  # first pass (whose first round is on bits 0..2), 6 in the others -- one CTA barrier per tile.
+  assert [[R["nobar"] for R in p["rounds"]] for p in plan["passes"]] == [[1, 1, 0, 0], [1, 0, 0], [1, 0, 0]]
+  assert all(p["warp_io"] == 1 for p in plan["passes"])
 
 
 def test_larose_plan_is_much_shorter_than_the_gate_list():
