@@ -45,6 +45,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "kernels.h"
 
 namespace qb {
@@ -270,7 +272,7 @@ __device__ __forceinline__ void hladder(double2 (&a)[8], double r, double2 cf, c
 // phase, the x' path as one multiply).
 // UPPER: the ladder partners inside the round are all above their pivot, so stage 1 has one
 // non-trivial in-round phase and stage 2 none (true for the QFT; otherwise all of F is used).
-template <bool UPPER, bool FULL, bool SCALED>
+template <bool UPPER, bool FULL, bool SCALED, int THREADS = kFThreads>
 __device__ __forceinline__ void round_hl3(const uint32_t tile_sa, const uint32_t tab_sa,
                                           const uint32_t *__restrict__ jbt, const QbOp *__restrict__ o,
                                           const QbRound *__restrict__ R, const RoundAux *__restrict__ X,
@@ -279,7 +281,7 @@ __device__ __forceinline__ void round_hl3(const uint32_t tile_sa, const uint32_t
   const double2 *F0 = reinterpret_cast<const double2 *>(o[0].F);
   const double2 *F1 = reinterpret_cast<const double2 *>(o[1].F);
   const double2 *F2 = reinterpret_cast<const double2 *>(o[2].F);
-  const uint32_t giters = FULL ? (ngroups / kFThreads) : ((ngroups + kFThreads - 1) / kFThreads);
+  const uint32_t giters = FULL ? (ngroups / THREADS) : ((ngroups + THREADS - 1) / THREADS);
   const uint32_t b0 = X->b[0], b1 = X->b[1], b2 = X->b[2];
   // ladder tables: T_a[lane] (fixed per thread), T_b[q >> 5] (uniform per warp)
   const uint32_t lane16 = (tid & 31u) << 4;
@@ -298,10 +300,11 @@ __device__ __forceinline__ void round_hl3(const uint32_t tile_sa, const uint32_t
   const uint32_t pb_t = swz(jb_t) << 4;
 #pragma unroll 1
   for (uint32_t git = 0; git < giters; ++git) {
-    const uint32_t q = git * kFThreads + tid;
+    const uint32_t q = git * THREADS + tid;
+    const uint32_t sub = THREADS == kFThreads ? git : (q >> 8);  // which block of 256 groups (uniform at 256 threads)
     uint32_t pb;  // base slot in bytes
     if (FULL) {
-      pb = pb_t ^ X->pbi[git];
+      pb = pb_t ^ X->pbi[sub];
     } else {
       if (q >= ngroups) break;
       pb = (__ldg(jbt + q) >> 12) & 0xffff0u;
@@ -397,12 +400,12 @@ __device__ __forceinline__ void ux_stage(double2 (&a)[8], const QbOp *__restrict
   }
 }
 
-template <bool FULL>
+template <bool FULL, int THREADS = kFThreads>
 __device__ __forceinline__ void round_ux(const uint32_t tile_sa, const uint32_t *__restrict__ jbt,
                                          const QbOp *__restrict__ o, const int nops,
                                          const QbRound *__restrict__ R, const RoundAux *__restrict__ X,
                                          const uint32_t ngroups, const uint32_t tid, const uint64_t base) {
-  const uint32_t giters = FULL ? (ngroups / kFThreads) : ((ngroups + kFThreads - 1) / kFThreads);
+  const uint32_t giters = FULL ? (ngroups / THREADS) : ((ngroups + THREADS - 1) / THREADS);
   const uint32_t b0 = X->b[0], b1 = X->b[1], b2 = X->b[2];
   const uint32_t ux = X->ux;
   const int nu = int(ux & 3u);
@@ -416,11 +419,12 @@ __device__ __forceinline__ void round_ux(const uint32_t tile_sa, const uint32_t 
   const uint32_t pb_t = swz(jb_t) << 4;
 #pragma unroll 1
   for (uint32_t git = 0; git < giters; ++git) {
-    const uint32_t q = git * kFThreads + tid;
+    const uint32_t q = git * THREADS + tid;
+    const uint32_t sub = THREADS == kFThreads ? git : (q >> 8);
     uint32_t pb, jb;
     if (FULL) {
-      pb = pb_t ^ X->pbi[git];
-      jb = jb_t | X->jbi[git];
+      pb = pb_t ^ X->pbi[sub];
+      jb = jb_t | X->jbi[sub];
     } else {
       if (q >= ngroups) break;
       const uint32_t w = __ldg(jbt + q);
@@ -486,6 +490,27 @@ __device__ __forceinline__ void cp_async_wait() {
 __device__ __forceinline__ void round_sync(bool warp_only) {
   if (warp_only) __syncwarp();
   else __syncthreads();
+}
+
+// One round that has a round program (QbRound::prog != GENERIC).
+template <bool FULL, int THREADS>
+__device__ __forceinline__ void program_round(const FusedParams &P, const int r, const int ob, const int oe,
+                                              const uint32_t tile_sa, const uint32_t tab_sa,
+                                              const uint32_t ngroups, const uint32_t tid, const uint64_t base) {
+  const QbRound *R = P.rounds + r;
+  const RoundAux *X = P.aux + r;
+  const QbOp *o = P.ops + ob;
+  const uint32_t *jbt = P.jbtab + (size_t(r) << P.desc.ngroups_log2);
+  const bool upper = R->prog == QB_PROG_HL3U;
+  if (R->prog == QB_PROG_UX) {
+    round_ux<FULL, THREADS>(tile_sa, jbt, o, oe - ob, R, X, ngroups, tid, base);
+  } else if (X->s != 1.0) {
+    if (upper) round_hl3<true, FULL, true, THREADS>(tile_sa, tab_sa, jbt, o, R, X, ngroups, tid);
+    else round_hl3<false, FULL, true, THREADS>(tile_sa, tab_sa, jbt, o, R, X, ngroups, tid);
+  } else {
+    if (upper) round_hl3<true, FULL, false, THREADS>(tile_sa, tab_sa, jbt, o, R, X, ngroups, tid);
+    else round_hl3<false, FULL, false, THREADS>(tile_sa, tab_sa, jbt, o, R, X, ngroups, tid);
+  }
 }
 
 // FULL: the tile has a multiple of 256 groups (K >= 11), so the group loop has a trip count that
@@ -639,17 +664,7 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
       const int ob = R->op_begin, oe = (P.debug & 1) ? R->op_begin : R->op_end;
       const uint32_t *jbt = P.jbtab + (size_t(r) << P.desc.ngroups_log2);
       if (FAST || (R->prog != QB_PROG_GENERIC && !(P.debug & (1 | 16)))) {
-        const RoundAux *X = P.aux + r;
-        const bool upper = R->prog == QB_PROG_HL3U;
-        if (R->prog == QB_PROG_UX) {
-          round_ux<FULL>(tile_sa, jbt, s_ops + ob, oe - ob, R, X, ngroups, tid, base);
-        } else if (X->s != 1.0) {
-          if (upper) round_hl3<true, FULL, true>(tile_sa, tab_sa, jbt, s_ops + ob, R, X, ngroups, tid);
-          else round_hl3<false, FULL, true>(tile_sa, tab_sa, jbt, s_ops + ob, R, X, ngroups, tid);
-        } else {
-          if (upper) round_hl3<true, FULL, false>(tile_sa, tab_sa, jbt, s_ops + ob, R, X, ngroups, tid);
-          else round_hl3<false, FULL, false>(tile_sa, tab_sa, jbt, s_ops + ob, R, X, ngroups, tid);
-        }
+        program_round<FULL, kFThreads>(P, r, ob, oe, tile_sa, tab_sa, ngroups, tid, base);
         round_sync((R->nobar || (warp_io && r + 1 == P.desc.nrounds)) && !(P.debug & 64));
         continue;
       }
@@ -785,6 +800,132 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
   }
 }
 
+// ---- k_fused_pipe: persistent, software-pipelined form of the pass for program-only passes --------
+// (kept as a measured experiment, see launch_fused_pass: it loses to the one-shot kernel)
+// One CTA of 512 threads per SM walks over its tiles with a ring of kPipeBufs 64 KiB tile buffers.
+// While all 16 warps run the rounds of tile k, the cp.async copies of tiles k+1 and k+2 are in
+// flight, so nobody ever sits waiting for HBM with nothing else resident to run: with one-shot CTAs
+// (k_fused_pass) a warp spends more than half of its life waiting for its tile to arrive and only
+// ~7 of the 24 resident warps are in their compute phase at any time, too few to cover the fp64 and
+// shared-memory latencies of the rounds.  One group per thread per round (512 groups at K = 12);
+// warps w and w + 8 share a per-warp sub-cube, so the barrier-free runs of rounds use a 64-thread
+// named barrier per pair instead of a warp sync.
+constexpr int kPipeThreads = 512;
+constexpr int kPipeBufs = 3;
+
+__global__ void __launch_bounds__(kPipeThreads, 1) k_fused_pipe(const __grid_constant__ FusedParams P) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int K = 12;
+  constexpr uint32_t tileN = 1u << K;
+  constexpr uint32_t kTileBytes = tileN * sizeof(double2);
+  double2 *s_tab = reinterpret_cast<double2 *>(smem_raw + size_t(kPipeBufs) * kTileBytes);
+  const uint32_t tid = threadIdx.x;
+  double2 *__restrict__ psi = P.psi;
+  const uint32_t buf0_sa = uint32_t(__cvta_generic_to_shared(smem_raw));
+  const uint32_t tab_sa = uint32_t(__cvta_generic_to_shared(s_tab));
+
+  // copy index c = tid + 512 i: bits 0..8 from the thread, bits 9..11 from the iteration
+  uint64_t g_ld = tid & 7u, g_st = tid & 7u;
+  uint32_t j_ld = tid & 7u, j_st = tid & 7u;
+#pragma unroll
+  for (int k = 3; k < 9; ++k) {
+    const uint32_t bit = (tid >> k) & 1u;
+    j_ld |= bit << P.desc.ld_map[k];
+    j_st |= bit << P.desc.st_map[k];
+    g_ld |= uint64_t(bit) << P.desc.tile_bits[P.desc.ld_map[k]];
+    g_st |= uint64_t(bit) << P.desc.tile_bits[P.desc.st_map[k]];
+  }
+  const uint32_t s_ld = swz(j_ld) << 4, s_st = swz(j_st) << 4;
+
+  const uint32_t ntiles = 1u << (P.nbits - K);
+  auto tile_base = [&](uint32_t t) {
+    uint64_t b = 0, tt = t;
+    if (P.desc.nseg >= 0) {
+#pragma unroll
+      for (int r = 0; r < QB_MAX_SEGS; ++r) {
+        if (r < P.desc.nseg) {
+          const int len = P.desc.seg_len[r];
+          b |= (tt & ((uint64_t(1) << len) - 1)) << P.desc.seg_pos[r];
+          tt >>= len;
+        }
+      }
+      return b;
+    }
+    for (int bit = 0; bit < P.nbits; ++bit) {
+      if (!((P.desc.tile_mask >> bit) & 1)) {
+        b |= (tt & 1) << bit;
+        tt >>= 1;
+      }
+    }
+    return b;
+  };
+  auto issue_load = [&](uint32_t t, uint32_t slot) {
+    if (t < ntiles) {
+      const double2 *src = psi + (tile_base(t) | g_ld);
+      const uint32_t sa = buf0_sa + slot * kTileBytes;
+#pragma unroll
+      for (uint32_t i = 0; i < tileN / kPipeThreads; ++i)
+        cp_async16(sa + (s_ld ^ P.ld_sxor[2 * i]), src + (uint64_t(P.ld_goff[2 * i]) << 3));
+    }
+    cp_async_commit();  // always: keeps the group count in step with the tile count
+  };
+
+  const uint32_t ngroups = tileN >> 3;
+  const int nb_tab = 1 << (K - QB_ROUND_BITS - QB_LADDER_LANE_BITS);
+  const uint32_t stride = gridDim.x;
+  issue_load(blockIdx.x, 0);
+  issue_load(blockIdx.x + stride, 1);
+  for (int i = tid; i < P.desc.ntable; i += kPipeThreads) s_tab[i] = __ldg(P.tables + i);
+  __syncthreads();
+  uint32_t slot = 0;
+  for (uint32_t t = blockIdx.x; t < ntiles; t += stride) {
+    const uint64_t base = tile_base(t);
+    // per-tile constants of the phase ladders, folded into this tile's copy of T_b (every round of
+    // the previous tile is finished: its store phase does not read the tables)
+    for (int oi = int(tid >> 5); oi < P.desc.nops; oi += kPipeThreads / 32) {
+      const QbOp *op = P.ops + oi;
+      const int k8 = op->kind & 0xff;
+      if (k8 == QB_K_LADDER || k8 == QB_K_ULADDER) {
+        const int lane = int(tid & 31u);
+        const double2 *ph = P.outph + op->outph_off;
+        double2 c = make_double2(1.0, 0.0);
+        if (lane < op->nout && ((base >> __ldg(P.outbits + op->out_off + lane)) & 1)) c = __ldg(ph + 1 + lane);
+        if (lane == 0) c = cmul(c, __ldg(ph));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          double2 d;
+          d.x = __shfl_xor_sync(0xffffffffu, c.x, o);
+          d.y = __shfl_xor_sync(0xffffffffu, c.y, o);
+          c = cmul(c, d);
+        }
+        if (lane < nb_tab) {
+          const int e = op->table_off + (1 << QB_LADDER_LANE_BITS) + lane;
+          s_tab[e] = cmul(__ldg(P.tables + e), c);
+        }
+      }
+    }
+    cp_async_wait<kPipeBufs - 2>();  // this tile has landed; the next one may still be in flight
+    __syncthreads();                 // ... for every thread; the store of the previous tile is done too
+    // refill the buffer the previous tile just left (two tiles ahead)
+    issue_load(t + (kPipeBufs - 1) * stride, (slot + kPipeBufs - 1) % kPipeBufs);
+    const uint32_t tile_sa = buf0_sa + slot * kTileBytes;
+    for (int r = 0; r < ((P.debug & 2) ? 0 : P.desc.nrounds); ++r) {
+      const QbRound *R = P.rounds + r;
+      program_round<true, kPipeThreads>(P, r, R->op_begin, R->op_end, tile_sa, tab_sa, ngroups, tid, base);
+      if (R->nobar) asm volatile("bar.sync %0, 64;" ::"r"(1u + ((tid >> 5) & 7u)) : "memory");
+      else __syncthreads();
+    }
+    if (!(P.debug & 4)) {
+      double2 *dst = psi + (base | g_st);
+#pragma unroll
+      for (uint32_t i = 0; i < tileN / kPipeThreads; ++i)
+        __stcs(dst + (uint64_t(P.st_goff[2 * i]) << 3), lds128(tile_sa + (s_st ^ P.st_sxor[2 * i])));
+    }
+    slot = (slot + 1) % kPipeBufs;
+  }
+  cp_async_wait<0>();
+}
+
 size_t fused_smem_bytes(int K, int ntable) {
   return (size_t(1) << K) * sizeof(double2) + size_t(ntable) * sizeof(double2) + 4 * sizeof(uint32_t);
 }
@@ -808,6 +949,9 @@ cudaError_t fused_configure(int device) {
   static_assert(sizeof(QbRound) % 4 == 0 && (QB_MAX_PASS_OPS * sizeof(QbOp)) % 16 == 0, "smem layout");
   cudaError_t err = cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, device);
   if (err != cudaSuccess) return err;
+  if ((err = cudaFuncSetAttribute(k_fused_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemLimit))) !=
+      cudaSuccess)
+    return err;
   if ((err = configure_one<true, true>()) != cudaSuccess) return err;
   if ((err = configure_one<true, false>()) != cudaSuccess) return err;
   if ((err = configure_one<false, true>()) != cudaSuccess) return err;
@@ -929,6 +1073,18 @@ cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cuda
   unsigned blocks = ntiles;
   if (persist > 0 && ntiles > unsigned(persist * g_sms)) blocks = unsigned(persist * g_sms);
   const bool full = ((1u << (K - 3)) % kFThreads) == 0;
+  // EXPERIMENT, off by default: QCC_B200_FUSED_PIPE=1 sends program-only passes over K = 12 tiles (with
+  // enough tiles to fill the ring on every SM; =2: any tile count, what the tests use) through the
+  // persistent pipelined kernel.  Measured on a B200 it is SLOWER than one-shot CTAs (QFT-30 32.8 vs 25.5 ms,
+  // larose-28 195 vs 163 ms): 16 warps that move through the rounds in lockstep cover the fp64 and
+  // shared-memory latencies worse than 24 warps of three CTAs in different phases.  Read per launch.
+  const char *pipe_env = getenv("QCC_B200_FUSED_PIPE");
+  const int pipe = pipe_env ? atoi(pipe_env) : 0;
+  const size_t pipe_smem = size_t(kPipeBufs) * (size_t(1) << 12) * sizeof(double2) + size_t(p.desc.ntable) * sizeof(double2);
+  if (pipe && fast && K == 12 && !(dbg & 8) && (pipe == 2 || ntiles >= unsigned(4 * g_sms)) && pipe_smem <= kSmemLimit) {
+    k_fused_pipe<<<std::min(unsigned(g_sms), ntiles), kPipeThreads, pipe_smem, st>>>(P);
+    return cudaGetLastError();
+  }
   if (full && fast) k_fused_pass<true, true><<<blocks, kFThreads, smem, st>>>(P);
   else if (full) k_fused_pass<true, false><<<blocks, kFThreads, smem, st>>>(P);
   else if (fast) k_fused_pass<false, true><<<blocks, kFThreads, smem, st>>>(P);

@@ -3,10 +3,10 @@
 # variants in $VARIANTS (name:K=V,K=V ...), then one ncu --set full capture of $NCU_WL's fused passes.
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/pytest_gpu.log
+timeout ${PYTEST_TIMEOUT:-400} python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee gpurun_out/pytest_gpu.log
 run() {  # workload, name, env...
   local wl=$1 name=$2; shift 2
-  env "$@" timeout 600 python bench.py --workload $wl --steps ${STEPS:-5} --no-e2e --no-cpu-baseline --no-secondary 2>&1 | tail -1 > gpurun_out/exp_${wl}_$name.json
+  env "$@" timeout ${BENCH_TIMEOUT:-300} python bench.py --workload $wl --steps ${STEPS:-5} --no-e2e --no-cpu-baseline --no-secondary 2>&1 | tail -1 > gpurun_out/exp_${wl}_$name.json
   python - <<PY
 import json
 try:

@@ -148,6 +148,35 @@ def test_cx_fan_in_and_scheduling(n, tile_bits, seed):
   assert np.abs(got - want).max() <= TOL
 
 
+@pytest.mark.parametrize("workload,n", [("qft", 12), ("qft", 15), ("qft", 19), ("larose", 13), ("larose", 17),
+                                        ("larose", 20)])
+def test_pipelined_kernel_small_states(workload, n, monkeypatch):
+  """The persistent software-pipelined kernel (k_fused_pipe) normally takes only program-only passes
+  with >= 4 tiles per SM; QCC_B200_FUSED_PIPE=2 forces it so that 1, 8 and 128+ tiles per pass
+  (fewer tiles than ring slots, fewer CTAs than SMs, ...) are checked against the oracle."""
+  monkeypatch.setenv("QCC_B200_FUSED_PIPE", "2")
+  stream = []
+  if workload == "qft":
+    for i in reversed(range(n)):
+      stream.append((1, 0, i, oracle.GATES["h"]))
+      for j in reversed(range(i)):
+        stream.append((2, i, j, oracle.u1(math.pi / 2 ** (i - j))))
+  else:
+    for _ in range(2):
+      for bit in range(n):
+        stream.append((1, 0, bit, oracle.GATES["h"]))
+        stream.append((1, 0, bit, oracle.GATES["v"]))
+        if bit > 0:
+          stream.append((2, bit, 0, oracle.GATES["x"]))
+  psi0 = random_state(n, 3 * n)
+  want = oracle.c_run(psi0.copy(), n, stream)
+  got, _ = run_device(n, psi0, stream, True, 12)
+  assert np.abs(got - want).max() <= TOL
+  monkeypatch.setenv("QCC_B200_FUSED_PIPE", "0")
+  got0, _ = run_device(n, psi0, stream, True, 12)
+  assert np.abs(got0 - want).max() <= TOL
+
+
 @pytest.mark.parametrize("n", [10, 16, 21])
 def test_qft_matches_oracle(n):
   stream = []
