@@ -54,6 +54,12 @@ namespace qb {
 namespace {
 
 constexpr int kFThreads = 256;
+// Direct loads of the first round (QbPassDesc::ld_direct) are compiled out: measured slower than the
+// cp.async copy (see planner.cc); build with -DQB_DIRECT_LD=1 and run with QCC_B200_DIRECT_LD=1 to repeat
+// the experiment.  Direct stores of the last round stay.
+#ifndef QB_DIRECT_LD
+#define QB_DIRECT_LD 0
+#endif
 
 // Host-precomputed per-round constants of the round programs (all derivable from QbRound / QbOp;
 // kept out of the hot loop's uniform-datapath instruction stream).
@@ -61,6 +67,8 @@ struct RoundAux {
   uint32_t b[3];     // byte XOR that sets round bit k in a swizzled slot
   uint32_t pbi[(1 << (QB_MAX_TILE_BITS - 3)) / kFThreads];  // byte slot of group 256 * git
   uint32_t jbi[(1 << (QB_MAX_TILE_BITS - 3)) / kFThreads];  // tile-local base index of group 256 * git
+  uint32_t gb[3];    // direct rounds: index offset of round bit k, in units of 8 amplitudes
+  uint32_t gji[(1 << (QB_MAX_TILE_BITS - 3)) / kFThreads];  // direct rounds: index offset of group 256 * git, same units
   uint32_t ta[3];    // HL3: byte offset of the three ladders' tables
   uint32_t ux;       // UX: leading uncontrolled U's on ascending round positions, run as straight-line code:
                      //     bits 0..1 = their number, bits 4+2k..5+2k = class at position k (0 none, 1 complex, 2 real,
@@ -264,6 +272,12 @@ __device__ __forceinline__ void hladder(double2 (&a)[8], double r, double2 cf, c
   }
 }
 
+// Direct rounds (QbPassDesc::ld_direct / st_direct): the first round of a pass takes its groups straight
+// from HBM, the last one writes them straight back -- the tile then passes through shared memory only
+// between rounds.  gp = psi + tile base; the thread's part of the index (its group-number bits scattered
+// to the tile bits) is built once per round, the iteration part and the round bits come from RoundAux.
+// IO (template parameter of the round programs): bit 0 = load directly, bit 1 = store directly.
+
 // ---- round program HL3: three Hadamard+ladder stages on round positions 0, 1, 2 ---------------
 // The shape of every round of a QFT (circuit.py:320-328): h(b0) + ladder(b0), h(b1) + ladder(b1),
 // h(b2) + ladder(b2).  Fully unrolled, no op decode: per group 8 LDS.128, three table lookups (two
@@ -272,11 +286,12 @@ __device__ __forceinline__ void hladder(double2 (&a)[8], double r, double2 cf, c
 // phase, the x' path as one multiply).
 // UPPER: the ladder partners inside the round are all above their pivot, so stage 1 has one
 // non-trivial in-round phase and stage 2 none (true for the QFT; otherwise all of F is used).
-template <bool UPPER, bool FULL, bool SCALED, int THREADS = kFThreads>
+template <bool UPPER, bool FULL, bool SCALED, int IO = 0, int THREADS = kFThreads>
 __device__ __forceinline__ void round_hl3(const uint32_t tile_sa, const uint32_t tab_sa,
                                           const uint32_t *__restrict__ jbt, const QbOp *__restrict__ o,
                                           const QbRound *__restrict__ R, const RoundAux *__restrict__ X,
-                                          const uint32_t ngroups, const uint32_t tid) {
+                                          const uint32_t ngroups, const uint32_t tid, double2 *const gp,
+                                          const uint64_t g_t) {
   const double s = X->s;
   const double2 *F0 = reinterpret_cast<const double2 *>(o[0].F);
   const double2 *F1 = reinterpret_cast<const double2 *>(o[1].F);
@@ -310,9 +325,17 @@ __device__ __forceinline__ void round_hl3(const uint32_t tile_sa, const uint32_t
       pb = (__ldg(jbt + q) >> 12) & 0xffff0u;
     }
     double2 a[8];
+    double2 *gq = nullptr;
+    if (IO != 0) gq = gp + (g_t + (uint64_t(X->gji[sub]) << 3));
+    if (IO & 1) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e)
-      a[e] = lds128(tile_sa + (pb ^ ((e & 1) ? b0 : 0u) ^ ((e & 2) ? b1 : 0u) ^ ((e & 4) ? b2 : 0u)));
+      for (int e = 0; e < 8; ++e)
+        a[e] = __ldcs(gq + (uint64_t(((e & 1) ? X->gb[0] : 0u) + ((e & 2) ? X->gb[1] : 0u) + ((e & 4) ? X->gb[2] : 0u)) << 3));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        a[e] = lds128(tile_sa + (pb ^ ((e & 1) ? b0 : 0u) ^ ((e & 2) ? b1 : 0u) ^ ((e & 4) ? b2 : 0u)));
+    }
     const uint32_t tboff = (32u + (q >> 5)) << 4;
     // stage 0: pairs (e, e|1)
     {
@@ -372,9 +395,15 @@ __device__ __forceinline__ void round_hl3(const uint32_t tile_sa, const uint32_t
         a[e | 4] = cmul(d, ph);
       }
     }
+    if (IO & 2) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e)
-      sts128(tile_sa + (pb ^ ((e & 1) ? b0 : 0u) ^ ((e & 2) ? b1 : 0u) ^ ((e & 4) ? b2 : 0u)), a[e]);
+      for (int e = 0; e < 8; ++e)
+        __stcs(gq + (uint64_t(((e & 1) ? X->gb[0] : 0u) + ((e & 2) ? X->gb[1] : 0u) + ((e & 4) ? X->gb[2] : 0u)) << 3), a[e]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        sts128(tile_sa + (pb ^ ((e & 1) ? b0 : 0u) ^ ((e & 2) ? b1 : 0u) ^ ((e & 4) ? b2 : 0u)), a[e]);
+    }
   }
 }
 
@@ -400,11 +429,12 @@ __device__ __forceinline__ void ux_stage(double2 (&a)[8], const QbOp *__restrict
   }
 }
 
-template <bool FULL, int THREADS = kFThreads>
+template <bool FULL, int IO = 0, int THREADS = kFThreads>
 __device__ __forceinline__ void round_ux(const uint32_t tile_sa, const uint32_t *__restrict__ jbt,
                                          const QbOp *__restrict__ o, const int nops,
                                          const QbRound *__restrict__ R, const RoundAux *__restrict__ X,
-                                         const uint32_t ngroups, const uint32_t tid, const uint64_t base) {
+                                         const uint32_t ngroups, const uint32_t tid, const uint64_t base,
+                                         double2 *const gp, const uint64_t g_t) {
   const uint32_t giters = FULL ? (ngroups / THREADS) : ((ngroups + THREADS - 1) / THREADS);
   const uint32_t b0 = X->b[0], b1 = X->b[1], b2 = X->b[2];
   const uint32_t ux = X->ux;
@@ -432,9 +462,17 @@ __device__ __forceinline__ void round_ux(const uint32_t tile_sa, const uint32_t 
       pb = (w >> 12) & 0xffff0u;
     }
     double2 a[8];
+    double2 *gq = nullptr;
+    if (IO != 0) gq = gp + (g_t + (uint64_t(X->gji[sub]) << 3));
+    if (IO & 1) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e)
-      a[e] = lds128(tile_sa + (pb ^ ((e & 1) ? b0 : 0u) ^ ((e & 2) ? b1 : 0u) ^ ((e & 4) ? b2 : 0u)));
+      for (int e = 0; e < 8; ++e)
+        a[e] = __ldcs(gq + (uint64_t(((e & 1) ? X->gb[0] : 0u) + ((e & 2) ? X->gb[1] : 0u) + ((e & 4) ? X->gb[2] : 0u)) << 3));
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        a[e] = lds128(tile_sa + (pb ^ ((e & 1) ? b0 : 0u) ^ ((e & 2) ? b1 : 0u) ^ ((e & 4) ? b2 : 0u)));
+    }
     if (c0) ux_stage<0>(a, o0, c0);
     if (c1) ux_stage<1>(a, o1, c1);
     if (c2) ux_stage<2>(a, o2, c2);
@@ -462,9 +500,15 @@ __device__ __forceinline__ void round_ux(const uint32_t tile_sa, const uint32_t 
         else ux_stage<2>(a, op, cls);
       }
     }
+    if (IO & 2) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e)
-      sts128(tile_sa + (pb ^ ((e & 1) ? b0 : 0u) ^ ((e & 2) ? b1 : 0u) ^ ((e & 4) ? b2 : 0u)), a[e]);
+      for (int e = 0; e < 8; ++e)
+        __stcs(gq + (uint64_t(((e & 1) ? X->gb[0] : 0u) + ((e & 2) ? X->gb[1] : 0u) + ((e & 4) ? X->gb[2] : 0u)) << 3), a[e]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        sts128(tile_sa + (pb ^ ((e & 1) ? b0 : 0u) ^ ((e & 2) ? b1 : 0u) ^ ((e & 4) ? b2 : 0u)), a[e]);
+    }
   }
 }
 
@@ -496,21 +540,39 @@ __device__ __forceinline__ void round_sync(bool warp_only) {
 template <bool FULL, int THREADS>
 __device__ __forceinline__ void program_round(const FusedParams &P, const int r, const int ob, const int oe,
                                               const uint32_t tile_sa, const uint32_t tab_sa,
-                                              const uint32_t ngroups, const uint32_t tid, const uint64_t base) {
+                                              const uint32_t ngroups, const uint32_t tid, const uint64_t base,
+                                              const bool direct) {
   const QbRound *R = P.rounds + r;
   const RoundAux *X = P.aux + r;
   const QbOp *o = P.ops + ob;
   const uint32_t *jbt = P.jbtab + (size_t(r) << P.desc.ngroups_log2);
   const bool upper = R->prog == QB_PROG_HL3U;
-  if (R->prog == QB_PROG_UX) {
-    round_ux<FULL, THREADS>(tile_sa, jbt, o, oe - ob, R, X, ngroups, tid, base);
-  } else if (X->s != 1.0) {
-    if (upper) round_hl3<true, FULL, true, THREADS>(tile_sa, tab_sa, jbt, o, R, X, ngroups, tid);
-    else round_hl3<false, FULL, true, THREADS>(tile_sa, tab_sa, jbt, o, R, X, ngroups, tid);
-  } else {
-    if (upper) round_hl3<true, FULL, false, THREADS>(tile_sa, tab_sa, jbt, o, R, X, ngroups, tid);
-    else round_hl3<false, FULL, false, THREADS>(tile_sa, tab_sa, jbt, o, R, X, ngroups, tid);
+  const bool ld = QB_DIRECT_LD && FULL && direct && r == 0 && P.desc.ld_direct;
+  const bool st = FULL && direct && r + 1 == P.desc.nrounds && P.desc.st_direct;
+  double2 *const gp = P.psi + base;
+  uint64_t g_t = 0;
+  if (ld || st) {
+    // the thread's group-number bits (0..7) scattered to the index bits they drive
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g_t |= uint64_t((tid >> k) & 1u) << P.desc.tile_bits[R->qmap[k]];
   }
+#define QB_ROUND_IO(CALL)                                    \
+  do {                                                       \
+    if (!FULL || THREADS != kFThreads || (!ld && !st)) { constexpr int IO = 0; CALL; } \
+    else if (QB_DIRECT_LD && ld && !st) { constexpr int IO = FULL && THREADS == kFThreads ? 1 : 0; CALL; } \
+    else if (!QB_DIRECT_LD || !ld) { constexpr int IO = FULL && THREADS == kFThreads ? 2 : 0; CALL; }       \
+    else { constexpr int IO = FULL && THREADS == kFThreads ? 3 : 0; CALL; }                \
+  } while (0)
+  if (R->prog == QB_PROG_UX) {
+    QB_ROUND_IO((round_ux<FULL, IO, THREADS>(tile_sa, jbt, o, oe - ob, R, X, ngroups, tid, base, gp, g_t)));
+  } else if (X->s != 1.0) {
+    if (upper) QB_ROUND_IO((round_hl3<true, FULL, true, IO, THREADS>(tile_sa, tab_sa, jbt, o, R, X, ngroups, tid, gp, g_t)));
+    else QB_ROUND_IO((round_hl3<false, FULL, true, IO, THREADS>(tile_sa, tab_sa, jbt, o, R, X, ngroups, tid, gp, g_t)));
+  } else {
+    if (upper) QB_ROUND_IO((round_hl3<true, FULL, false, IO, THREADS>(tile_sa, tab_sa, jbt, o, R, X, ngroups, tid, gp, g_t)));
+    else QB_ROUND_IO((round_hl3<false, FULL, false, IO, THREADS>(tile_sa, tab_sa, jbt, o, R, X, ngroups, tid, gp, g_t)));
+  }
+#undef QB_ROUND_IO
 }
 
 // FULL: the tile has a multiple of 256 groups (K >= 11), so the group loop has a trip count that
@@ -586,8 +648,11 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
     }
     return b;
   };
+  // direct first / last round: no copy-in / copy-out of the tile (FAST or not, the first / last round
+  // then has a round program; the debug switches that bypass the programs turn it off on the host)
+  const bool ld_direct = QB_DIRECT_LD && FULL && P.desc.ld_direct, st_direct = FULL && P.desc.st_direct;
   auto issue_load = [&](uint64_t b) {
-    if (!(P.debug & 8) && io_on) {
+    if (!(P.debug & 8) && io_on && !ld_direct) {
       const double2 *src = psi + (b | g_ld);
       if (io_iters == 16) {  // K = 12: constant-bank operands with immediate addresses
 #pragma unroll
@@ -664,7 +729,7 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
       const int ob = R->op_begin, oe = (P.debug & 1) ? R->op_begin : R->op_end;
       const uint32_t *jbt = P.jbtab + (size_t(r) << P.desc.ngroups_log2);
       if (FAST || (R->prog != QB_PROG_GENERIC && !(P.debug & (1 | 16)))) {
-        program_round<FULL, kFThreads>(P, r, ob, oe, tile_sa, tab_sa, ngroups, tid, base);
+        program_round<FULL, kFThreads>(P, r, ob, oe, tile_sa, tab_sa, ngroups, tid, base, true);
         round_sync((R->nobar || (warp_io && r + 1 == P.desc.nrounds)) && !(P.debug & 64));
         continue;
       }
@@ -782,7 +847,7 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
     }
 
     // ---- STORE ---------------------------------------------------------------------------
-    if (!(P.debug & 4) && io_on) {
+    if (!(P.debug & 4) && io_on && !st_direct) {
       double2 *dst = psi + (base | g_st);
       if (io_iters == 16) {
 #pragma unroll
@@ -911,7 +976,7 @@ __global__ void __launch_bounds__(kPipeThreads, 1) k_fused_pipe(const __grid_con
     const uint32_t tile_sa = buf0_sa + slot * kTileBytes;
     for (int r = 0; r < ((P.debug & 2) ? 0 : P.desc.nrounds); ++r) {
       const QbRound *R = P.rounds + r;
-      program_round<true, kPipeThreads>(P, r, R->op_begin, R->op_end, tile_sa, tab_sa, ngroups, tid, base);
+      program_round<true, kPipeThreads>(P, r, R->op_begin, R->op_end, tile_sa, tab_sa, ngroups, tid, base, false);
       if (R->nobar) asm volatile("bar.sync %0, 64;" ::"r"(1u + ((tid >> 5) & 7u)) : "memory");
       else __syncthreads();
     }
@@ -932,6 +997,13 @@ size_t fused_smem_bytes(int K, int ntable) {
 
 constexpr size_t kSmemLimit = 227 * 1024;
 int g_sms = 0;
+
+// QCC_B200_FUSED_PIPE (experiment, see launch_fused_pass), read per launch
+int pipe_mode() {
+  const char *e = getenv("QCC_B200_FUSED_PIPE");
+  return e ? atoi(e) : 0;
+}
+bool pipe_forced() { return pipe_mode() != 0; }
 
 template <bool FULL, bool FAST>
 cudaError_t configure_one() {
@@ -1020,7 +1092,11 @@ cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cuda
       for (int k = 8; k < K - 3; ++k) jb |= ((git >> (k - 8)) & 1u) << R.qmap[k];
       X.pbi[git] = swz_h(jb) << 4;
       X.jbi[git] = jb;
+      uint64_t g = 0;
+      for (int k = 8; k < K - 3; ++k) g |= uint64_t((git >> (k - 8)) & 1u) << p.desc.tile_bits[R.qmap[k]];
+      X.gji[git] = uint32_t(g >> 3);
     }
+    for (int k = 0; k < 3; ++k) X.gb[k] = uint32_t((uint64_t(1) << p.desc.tile_bits[R.rbit[k]]) >> 3);
     if (R.prog == QB_PROG_UX) {
       int prev = -1;
       uint32_t nu = 0;
@@ -1060,6 +1136,8 @@ cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cuda
           for (int k = 0; k < 3; ++k) P.aux[r].s *= p.ops[p.rounds[r].op_begin + k].m[0];
         }
   }
+  if (dbg & (1 | 2 | 4 | 8 | 16)) P.desc.ld_direct = P.desc.st_direct = 0;  // timing experiments use the copy path
+  if (pipe_forced()) P.desc.ld_direct = P.desc.st_direct = 0;
   // FAST: no round needs the op interpreter (and the debug switches that fall back to it are off)
   bool fast = !(dbg & (1 | 16));
   for (int r = 0; r < p.desc.nrounds; ++r)
@@ -1078,8 +1156,7 @@ cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cuda
   // persistent pipelined kernel.  Measured on a B200 it is SLOWER than one-shot CTAs (QFT-30 32.8 vs 25.5 ms,
   // larose-28 195 vs 163 ms): 16 warps that move through the rounds in lockstep cover the fp64 and
   // shared-memory latencies worse than 24 warps of three CTAs in different phases.  Read per launch.
-  const char *pipe_env = getenv("QCC_B200_FUSED_PIPE");
-  const int pipe = pipe_env ? atoi(pipe_env) : 0;
+  const int pipe = pipe_mode();
   const size_t pipe_smem = size_t(kPipeBufs) * (size_t(1) << 12) * sizeof(double2) + size_t(p.desc.ntable) * sizeof(double2);
   if (pipe && fast && K == 12 && !(dbg & 8) && (pipe == 2 || ntiles >= unsigned(4 * g_sms)) && pipe_smem <= kSmemLimit) {
     k_fused_pipe<<<std::min(unsigned(g_sms), ntiles), kPipeThreads, pipe_smem, st>>>(P);

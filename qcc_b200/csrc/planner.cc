@@ -916,6 +916,24 @@ void emit_pass(int nbits, int K, const std::vector<const Item *> &items, const s
   for (RoundPlan &rp : rplans) close_round(tm, rp, &nlad, &pp);
   pp.desc.nrounds = int32_t(pp.rounds.size());
   pp.desc.nops = int32_t(pp.ops.size());
+  {
+    static const bool no_direct = getenv("QCC_B200_NO_DIRECT") != nullptr;
+    auto direct_ok = [&](const QbRound &R) {
+      if (!pp.desc.warp_io || no_direct || R.prog == QB_PROG_GENERIC) return false;
+      int low = 0;
+      for (int k = 0; k < 3; ++k) {
+        if (R.rbit[k] < 3) return false;
+        if (R.qmap[k] < 3) low |= 1 << R.qmap[k];
+      }
+      return low == 7;
+    };
+    // Direct LOADS are a measured loss (QFT-30 27.4 vs 26.5 ms, larose-28 203 vs 174 ms on the same box): a
+    // thread can only have the 8 loads of one group in flight (registers), half the bytes in flight of
+    // the cp.async copy, and pays the HBM latency once per group instead of once per tile.  Opt-in only.
+    static const bool direct_ld = getenv("QCC_B200_DIRECT_LD") != nullptr;
+    pp.desc.ld_direct = direct_ld && !pp.rounds.empty() && direct_ok(pp.rounds.front()) ? 1 : 0;
+    pp.desc.st_direct = !pp.rounds.empty() && direct_ok(pp.rounds.back()) ? 1 : 0;
+  }
   pp.desc.ntable = int32_t(pp.tables.size());
   pp.desc.ngroups_log2 = tm.K - 3;
   // runs of consecutive non-tile bits: the kernel scatters the tile number over them
@@ -1073,8 +1091,8 @@ std::string Plan::to_json() const {
       s += "]}";
       continue;
     }
-    snprintf(buf, sizeof buf, "{\"single_gate\":-1,\"ngates\":%lld,\"K\":%d,\"warp_io\":%d,\"ld_map\":[",
-             (long long)p.ngates, p.desc.K, p.desc.warp_io);
+    snprintf(buf, sizeof buf, "{\"single_gate\":-1,\"ngates\":%lld,\"K\":%d,\"warp_io\":%d,\"ld_direct\":%d,\"st_direct\":%d,\"ld_map\":[",
+             (long long)p.ngates, p.desc.K, p.desc.warp_io, p.desc.ld_direct, p.desc.st_direct);
     s += buf;
     for (int k = 0; k < p.desc.K; ++k) {
       snprintf(buf, sizeof buf, "%s%d", k ? "," : "", p.desc.ld_map[k]);
