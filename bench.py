@@ -75,41 +75,80 @@ def hbm_peak():
 
 
 class ClockSampler(threading.Thread):
-  """nvidia-smi clocks + throttle reasons while the timed region runs."""
+  """SM clock, power and throttle reasons while the timed region runs: NVML every 10 ms (the timed
+  region of the default run is a quarter of a second), nvidia-smi every 200 ms when NVML is missing."""
   Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
        "clocks_event_reasons.sw_power_cap")
+  NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+  NVML_BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
   def __init__(self, index):
     super().__init__(daemon=True)
     self.index = index
-    self.samples = []
+    self.samples = []     # (sm_mhz, power_w, set of reasons)
+    self.sm_max = None
     self.stop_flag = False
+    self.source = "nvidia-smi"
+    self.nvml = None
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+      self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+      self.nvml = pynvml
+      self.source = "nvml"
+    except Exception:  # pylint: disable=broad-except
+      self.nvml = None
+
+  def _sample_nvml(self):
+    nv = self.nvml
+    sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+    try:
+      pw = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+    except Exception:  # pylint: disable=broad-except
+      pw = None
+    try:
+      bits = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+    except Exception:  # pylint: disable=broad-except
+      bits = 0
+    self.samples.append((sm, pw, {nm for nm, b in self.NVML_BITS.items() if bits & b}))
+
+  def _sample_smi(self):
+    out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                          "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                         timeout=5).stdout.strip()
+    if not out:
+      return
+    f = [x.strip() for x in out.split(",")]
+    num = lambda x: float(x) if x.replace(".", "").isdigit() else None
+    if self.sm_max is None:
+      self.sm_max = num(f[1])
+    if num(f[0]) is not None:
+      self.samples.append((num(f[0]), num(f[2]), {nm for k, nm in enumerate(self.NAMES) if f[3 + k] == "Active"}))
 
   def run(self):
     while not self.stop_flag:
       try:
-        out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                              "--format=csv,noheader,nounits"], capture_output=True, text=True,
-                             timeout=5).stdout.strip()
-        if out:
-          self.samples.append([x.strip() for x in out.split(",")])
+        if self.nvml is not None:
+          self._sample_nvml()
+        else:
+          self._sample_smi()
       except Exception:  # pylint: disable=broad-except
         pass
-      time.sleep(0.2)
+      time.sleep(0.01 if self.nvml is not None else 0.2)
 
   def summary(self):
     self.stop_flag = True
     self.join(timeout=6)
     if not self.samples:
-      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-    sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
-    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-    reasons = [nm for k, nm in enumerate(names) if any(s[3 + k] == "Active" for s in self.samples)]
-    return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-            "sm_max_mhz": float(self.samples[0][1]) if self.samples[0][1].replace(".", "").isdigit() else None,
-            "power_w_max": max((float(s[2]) for s in self.samples if s[2].replace(".", "").isdigit()), default=None),
-            "samples": len(self.samples), "reasons": reasons}
+      return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["no clock samples (nvml / nvidia-smi unavailable)"]}
+    sm = sorted(s[0] for s in self.samples)
+    pw = [s[1] for s in self.samples if s[1] is not None]
+    reasons = [nm for nm in self.NAMES if any(nm in s[2] for s in self.samples)]
+    return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.sm_max,
+            "power_w_max": max(pw) if pw else None, "samples": len(self.samples), "source": self.source,
+            "reasons": reasons}
 
 
 def cpu_reference_sample(n, stream, budget_s=20.0, max_gates=8):

@@ -518,8 +518,9 @@ std::vector<RoundPlan> inorder_rounds(const TileMap &tm, const std::vector<const
 // items: everything ready that fits the round's bits is absorbed (diagonal items always fit); a new
 // round bit is taken from the ready item whose bit strands the least work -- items on that bit that
 // could not finish inside this round and would force the bit into a later round again -- with
-// uncontrolled U's preferred (they are what the predicate-free UX round program runs) and program order as the
-// tie break, so a stream without freedom (the QFT) comes out exactly as written.
+// uncontrolled U's preferred (they are what the predicate-free UX round program runs; those on tile
+// positions 0..2 first) and program order as the tie break, so a stream without freedom (the QFT)
+// comes out exactly as written.
 std::vector<RoundPlan> schedule_rounds(const TileMap &tm, const std::vector<const Item *> &items) {
   const int n = int(items.size());
   const int nr = std::min(tm.K, QB_ROUND_BITS);
@@ -580,7 +581,11 @@ std::vector<RoundPlan> schedule_rounds(const TileMap &tm, const std::vector<cons
           if (!ok && lp_of[size_t(k)] == lp) ++stranded;
         }
         const Item &it = *items[size_t(j)];
-        const int cls = (it.kind == QB_K_U && it.g.ctl_mask == 0) ? 0 : 1;
+        // class 0: uncontrolled U on tile positions 0..2 -- taken first, so that these bits are used up in
+        // the early rounds and the LAST round of the pass can store straight to HBM (st_direct needs its
+        // round bits outside positions 0..2); class 1: other uncontrolled U's; class 2: the rest
+        const bool free_u = it.kind == QB_K_U && it.g.ctl_mask == 0;
+        const int cls = free_u ? (lp < QB_TILE_LOW ? 0 : 1) : 2;
         if (best < 0 || stranded < best_stranded || (stranded == best_stranded && cls < best_cls)) {
           best = j;
           best_stranded = stranded;
