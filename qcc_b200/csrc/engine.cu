@@ -265,8 +265,6 @@ int do_exchange(qb_state *s, int rank_bit, int victim) {
   const size_t half_bytes = size_t(s->len / 2) * sizeof(double2);
   if (s->xbuf_bytes < half_bytes) {
     if (s->xbuf) cudaFree(s->xbuf);
-  for (auto e : s->xevents) cudaEventDestroy(e);
-  if (s->xstream) cudaStreamDestroy(s->xstream);
     s->xbuf = nullptr;
     s->xbuf_bytes = 0;
     cudaError_t e = cudaMalloc(&s->xbuf, half_bytes);

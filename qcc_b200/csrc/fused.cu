@@ -67,6 +67,7 @@ struct RoundAux {
   uint32_t b[3];     // byte XOR that sets round bit k in a swizzled slot
   uint32_t pbi[(1 << (QB_MAX_TILE_BITS - 3)) / kFThreads];  // byte slot of group 256 * git
   uint32_t jbi[(1 << (QB_MAX_TILE_BITS - 3)) / kFThreads];  // tile-local base index of group 256 * git
+  uint32_t pbt[8];   // byte XOR that group-number bit k (a thread-index bit) contributes to the swizzled slot
   uint32_t gb[3];    // direct rounds: index offset of round bit k, in units of 8 amplitudes
   uint32_t gji[(1 << (QB_MAX_TILE_BITS - 3)) / kFThreads];  // direct rounds: index offset of group 256 * git, same units
   uint32_t ta[3];    // HL3: byte offset of the three ladders' tables
@@ -88,6 +89,8 @@ struct FusedParams {
   // per copy iteration i (thread t moves copy index t + 256 i, see QbPassDesc::ld_map / st_map): global
   // offset of copy index 256 i in units of 8 amplitudes, and the XOR that takes the byte slot of copy
   // index t to the byte slot of copy index t + 256 i
+  // copy index bits 3..7 (thread bits): index offset in units of 8 amplitudes / byte XOR of the swizzled slot
+  uint32_t ld_gbit[8], ld_sbit[8], st_gbit[8], st_sbit[8];
   uint32_t ld_goff[(1 << QB_MAX_TILE_BITS) / kFThreads];
   uint32_t ld_sxor[(1 << QB_MAX_TILE_BITS) / kFThreads];
   uint32_t st_goff[(1 << QB_MAX_TILE_BITS) / kFThreads];
@@ -307,12 +310,11 @@ __device__ __forceinline__ void round_hl3(const uint32_t tile_sa, const uint32_t
   // qmap[]).  The slot is linear over XOR in q, so the per-thread part is built once per round
   // from tid and the per-iteration part is uniform: no table load at the head of the dependency
   // chain of every group.
-  uint32_t jb_t = 0;
+  uint32_t pb_t = 0;
   if (FULL) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) jb_t |= ((tid >> k) & 1u) << R->qmap[k];
+    for (int k = 0; k < 8; ++k) pb_t ^= ((tid >> k) & 1u) ? X->pbt[k] : 0u;
   }
-  const uint32_t pb_t = swz(jb_t) << 4;
 #pragma unroll 1
   for (uint32_t git = 0; git < giters; ++git) {
     const uint32_t q = git * THREADS + tid;
@@ -606,18 +608,18 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
   // XOR and the copy itself per 16 bytes.
   // With warp_io the copy index is not the tile-local index: its warp bits (5..7) select the per-warp
   // sub-cube of the first (load) / last (store) run of rounds, so a warp moves what it computes on.
-  uint64_t g_ld = tid & 7u, g_st = tid & 7u;
-  uint32_t j_ld = tid & 7u, j_st = tid & 7u;
+  // (per-bit terms precomputed on the host: positions 0..2 keep their slot bits under the swizzle XOR)
+  uint32_t g8_ld = 0, g8_st = 0;
+  uint32_t s_ld = swz(tid & 7u) << 4, s_st = s_ld;
 #pragma unroll
-  for (int k = 3; k < 8; ++k)
-    if (k < K) {
-      const uint32_t bit = (tid >> k) & 1u;
-      j_ld |= bit << P.desc.ld_map[k];
-      j_st |= bit << P.desc.st_map[k];
-      g_ld |= uint64_t(bit) << P.desc.tile_bits[P.desc.ld_map[k]];
-      g_st |= uint64_t(bit) << P.desc.tile_bits[P.desc.st_map[k]];
-    }
-  const uint32_t s_ld = swz(j_ld) << 4, s_st = swz(j_st) << 4;
+  for (int k = 3; k < 8; ++k) {
+    const bool bit = (tid >> k) & 1u;
+    g8_ld += bit ? P.ld_gbit[k] : 0u;
+    g8_st += bit ? P.st_gbit[k] : 0u;
+    s_ld ^= bit ? P.ld_sbit[k] : 0u;
+    s_st ^= bit ? P.st_sbit[k] : 0u;
+  }
+  const uint64_t g_ld = (uint64_t(g8_ld) << 3) | (tid & 7u), g_st = (uint64_t(g8_st) << 3) | (tid & 7u);
   const bool warp_io = P.desc.warp_io != 0;
   const uint32_t io_iters = tileN > kFThreads ? tileN / kFThreads : 1u;
   const bool io_on = tid < tileN;
@@ -1057,6 +1059,15 @@ cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cuda
     return j ^ (x & 7u);
   };
   P.ld_goff[0] = P.ld_sxor[0] = P.st_goff[0] = P.st_sxor[0] = 0;
+  for (int k = 0; k < 8; ++k) {
+    P.ld_gbit[k] = P.ld_sbit[k] = P.st_gbit[k] = P.st_sbit[k] = 0;
+    if (k >= 3 && k < K) {
+      P.ld_gbit[k] = uint32_t((uint64_t(1) << p.desc.tile_bits[p.desc.ld_map[k]]) >> 3);
+      P.st_gbit[k] = uint32_t((uint64_t(1) << p.desc.tile_bits[p.desc.st_map[k]]) >> 3);
+      P.ld_sbit[k] = swz_h(1u << p.desc.ld_map[k]) << 4;
+      P.st_sbit[k] = swz_h(1u << p.desc.st_map[k]) << 4;
+    }
+  }
   for (uint32_t i = 0; i < (1u << K) / kFThreads; ++i) {
     // copy index 256 i: its bits 8.. drive tile-local positions ld_map[8..] / st_map[8..]
     uint32_t jl = 0, js = 0;
@@ -1097,6 +1108,7 @@ cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cuda
       X.gji[git] = uint32_t(g >> 3);
     }
     for (int k = 0; k < 3; ++k) X.gb[k] = uint32_t((uint64_t(1) << p.desc.tile_bits[R.rbit[k]]) >> 3);
+    for (int k = 0; k < 8 && k < K - 3; ++k) X.pbt[k] = swz_h(1u << R.qmap[k]) << 4;
     if (R.prog == QB_PROG_UX) {
       int prev = -1;
       uint32_t nu = 0;
