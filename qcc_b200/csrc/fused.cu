@@ -68,6 +68,8 @@ struct RoundAux {
   uint32_t pbi[(1 << (QB_MAX_TILE_BITS - 3)) / kFThreads];  // byte slot of group 256 * git
   uint32_t jbi[(1 << (QB_MAX_TILE_BITS - 3)) / kFThreads];  // tile-local base index of group 256 * git
   uint32_t pbt[8];   // byte XOR that group-number bit k (a thread-index bit) contributes to the swizzled slot
+  uint32_t jbk[8];   // ... and the tile-local index bit it drives (1 << qmap[k])
+  uint32_t gbk[8];   // ... and its index offset in units of 8 amplitudes (direct rounds; 0 for tile positions 0..2)
   uint32_t gb[3];    // direct rounds: index offset of round bit k, in units of 8 amplitudes
   uint32_t gji[(1 << (QB_MAX_TILE_BITS - 3)) / kFThreads];  // direct rounds: index offset of group 256 * git, same units
   uint32_t ta[3];    // HL3: byte offset of the three ladders' tables
@@ -443,12 +445,15 @@ __device__ __forceinline__ void round_ux(const uint32_t tile_sa, const uint32_t 
   const int nu = int(ux & 3u);
   const uint32_t c0 = (ux >> 4) & 3u, c1 = (ux >> 6) & 3u, c2 = (ux >> 8) & 3u;
   const QbOp *o0 = o, *o1 = o + (c0 ? 1 : 0), *o2 = o1 + (c1 ? 1 : 0);
-  uint32_t jb_t = 0;
+  uint32_t jb_t = 0, pb_t = 0;
   if (FULL) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) jb_t |= ((tid >> k) & 1u) << R->qmap[k];
+    for (int k = 0; k < 8; ++k) {
+      const bool bit = (tid >> k) & 1u;
+      jb_t |= bit ? X->jbk[k] : 0u;
+      pb_t ^= bit ? X->pbt[k] : 0u;
+    }
   }
-  const uint32_t pb_t = swz(jb_t) << 4;
 #pragma unroll 1
   for (uint32_t git = 0; git < giters; ++git) {
     const uint32_t q = git * THREADS + tid;
@@ -554,9 +559,16 @@ __device__ __forceinline__ void program_round(const FusedParams &P, const int r,
   double2 *const gp = P.psi + base;
   uint64_t g_t = 0;
   if (ld || st) {
-    // the thread's group-number bits (0..7) scattered to the index bits they drive
+    // the thread's group-number bits (0..7) scattered to the index bits they drive (lanes 0..7 sit on
+    // tile positions 0..2 = index bits 0..2; the other terms are multiples of 8 amplitudes)
+    uint32_t g8 = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) g_t |= uint64_t((tid >> k) & 1u) << P.desc.tile_bits[R->qmap[k]];
+    for (int k = 0; k < 8; ++k) {
+      const bool bit = (tid >> k) & 1u;
+      if (k < 3) g_t |= bit ? uint64_t(X->jbk[k]) : 0u;
+      else g8 += bit ? X->gbk[k] : 0u;
+    }
+    g_t |= uint64_t(g8) << 3;
   }
 #define QB_ROUND_IO(CALL)                                    \
   do {                                                       \
@@ -1108,7 +1120,11 @@ cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cuda
       X.gji[git] = uint32_t(g >> 3);
     }
     for (int k = 0; k < 3; ++k) X.gb[k] = uint32_t((uint64_t(1) << p.desc.tile_bits[R.rbit[k]]) >> 3);
-    for (int k = 0; k < 8 && k < K - 3; ++k) X.pbt[k] = swz_h(1u << R.qmap[k]) << 4;
+    for (int k = 0; k < 8 && k < K - 3; ++k) {
+      X.pbt[k] = swz_h(1u << R.qmap[k]) << 4;
+      X.jbk[k] = 1u << R.qmap[k];
+      X.gbk[k] = uint32_t((uint64_t(1) << p.desc.tile_bits[R.qmap[k]]) >> 3);
+    }
     if (R.prog == QB_PROG_UX) {
       int prev = -1;
       uint32_t nu = 0;
