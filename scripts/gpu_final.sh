@@ -11,7 +11,7 @@ timeout 900 python bench.py --workload hsweep30 --steps 5 --warmup 3 --no-e2e --
 timeout 900 python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -1 > gpurun_out/bench_reference.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_qft30.csv \
   python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_launch.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_fused_pass -s 9 -c 3 -o gpurun_out/prof_fused_final \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_fused_pass -s 9 -c 3 -f -o gpurun_out/prof_fused_final \
   python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-secondary > gpurun_out/ncu_full.log 2>&1
 for f in qft30 larose28 hsweep30 reference; do python - <<PY
 import json
@@ -23,3 +23,7 @@ except Exception as e:
   print("$f FAILED", e, open("gpurun_out/bench_$f.json").read()[-500:])
 PY
 done
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_fused_pass -s 20 -c 3 -f -o gpurun_out/prof_larose_final \
+  python bench.py --workload larose28 --steps 1 --warmup 3 --no-e2e --no-cpu-baseline --no-secondary > gpurun_out/ncu_full_larose.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_larose28.csv \
+  python bench.py --workload larose28 --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-secondary > gpurun_out/ncu_launch_larose.log 2>&1

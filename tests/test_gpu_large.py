@@ -107,3 +107,30 @@ def test_fused_equals_single_gate_path_at_28():
       y = b.copy_out(first, 1 << 16)
       assert np.abs(x - y).max() < 1e-15 * 1e3  # amplitudes are ~6e-5; agreement to ~1e-16 relative
     assert a.counters()["passes"] * 3 < b.counters()["passes"]
+
+
+def test_larose_28_fused_equals_single_gate_path():
+  """configs[1] at full size: two depths of larose_benchmark.py:47-54 (h, v, cx(bit, 0) per qubit) --
+  scheduled UX rounds, the cx fan-in as parity swaps, direct-store last rounds -- against the
+  gate-by-gate sweeps on sampled slices of a random state."""
+  n = 28
+  stream = []
+  for _ in range(2):
+    for bit in range(n):
+      stream.append((1, 0, bit, oracle.GATES["h"]))
+      stream.append((1, 0, bit, oracle.GATES["v"]))
+      if bit > 0:
+        stream.append((2, bit, 0, oracle.GATES["x"]))
+  packed = _cabi.pack_xg_gates(stream)
+  with _cabi.DeviceState(n) as a, _cabi.DeviceState(n) as b:
+    a.fill_random(7)
+    b.fill_random(7)
+    b.set_fusion(False)
+    a.xg_apply_gates(packed)
+    b.xg_apply_gates(packed)
+    assert abs(a.norm2() - 1.0) < 1e-9 and abs(b.norm2() - 1.0) < 1e-9
+    for first in (0, (1 << 19) + 8, (1 << 27) - (1 << 15), (1 << 27) + 4093 * 16, (1 << 28) - (1 << 16)):
+      x = a.copy_out(first, 1 << 16)
+      y = b.copy_out(first, 1 << 16)
+      assert np.abs(x - y).max() < 1e-12
+    assert a.counters()["passes"] == 6 and b.counters()["passes"] == len(stream)
