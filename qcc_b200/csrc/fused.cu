@@ -445,6 +445,7 @@ __device__ __forceinline__ void round_ux(const uint32_t tile_sa, const uint32_t 
   const int nu = int(ux & 3u);
   const uint32_t c0 = (ux >> 4) & 3u, c1 = (ux >> 6) & 3u, c2 = (ux >> 8) & 3u;
   const QbOp *o0 = o, *o1 = o + (c0 ? 1 : 0), *o2 = o1 + (c1 ? 1 : 0);
+  const uint32_t uni = (c0 == c1 && c1 == c2) ? c0 : 0u;  // all three stages present and of one matrix class
   uint32_t jb_t = 0, pb_t = 0;
   if (FULL) {
 #pragma unroll
@@ -480,9 +481,28 @@ __device__ __forceinline__ void round_ux(const uint32_t tile_sa, const uint32_t 
       for (int e = 0; e < 8; ++e)
         a[e] = lds128(tile_sa + (pb ^ ((e & 1) ? b0 : 0u) ^ ((e & 2) ? b1 : 0u) ^ ((e & 4) ? b2 : 0u)));
     }
-    if (c0) ux_stage<0>(a, o0, c0);
-    if (c1) ux_stage<1>(a, o1, c1);
-    if (c2) ux_stage<2>(a, o2, c2);
+    if (uni == 3) {
+      // all three positions carry a column-imaginary U (every round of larose): one straight-line block,
+      // no control-flow joins between the stages, so no register moves to line results up
+      const double2 *m0 = reinterpret_cast<const double2 *>(o0->m);
+      const double2 *m1 = reinterpret_cast<const double2 *>(o1->m);
+      const double2 *m2 = reinterpret_cast<const double2 *>(o2->m);
+      bfly_colimag<0>(a, m0[0].x, m0[1].y, m0[2].x, m0[3].y);
+      bfly_colimag<1>(a, m1[0].x, m1[1].y, m1[2].x, m1[3].y);
+      bfly_colimag<2>(a, m2[0].x, m2[1].y, m2[2].x, m2[3].y);
+    } else if (uni == 1) {
+      ux_stage<0>(a, o0, 1);
+      ux_stage<1>(a, o1, 1);
+      ux_stage<2>(a, o2, 1);
+    } else if (uni == 2) {
+      ux_stage<0>(a, o0, 2);
+      ux_stage<1>(a, o1, 2);
+      ux_stage<2>(a, o2, 2);
+    } else {
+      if (c0) ux_stage<0>(a, o0, c0);
+      if (c1) ux_stage<1>(a, o1, c1);
+      if (c2) ux_stage<2>(a, o2, c2);
+    }
 #pragma unroll 1
     for (int oi = nu; oi < nops; ++oi) {
       const QbOp *op = o + oi;
@@ -700,7 +720,9 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
       if ((tid & 31u) == 0) s_active[tid >> 5] = bal;
     }
     // per-tile constants of the phase ladders (overlaps the wait for the tile's data): one
-    // warp per ladder, lane k owns outside bit k, product by butterfly shuffles
+    // warp per ladder, lane k owns outside bit k, product by butterfly shuffles.  (One warp with a
+    // lane per ladder needs 4x fewer instructions but was measured 9 % SLOWER on QFT-30: its serial
+    // chain of up to 18 dependent complex multiplies sits on every CTA's critical path.)
     for (int oi = int(tid >> 5); oi < P.desc.nops; oi += kFThreads / 32) {
       const QbOp *op = s_ops + oi;
       const int k8 = op->kind & 0xff;
