@@ -19,6 +19,11 @@ def val2bits(val: int, nbits: int) -> List[int]:
   return [(val >> (nbits - 1 - k)) & 1 for k in range(nbits)]
 
 
+def bits2frac(bits: Iterable[int]) -> float:
+  """(1, 0, 1) -> 0.625: the bits as a binary fraction, first bit = 1/2 (helper.py:34-37)."""
+  return sum((1 if b else 0) * 2.0 ** (-(k + 1)) for k, b in enumerate(bits))
+
+
 def pi_fractions(val, pi: str = "pi") -> str:
   """Pretty-print an angle as a fraction of pi when it is one (helper.py:84-106): the
   transpiler relies on this to emit M_PI/2, -M_PI/4, ... instead of decimals."""

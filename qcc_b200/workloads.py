@@ -176,3 +176,128 @@ def qft_adder(n: int, init_a: int, init_b: int, factor: float = 1.0, *, eager: b
   for i in range(n + 1):
     inverse_qft_step(a, i)
   return qc, a, b
+
+
+# ---------------------------------------------------------------------------------------------
+# Order finding: the phase-estimation circuit of order_finding.py:152-183 --
+# Beauregard-style modular multiplication out of Fourier-space adders -- on the device-resident qc,
+# with the readout of order_finding.py:185-202 done by a device-side listing instead of a Python
+# scan over all 2^n bit strings.
+# ---------------------------------------------------------------------------------------------
+def _modinv(a: int, m: int) -> int:
+  """a^-1 mod m (order_finding.py:33-50)."""
+  g, x, _ = _egcd(a % m, m)
+  assert g == 1, f"modular inverse ({a}, {m}) does not exist"
+  return x % m
+
+
+def _egcd(a: int, b: int):
+  if a == 0:
+    return b, 0, 1
+  g, y, x = _egcd(b % a, a)
+  return g, x - (b // a) * y, y
+
+
+def _fourier_angles(a: int, n: int):
+  """Rotation angle of each qubit of an n-qubit Fourier-space register when the classical number
+  `a` is added to it (order_finding.py:53-62): qubit n-1-i collects a's bits i.. with halving weights."""
+  out = [0.0] * n
+  for i in range(n):
+    acc = 0.0
+    for j in range(i, n):
+      if a & (1 << (n - j - 1)):
+        acc += 2.0 ** (-(j - i))
+    out[n - i - 1] = acc * math.pi
+  return out
+
+
+def order_finding(number: int, a: int, *, eager: bool = True, qc_factory=None):
+  """Quantum order finding for `a` modulo `number` (order_finding.py:152-183): 4 * nbits + 2
+  qubits with nbits = number.bit_length() -- N=15, a=4: 18 qubits; N=21, a=11: 22 qubits (the circuit
+  behind src/libq/libq_order22_test.cc).  Returns (qc, aux, up, down); `up` holds the phase."""
+  from qcc_b200 import circuit
+  nbits = number.bit_length()
+  qc = qc_factory("order_finding") if qc_factory else circuit.qc("order_finding", eager=eager)
+  aux = qc.reg(nbits + 2)          # adder / multiplier work register (order_finding.py:165)
+  up = qc.reg(nbits * 2)           # phase register (:168)
+  down = qc.reg(nbits)             # the number being multiplied (:171)
+  _modinv(int(a), number)
+
+  def add(q, val, n, factor):                       # order_finding.py:65-69
+    for k, angle in enumerate(_fourier_angles(val, n)):
+      qc.u1(q[k], factor * angle)
+
+  def cadd(q, ctl, val, n, factor):                 # :72-76
+    for k, angle in enumerate(_fourier_angles(val, n)):
+      qc.cu1(ctl, q[k], factor * angle)
+
+  def ccadd(q, c1, c2, val, n, factor):             # :79-84
+    for k, angle in enumerate(_fourier_angles(val, n)):
+      qc.ccu1(c1, c2, q[k], factor * angle)
+
+  def cc_add_mod(q, c1, c2, anc, val, n):           # :95-109
+    ccadd(q, c1, c2, val, n, 1.0)
+    add(q, number, n, -1.0)
+    qc.inverse_qft(q[:n])
+    qc.cx(q[n - 1], anc)
+    qc.qft(q[:n])
+    cadd(q, anc, number, n, 1.0)
+    ccadd(q, c1, c2, val, n, -1.0)
+    qc.inverse_qft(q[:n])
+    qc.cx0(q[n - 1], anc)
+    qc.qft(q[:n])
+    ccadd(q, c1, c2, val, n, 1.0)
+
+  def cc_add_mod_inverse(q, c1, c2, anc, val, n):   # :112-126
+    ccadd(q, c1, c2, val, n, -1.0)
+    qc.inverse_qft(q[:n])
+    qc.cx0(q[n - 1], anc)
+    qc.qft(q[:n])
+    ccadd(q, c1, c2, val, n, 1.0)
+    cadd(q, anc, number, n, -1.0)
+    qc.inverse_qft(q[:n])
+    qc.cx(q[n - 1], anc)
+    qc.qft(q[:n])
+    add(q, number, n, 1.0)
+    ccadd(q, c1, c2, val, n, -1.0)
+
+  def cmult_mod(ctl, mult):                         # :129-149
+    n = nbits
+    qc.qft(aux[:n + 1])
+    for i in range(n):
+      cc_add_mod(aux, down[i], ctl, aux[n + 1], ((2 ** i) * mult) % number, n + 1)
+    qc.inverse_qft(aux[:n + 1])
+    for i in range(n):
+      qc.cswap(ctl, down[i], aux[i])
+    inv = _modinv(mult, number)
+    qc.qft(aux[:n + 1])
+    for i in reversed(range(n)):
+      cc_add_mod_inverse(aux, down[i], ctl, aux[n + 1], ((2 ** i) * inv) % number, n + 1)
+    qc.inverse_qft(aux[:n + 1])
+
+  qc.h(up)                                          # :177-181
+  qc.x(down[0])
+  for i in range(nbits * 2):
+    cmult_mod(up[i], int(a ** (2 ** i)))
+  qc.inverse_qft(up[:2 * nbits], with_swaps=True)
+  return qc, aux, up, down
+
+
+def order_readout(qc, number: int, a: int, threshold: float = 0.01):
+  """order_finding.py:185-202 without the scan over 2^n bit strings: every basis state with
+  probability > threshold, as (x, phase, prob, order guess r, factor guesses)."""
+  import fractions
+  from qcc_b200 import helper
+  nbits = number.bit_length()
+  n = 4 * nbits + 2
+  labels, amps, _ = qc.psi.nonzero(threshold)
+  out = []
+  for idx, amp in zip(labels, amps):
+    bits = helper.val2bits(int(idx), n)
+    bitslice = bits[nbits + 2: nbits + 2 + nbits * 2][::-1]
+    x = helper.bits2val(bitslice)
+    phase = helper.bits2frac(bitslice)
+    r = fractions.Fraction(phase).limit_denominator(8).denominator
+    guesses = [math.gcd(a ** (r // 2) - 1, number), math.gcd(a ** (r // 2) + 1, number)]
+    out.append((x, phase, float(abs(amp) ** 2), r, guesses))
+  return out

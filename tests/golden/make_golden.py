@@ -22,6 +22,11 @@ Everything written here is small (n <= 12 qubits) and committed; tests never nee
                      the oracle-safe gate subset, read from the qureg struct.
   libq_*_test.out    stdout of the reference's three libq test mains.
   qft6_libq.cc       dumpers.libq() text for the 6-qubit QFT (configs[0]).
+  order_N15_a4.npz   SURVEY 8(f)1: the gate stream the reference's order_finding.py builds
+                     for N=15, a=4 (18 qubits, 12 353 IR nodes), and what its xgates build
+                     computes from it: the basis states with p > 0.01 that the script's
+                     measurement loop prints (order_finding.py:185-202), 64 sampled
+                     amplitudes and the norm (the 4 MiB state itself is not stored).
 """
 import math
 import os
@@ -324,8 +329,45 @@ def libq_cases():
     f.write(f"{hashlib.sha256(chr(10).join(lines).encode()).hexdigest()} {len(lines)}\n")
 
 
+def order_finding_case(number=15, a=4):
+  """order_finding.py:152-183 recorded as IR through the reference's own functions, then run with
+  its xgates build.  Only the readout is stored (see the module docstring)."""
+  from src import order_finding as of    # defines its --N / --a flags on import: harmless here
+  nbits = number.bit_length()
+  n = 4 * nbits + 2
+  qc = circuit.qc("order_finding", eager=False)
+  aux = qc.reg(nbits + 2)
+  up = qc.reg(nbits * 2)
+  down = qc.reg(nbits)
+  qc.h(up)
+  qc.x(down[0])
+  for i in range(nbits * 2):
+    of.cmultmodn(qc, up[i], down, aux, int(a ** (2 ** i)), number, nbits)
+  of.inverse_qft(qc, up, 2 * nbits, with_swaps=True)
+  stream = ir_stream(qc)
+  psi = np.zeros(1 << n, dtype=np.complex128)
+  psi[0] = 1.0
+  XG.run(psi, n, [g[:4] for g in stream])
+  p = np.abs(psi) ** 2
+  keep = np.nonzero(p > 0.01)[0]
+  rng = np.random.default_rng(15)
+  sample = np.sort(rng.choice(1 << n, size=64, replace=False))
+  psi0 = np.zeros(2, dtype=np.complex128)   # placeholder: the initial state is |0...0>
+  save_stream(os.path.join(HERE, f"order_N{number}_a{a}.npz"), n, psi0, stream,
+              labels=keep.astype(np.int64), probs=p[keep], sample_idx=sample.astype(np.int64),
+              sample_amp=psi[sample], norm2=float(p.sum()))
+  for k in keep:
+    bits = [int(b) for b in format(int(k), f"0{n}b")]
+    bitslice = bits[nbits + 2: nbits + 2 + nbits * 2][::-1]
+    print("  x =", int("".join(map(str, bitslice)), 2), "p =", round(float(p[k]), 4))
+
+
 if __name__ == "__main__":
+  if len(sys.argv) > 1 and sys.argv[1] == "order":
+    order_finding_case()
+    sys.exit(0)
   dense_cases()
   acceleration_case()
   circuit_cases()
   libq_cases()
+  order_finding_case()

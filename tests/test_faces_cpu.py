@@ -148,3 +148,25 @@ def test_transpiled_adder_reproduces_the_reference_test_program():
   want, count = open(os.path.join(GOLDEN, "libq_arith_test.calls.sha256")).read().split()
   assert len(lines) == int(count)
   assert hashlib.sha256("\n".join(lines).encode()).hexdigest() == want
+
+
+def test_order_finding_stream_matches_the_reference():
+  """order_finding.py:152-183 (N=15, a=4, 18 qubits) written against our surface records
+  gate for gate the stream the reference's own functions record (ccu1 -> sqrt expansions, cswap, cx0,
+  inverse_qft with swaps), and the oracle reproduces what the reference's xgates build computes from it."""
+  from helpers import oracle
+  from qcc_b200 import workloads
+  z = load_golden("order_N15_a4.npz")
+  qc, aux, up, down = workloads.order_finding(15, 4, eager=False)
+  assert qc.nbits == 18 == int(z["nbits"]) and (len(aux), len(up), len(down)) == (6, 8, 4)
+  ours = ir_stream(qc)
+  assert len(ours) == 10297
+  assert_same_stream(ours, z)
+  psi = np.zeros(1 << 18, dtype=np.complex128)
+  psi[0] = 1.0
+  oracle.c_run(psi, 18, [g[:4] for g in ours])
+  p = np.abs(psi) ** 2
+  assert abs(p.sum() - float(z["norm2"])) < 1e-10
+  assert np.array_equal(np.nonzero(p > 0.01)[0], z["labels"])
+  assert np.abs(p[z["labels"]] - z["probs"]).max() < 1e-10
+  assert np.abs(psi[z["sample_idx"]] - z["sample_amp"]).max() < 1e-10

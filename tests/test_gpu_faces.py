@@ -330,3 +330,51 @@ def test_qft_adder_transpiled_to_libq(tmp_path):
   ref = parse_print_qureg(open(os.path.join(GOLDEN, "libq_arith_test.out")).read())
   assert bits == ref[_arith_golden_label()][2]
   assert "# of qubits        : 26" in out
+
+
+# ---------------------------------------------------------------------------------------
+# order finding (order_finding.py:152-204) end to end
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fusion", [True, False])
+def test_order_finding_golden_stream_on_device(fusion):
+  """The 10 297-gate stream the reference records for N=15, a=4 (18 qubits): the device state has the
+  basis states with p > 0.01, the sampled amplitudes and the norm of the reference's xgates run."""
+  from qcc_b200 import _cabi
+  z = load_golden("order_N15_a4.npz")
+  n = int(z["nbits"])
+  with _cabi.DeviceState(n, 0) as s:
+    s.set_fusion(fusion)
+    s.xg_apply_gates(_cabi.pack_xg_gates(stream_of(z)))
+    assert abs(s.norm2() - float(z["norm2"])) < 1e-10
+    labels, amps, total = s.list_above(0.01)
+    assert total == len(z["labels"]) and np.array_equal(np.sort(labels), z["labels"])
+    order = np.argsort(labels)
+    assert np.abs(np.abs(np.asarray(amps)[order]) ** 2 - z["probs"]).max() < 1e-10
+    for idx, want in zip(z["sample_idx"], z["sample_amp"]):
+      assert abs(s.amplitude(int(idx)) - want) < 1e-10
+    cnt = s.counters()
+    assert cnt["gates_applied"] == 10297
+    if fusion:
+      assert cnt["passes"] * 50 < cnt["gates_applied"]
+
+
+@pytest.mark.parametrize("number,a,order", [(15, 4, 2), (21, 11, 6)])
+def test_order_finding_python_face(number, a, order):
+  """order_finding.py main on the device-resident surface (18 and 22 qubits -- the second is the
+  circuit behind src/libq/libq_order22_test.cc): the phase register peaks at multiples of 1/order and
+  the continued-fraction readout of order_finding.py:185-202 recovers the order."""
+  qc, aux, up, down = workloads.order_finding(number, a)
+  nbits = number.bit_length()
+  assert qc.nbits == 4 * nbits + 2
+  assert abs(qc.psi.norm2() - 1.0) < 1e-9
+  found = workloads.order_readout(qc, number, a)
+  assert found and sum(p for _, _, p, _, _ in found) > 0.5
+  rs = set()
+  for x, phase, p, r, guesses in found:
+    # every peak sits (to register resolution) on a multiple of 1/order
+    k = round(phase * order)
+    assert abs(phase - k / order) < 2.0 ** (-2 * nbits) * 1.01 + 1e-12, (x, phase)
+    rs.add(r)
+  assert all(order % r == 0 for r in rs) and math.lcm(*rs) == order
+  assert pow(a, order, number) == 1
+  qc.close()
