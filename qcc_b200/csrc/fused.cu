@@ -713,7 +713,7 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
     const uint32_t tn = t + gridDim.x;
     const bool more = tn < ntiles;
     // which ops apply to this tile at all (their controls outside the tile): one bit per op
-    if (!FAST && tid < 64) {
+    if (!FAST && tid < 128) {
       const bool on = int(tid) < P.desc.nops && ((s_ops[tid].kind & 0xff) == QB_K_PARSWAP ||  // its gmask is a parity
                                                   (base & s_ops[tid].gmask) == s_ops[tid].gwant);
       const uint32_t bal = __ballot_sync(0xffffffffu, on);
@@ -786,10 +786,11 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
 
         // One dense opcode per (kind, target position, matrix class): a single jump-table switch
         // replaces the chain of compare-and-branch steps a generic (kind, tpos, flags) decode needs.
-        const uint64_t active = (uint64_t(s_active[1]) << 32) | s_active[0];
+        const uint64_t active_lo = (uint64_t(s_active[1]) << 32) | s_active[0];
+        const uint64_t active_hi = (uint64_t(s_active[3]) << 32) | s_active[2];
 #pragma unroll 1
         for (int oi = ob; oi < oe; ++oi) {
-          if (!((active >> oi) & 1)) continue;                            // uniform per tile
+          if (!(((oi < 64 ? active_lo : active_hi) >> (oi & 63)) & 1)) continue;  // uniform per tile
           const QbOp *op = s_ops + oi;
           const double2 *mp = reinterpret_cast<const double2 *>(op->m);
           const int opc = int(uint32_t(op->kind) >> 24);
@@ -1055,6 +1056,8 @@ cudaError_t configure_one() {
 cudaError_t fused_configure(int device) {
   static_assert(sizeof(QbOp) == 256, "QbOp layout");
   static_assert(sizeof(QbRound) % 4 == 0 && (QB_MAX_PASS_OPS * sizeof(QbOp)) % 16 == 0, "smem layout");
+  static_assert(QB_MAX_PASS_OPS <= 128, "the active-op mask of the interpreter has 128 bits");
+  static_assert(sizeof(FusedParams) <= 32764, "kernel parameter space");
   cudaError_t err = cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, device);
   if (err != cudaSuccess) return err;
   if ((err = cudaFuncSetAttribute(k_fused_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemLimit))) !=

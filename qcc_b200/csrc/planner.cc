@@ -437,17 +437,46 @@ void assign_group_maps(const TileMap &tm, std::vector<RoundPlan> *rounds, QbPass
         if (std::find(U.begin(), U.end(), b) == U.end()) U.push_back(b);
       return U;
     };
+    // pad a sub-cube to gbits bits: first whatever swizzle class (bit % 3) some round of the run would
+    // otherwise miss among its free bits (its lanes 0..2 need one bit of each class for conflict-free
+    // shared-memory access), then the lowest tile bits
+    auto padded = [&](std::vector<int> base, size_t r0, size_t r1) {
+      for (size_t r = r0; r < r1; ++r)
+        for (int cls = 0; cls < 3 && int(base.size()) < gbits; ++cls) {
+          bool have = false;
+          for (int b : base)
+            if (b % 3 == cls && std::find((*rounds)[r].rset.begin(), (*rounds)[r].rset.end(), b) == (*rounds)[r].rset.end())
+              have = true;
+          for (int k = 0; k < K && !have; ++k)
+            if (k % 3 == cls && std::find(base.begin(), base.end(), k) == base.end()) {
+              base.push_back(k);
+              have = true;
+            }
+        }
+      for (int k = 0; k < K && int(base.size()) < gbits; ++k)
+        if (std::find(base.begin(), base.end(), k) == base.end()) base.push_back(k);
+      return base;
+    };
+    auto classes_ok = [&](const std::vector<int> &full, size_t r0, size_t r1) {
+      for (size_t r = r0; r < r1; ++r) {
+        int seen = 0;
+        for (int b : full)
+          if (std::find((*rounds)[r].rset.begin(), (*rounds)[r].rset.end(), b) == (*rounds)[r].rset.end()) seen |= 1 << (b % 3);
+        if (seen != 7) return false;
+      }
+      return true;
+    };
     S = merged(S, (*rounds)[i].rset);
     size_t j = i + 1;
     for (; j < rounds->size(); ++j) {
       std::vector<int> U = merged(S, (*rounds)[j].rset);
       if (int(U.size()) > gbits) break;
+      // a longer run must not cost any of its rounds its conflict-free lane bits
+      if (!classes_ok(padded(U, i, j + 1), i, j + 1) && classes_ok(padded(S, i, j), i, j)) break;
       S = U;
     }
     if (j - i >= 2 || low3) {
-      // pad S to gbits bits, preferring the lowest tile bits
-      for (int k = 0; k < K && int(S.size()) < gbits; ++k)
-        if (std::find(S.begin(), S.end(), k) == S.end()) S.push_back(k);
+      S = padded(S, i, j);
       std::sort(S.begin(), S.end());
       std::vector<int> W;
       for (int k = 0; k < K; ++k)

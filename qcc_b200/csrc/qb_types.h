@@ -60,7 +60,7 @@ struct QbGate {
 #define QB_MAX_TILE_BITS 13  // 2^13 * 16 B = 128 KiB
 #define QB_ROUND_BITS 3      // 8 amplitudes = 16 doubles in registers per thread
 #define QB_LADDER_LANE_BITS 5 // ladder lookup tables: T_a over group-index bits 0..4 (the lane), T_b over the rest
-#define QB_MAX_PASS_OPS 48   // ops of one pass travel as kernel parameters (48 * 256 B)
+#define QB_MAX_PASS_OPS 96   // ops of one pass travel as kernel parameters (96 * 256 B of the 32 KiB parameter space)
 #define QB_MAX_PASS_ROUNDS 16
 #define QB_MAX_SEGS 6
 #define QB_MAX_PASS_LADDERS 12  // their lookup tables (48 x 16 B each at K = 12) are staged in shared memory too
