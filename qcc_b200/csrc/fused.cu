@@ -197,6 +197,20 @@ __device__ __forceinline__ void bfly_masked(double2 (&a)[8], const Mat &m, uint3
   }
 }
 
+// butterfly on the pairs selected by bit e of sel (sel is uniform: a precomputed round-level predicate)
+template <int TP>
+__device__ __forceinline__ void bfly_sel(double2 (&a)[8], const Mat &m, uint32_t sel) {
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    if (e & (1 << TP)) continue;
+    if ((sel >> e) & 1u) {
+      const double2 x = a[e], y = a[e | (1 << TP)];
+      a[e] = mad2f(m.a, x, m.b, y);
+      a[e | (1 << TP)] = mad2f(m.c, x, m.d, y);
+    }
+  }
+}
+
 template <int TP>
 __device__ __forceinline__ void perm_masked(double2 (&a)[8], double2 mb, double2 mc, uint32_t rmask,
                                             uint32_t rwant) {
@@ -507,11 +521,37 @@ __device__ __forceinline__ void round_ux(const uint32_t tile_sa, const uint32_t 
     for (int oi = nu; oi < nops; ++oi) {
       const QbOp *op = o + oi;
       const int opc = int(uint32_t(op->kind) >> 24);
+      // controls outside the tile: uniform per CTA (a PARSWAP's gmask is a parity, handled below)
+      if (!(opc >= QB_OPC_PARSWAP && opc < QB_OPC_PARSWAP + 3) && (base & op->gmask) != op->gwant) continue;
       if (opc >= QB_OPC_U_CI) {
         const uint32_t tp = uint32_t(opc - QB_OPC_U_CI);
         if (tp == 0) ux_stage<0>(a, op, 3);
         else if (tp == 1) ux_stage<1>(a, op, 3);
         else ux_stage<2>(a, op, 3);
+      } else if ((opc >= QB_OPC_SWAP && opc <= QB_OPC_PHASE) || (opc >= QB_OPC_U_MASKED && opc < QB_OPC_U_MASKED + 3)) {
+        // controlled swap (cx, ccx, ...) / controlled phase / controlled 2x2: controls outside the tile
+        // are uniform per CTA, tile bits outside the round one test per group, round bits precomputed
+        // (op->flags)
+        if ((jb & op->lmask) != op->lwant) continue;
+        const uint32_t sel = uint32_t(op->flags);
+        if (opc < QB_OPC_SWAP) {
+          const double2 *mp = reinterpret_cast<const double2 *>(op->m);
+          const Mat m{mp[0], mp[1], mp[2], mp[3]};
+          if (opc == QB_OPC_U_MASKED + 0) bfly_sel<0>(a, m, sel);
+          else if (opc == QB_OPC_U_MASKED + 1) bfly_sel<1>(a, m, sel);
+          else bfly_sel<2>(a, m, sel);
+        } else if (opc == QB_OPC_PHASE) {
+          const double2 ph = *reinterpret_cast<const double2 *>(op->m);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if ((sel >> e) & 1u) a[e] = cmul(ph, a[e]);
+        } else if (opc == QB_OPC_SWAP + 0) {
+          parswap<0>(a, sel);
+        } else if (opc == QB_OPC_SWAP + 1) {
+          parswap<1>(a, sel);
+        } else {
+          parswap<2>(a, sel);
+        }
       } else if (opc >= QB_OPC_PARSWAP) {
         const uint32_t odd = (uint32_t(__popcll(base & op->gmask)) + uint32_t(__popc(jb & op->lmask)) + op->rwant) & 1u;
         const uint32_t sel = op->lwant ^ (0u - odd);
@@ -1160,7 +1200,7 @@ cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cuda
         if (opc >= QB_OPC_U_ALL && opc < QB_OPC_U_ALL + 3) cls = 1;
         else if (opc >= QB_OPC_U_ALL + 3 && opc < QB_OPC_U_ALL + 6) cls = 2;
         else if (opc >= QB_OPC_U_CI && opc < QB_OPC_U_CI + 3) cls = 3;
-        if (cls == 0 || o.tpos <= prev) break;
+        if (cls == 0 || o.tpos <= prev || o.gmask != 0) break;  // the straight-line prefix has no predicates
         X.ux |= cls << (4 + 2 * o.tpos);
         prev = o.tpos;
         ++nu;

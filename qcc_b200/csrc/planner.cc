@@ -865,6 +865,13 @@ void close_round(const TileMap &tm, RoundPlan &rp, int *nladders, PlannedPass *p
       case QB_K_PHASE: opc = QB_OPC_PHASE; break;
       default: opc = QB_OPC_LADDER; break;
     }
+    if ((op.kind & 0xff) == QB_K_SWAP || (op.kind & 0xff) == QB_K_PHASE ||
+        ((op.kind & 0xff) == QB_K_U && opc >= QB_OPC_U_MASKED && opc < QB_OPC_U_MASKED + 3)) {
+      // which of the 8 registers the round-level predicate selects, precomputed for the lean interpreter
+      op.flags = 0;
+      for (int e = 0; e < 8; ++e)
+        if ((uint32_t(e) & op.rmask) == op.rwant) op.flags |= 1 << e;
+    }
     op.kind = (op.kind & 0xff) | ((op.tpos & 0xff) << 8) | ((op.mflags & 0xff) << 16) | (opc << 24);
     pp->ops.push_back(op);
   }
@@ -886,16 +893,22 @@ void close_round(const TileMap &tm, RoundPlan &rp, int *nladders, PlannedPass *p
       r.prog = upper ? QB_PROG_HL3U : QB_PROG_HL3;
     }
   }
-  // Round program UX: nothing but uncontrolled U's and parity swaps (every round of larose_benchmark).
+  // Round program UX: uncontrolled U's, parity swaps (every round of larose_benchmark), and -- unless
+  // QCC_B200_UX_NARROW is set -- controlled swaps (cx / ccx), controlled phases (z s t u1 cz cu1 ...) and
+  // controlled 2x2s (cv, ch, crx, ... and the sqrt(X) of the Toffoli expansion):
+  // everything the lean interpreter of fused.cu handles without the generic one's registers.
   if (r.prog == QB_PROG_GENERIC && nr == QB_ROUND_BITS && r.op_end > r.op_begin) {
+    static const bool narrow = getenv("QCC_B200_UX_NARROW") != nullptr;
     bool ux = true;
     for (int k = r.op_begin; k < r.op_end; ++k) {
       const QbOp &o = pp->ops[size_t(k)];
       const int opc = int(uint32_t(o.kind) >> 24);
       const bool u_all = ((opc >= QB_OPC_U_ALL && opc < QB_OPC_U_ALL + 6) || (opc >= QB_OPC_U_CI && opc < QB_OPC_U_CI + 3)) &&
-                         o.gmask == 0;
+                         (o.gmask == 0 || !narrow);
       const bool psw = opc >= QB_OPC_PARSWAP && opc < QB_OPC_PARSWAP + 3;
-      if (!u_all && !psw) ux = false;
+      const bool cswap_or_phase = !narrow && ((opc >= QB_OPC_SWAP && opc < QB_OPC_SWAP + 3) || opc == QB_OPC_PHASE ||
+                                              (opc >= QB_OPC_U_MASKED && opc < QB_OPC_U_MASKED + 3));
+      if (!u_all && !psw && !cswap_or_phase) ux = false;
     }
     if (ux) r.prog = QB_PROG_UX;
   }

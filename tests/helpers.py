@@ -172,9 +172,12 @@ def interpret_plan(plan_json: str, n: int, gates, psi: np.ndarray) -> np.ndarray
         # UX program: uncontrolled U's and parity swaps only (the kernel's predicate-free interpreter)
         for o in rops:
           k8 = o["kind"] & 0xFF
-          assert k8 in (K_U, K_PARSWAP) and len(rops) >= 1
-          if k8 == K_U:
-            assert o["lmask"] == 0 and o["rmask"] == 0 and o["gmask"] == 0
+          assert k8 in (K_U, K_PARSWAP, K_SWAP, K_PHASE) and len(rops) >= 1
+          masked_u = k8 == K_U and 15 <= (o["kind"] >> 24) < 18
+          if k8 in (K_SWAP, K_PHASE) or masked_u:
+            assert o["flags"] == sum(1 << e for e in range(8) if (e & o["rmask"]) == o["rwant"])
+          if k8 == K_U and not masked_u:
+            assert o["lmask"] == 0 and o["rmask"] == 0
             real = all(o["m"][2 * i + 1] == 0.0 for i in range(4))
             colimag = not real and o["m"][1] == 0 and o["m"][5] == 0 and o["m"][2] == 0 and o["m"][6] == 0
             assert (o["kind"] >> 24) == (29 + o["tpos"] if colimag else 9 + o["tpos"] + (3 if real else 0))
