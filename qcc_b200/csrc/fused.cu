@@ -452,7 +452,7 @@ __device__ __forceinline__ void round_ux(const uint32_t tile_sa, const uint32_t 
                                          const QbOp *__restrict__ o, const int nops,
                                          const QbRound *__restrict__ R, const RoundAux *__restrict__ X,
                                          const uint32_t ngroups, const uint32_t tid, const uint64_t base,
-                                         double2 *const gp, const uint64_t g_t) {
+                                         double2 *const gp, const uint64_t g_t, const uint32_t tab_sa) {
   const uint32_t giters = FULL ? (ngroups / THREADS) : ((ngroups + THREADS - 1) / THREADS);
   const uint32_t b0 = X->b[0], b1 = X->b[1], b2 = X->b[2];
   const uint32_t ux = X->ux;
@@ -523,7 +523,36 @@ __device__ __forceinline__ void round_ux(const uint32_t tile_sa, const uint32_t 
       const int opc = int(uint32_t(op->kind) >> 24);
       // controls outside the tile: uniform per CTA (a PARSWAP's gmask is a parity, handled below)
       if (!(opc >= QB_OPC_PARSWAP && opc < QB_OPC_PARSWAP + 3) && (base & op->gmask) != op->gwant) continue;
-      if (opc >= QB_OPC_U_CI) {
+      if (opc < QB_OPC_U_ALL || opc == QB_OPC_LADDER) {
+        // phase ladder (optionally fused with the butterfly on its pivot): phase = T_a[lane] * T_b[q >> 5]
+        // (the tile's copy of T_b carries the per-tile constant) * F[e]
+        const uint32_t tb = tab_sa + (uint32_t(op->table_off) << 4);
+        const double2 c = cmul(lds128(tb + ((q & 31u) << 4)), lds128(tb + ((32u + (q >> QB_LADDER_LANE_BITS)) << 4)));
+        const double2 *F = reinterpret_cast<const double2 *>(op->F);
+        const double2 *mp = reinterpret_cast<const double2 *>(op->m);
+        if (opc == QB_OPC_LADDER) {
+          if ((jb & op->lmask) != op->lwant) continue;
+          const uint32_t rmask = op->rmask, rwant = op->rwant;
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if ((uint32_t(e) & rmask) == rwant) a[e] = cmul(cmul(c, F[e]), a[e]);
+        } else if (opc < 3) {
+          const Mat m{mp[0], mp[1], mp[2], mp[3]};
+          if (opc == 0) uladder<0, false>(a, m, c, F);
+          else if (opc == 1) uladder<1, false>(a, m, c, F);
+          else uladder<2, false>(a, m, c, F);
+        } else if (opc < 6) {
+          Mat m;
+          m.a.x = mp[0].x; m.b.x = mp[1].x; m.c.x = mp[2].x; m.d.x = mp[3].x;
+          if (opc == 3) uladder<0, true>(a, m, c, F);
+          else if (opc == 4) uladder<1, true>(a, m, c, F);
+          else uladder<2, true>(a, m, c, F);
+        } else {
+          if (opc == 6) hladder<0>(a, mp[0].x, c, F);
+          else if (opc == 7) hladder<1>(a, mp[0].x, c, F);
+          else hladder<2>(a, mp[0].x, c, F);
+        }
+      } else if (opc >= QB_OPC_U_CI) {
         const uint32_t tp = uint32_t(opc - QB_OPC_U_CI);
         if (tp == 0) ux_stage<0>(a, op, 3);
         else if (tp == 1) ux_stage<1>(a, op, 3);
@@ -638,7 +667,7 @@ __device__ __forceinline__ void program_round(const FusedParams &P, const int r,
     else { constexpr int IO = FULL && THREADS == kFThreads ? 3 : 0; CALL; }                \
   } while (0)
   if (R->prog == QB_PROG_UX) {
-    QB_ROUND_IO((round_ux<FULL, IO, THREADS>(tile_sa, jbt, o, oe - ob, R, X, ngroups, tid, base, gp, g_t)));
+    QB_ROUND_IO((round_ux<FULL, IO, THREADS>(tile_sa, jbt, o, oe - ob, R, X, ngroups, tid, base, gp, g_t, tab_sa)));
   } else if (X->s != 1.0) {
     if (upper) QB_ROUND_IO((round_hl3<true, FULL, true, IO, THREADS>(tile_sa, tab_sa, jbt, o, R, X, ngroups, tid, gp, g_t)));
     else QB_ROUND_IO((round_hl3<false, FULL, true, IO, THREADS>(tile_sa, tab_sa, jbt, o, R, X, ngroups, tid, gp, g_t)));

@@ -895,7 +895,7 @@ void close_round(const TileMap &tm, RoundPlan &rp, int *nladders, PlannedPass *p
   }
   // Round program UX: uncontrolled U's, parity swaps (every round of larose_benchmark), and -- unless
   // QCC_B200_UX_NARROW is set -- controlled swaps (cx / ccx), controlled phases (z s t u1 cz cu1 ...) and
-  // controlled 2x2s (cv, ch, crx, ... and the sqrt(X) of the Toffoli expansion):
+  // controlled 2x2s (cv, ch, crx, ... and the sqrt(X) of the Toffoli expansion) and phase ladders:
   // everything the lean interpreter of fused.cu handles without the generic one's registers.
   if (r.prog == QB_PROG_GENERIC && nr == QB_ROUND_BITS && r.op_end > r.op_begin) {
     static const bool narrow = getenv("QCC_B200_UX_NARROW") != nullptr;
@@ -908,7 +908,8 @@ void close_round(const TileMap &tm, RoundPlan &rp, int *nladders, PlannedPass *p
       const bool psw = opc >= QB_OPC_PARSWAP && opc < QB_OPC_PARSWAP + 3;
       const bool cswap_or_phase = !narrow && ((opc >= QB_OPC_SWAP && opc < QB_OPC_SWAP + 3) || opc == QB_OPC_PHASE ||
                                               (opc >= QB_OPC_U_MASKED && opc < QB_OPC_U_MASKED + 3));
-      if (!u_all && !psw && !cswap_or_phase) ux = false;
+      const bool ladder = !narrow && (opc < QB_OPC_U_ALL || opc == QB_OPC_LADDER);  // ULADDER family / LADDER
+      if (!u_all && !psw && !cswap_or_phase && !ladder) ux = false;
     }
     if (ux) r.prog = QB_PROG_UX;
   }

@@ -172,7 +172,7 @@ def interpret_plan(plan_json: str, n: int, gates, psi: np.ndarray) -> np.ndarray
         # UX program: uncontrolled U's and parity swaps only (the kernel's predicate-free interpreter)
         for o in rops:
           k8 = o["kind"] & 0xFF
-          assert k8 in (K_U, K_PARSWAP, K_SWAP, K_PHASE) and len(rops) >= 1
+          assert k8 in (K_U, K_PARSWAP, K_SWAP, K_PHASE, K_LADDER, K_ULADDER) and len(rops) >= 1
           masked_u = k8 == K_U and 15 <= (o["kind"] >> 24) < 18
           if k8 in (K_SWAP, K_PHASE) or masked_u:
             assert o["flags"] == sum(1 << e for e in range(8) if (e & o["rmask"]) == o["rwant"])
