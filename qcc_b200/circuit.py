@@ -447,10 +447,21 @@ class qc:
     """C++ program for this circuit's IR against libq.h (dumpers.libq)."""
     return dumpers.libq(self.ir)
 
-  def dump_to_file(self, libq: str = None) -> None:
-    if libq:
-      with open(libq, "w") as f:
-        print(self.libq(), file=f)
+  def qasm(self) -> str:
+    """OPENQASM 2.0 text for this circuit's IR (dumpers.qasm)."""
+    return dumpers.qasm(self.ir)
+
+  def cirq(self) -> str:
+    """Cirq script for this circuit's IR (dumpers.cirq)."""
+    return dumpers.cirq(self.ir)
+
+  def dump_to_file(self, libq: str = None, qasm: str = None, cirq: str = None) -> None:
+    """circuit.py:505-520: the reference takes the file names from absl flags (--libq, --qasm, --cirq);
+    here they are arguments."""
+    for path, text in ((libq, self.libq), (qasm, self.qasm), (cirq, self.cirq)):
+      if path:
+        with open(path, "w") as f:
+          print(text(), file=f)
 
   def dump(self, *, desc=None, draw=False, pstate=True) -> None:
     if desc:

@@ -22,6 +22,8 @@ Everything written here is small (n <= 12 qubits) and committed; tests never nee
                      the oracle-safe gate subset, read from the qureg struct.
   libq_*_test.out    stdout of the reference's three libq test mains.
   qft6_libq.cc       dumpers.libq() text for the 6-qubit QFT (configs[0]).
+  *.qasm, *_cirq.py.txt  SURVEY 8(f)4: dumpers.qasm() / dumpers.cirq() text for the 6-qubit QFT and a
+                     two-register circuit with every gate name the cirq emitter knows.
   order_N15_a4.npz   SURVEY 8(f)1: the gate stream the reference's order_finding.py builds
                      for N=15, a=4 (18 qubits, 12 353 IR nodes), and what its xgates build
                      computes from it: the basis states with p > 0.01 that the script's
@@ -329,6 +331,30 @@ def libq_cases():
     f.write(f"{hashlib.sha256(chr(10).join(lines).encode()).hexdigest()} {len(lines)}\n")
 
 
+def emitter_cases():
+  """the reference's qasm / cirq text (dumpers.py:20-37, 89-161) for the 6-qubit QFT and
+  for a two-register circuit using every gate name its cirq emitter knows."""
+  from src.lib import dumpers
+  qc = circuit.qc("qft6", eager=False)
+  r = qc.reg(6, 0b101101)
+  qc.qft(r)
+  with open(os.path.join(HERE, "qft6.qasm"), "w") as f:
+    f.write(dumpers.qasm(qc.ir))
+  # (dumpers.cirq cannot print cu1 / cv: it reads op.idx0 of a controlled node, which ir.py asserts
+  # against -- so the cirq golden is limited to the names that work: h x y z cx cz u1)
+  qc = circuit.qc("mixed", eager=False)
+  a = qc.reg(3, 0b101, name="a")
+  b = qc.reg(2, 0, name="b")
+  qc.h(a[0]); qc.x(a[1]); qc.y(a[2]); qc.z(b[0])
+  qc.cx(a[0], b[1]); qc.cz(a[2], b[0]); qc.u1(b[1], math.pi / 8)
+  with open(os.path.join(HERE, "mixed_cirq.py.txt"), "w") as f:
+    f.write(dumpers.cirq(qc.ir))
+  qc.cu1(a[1], b[0], -math.pi / 4); qc.cv(a[0], a[2]); qc.cu1(b[1], a[0], 0.3)
+  with open(os.path.join(HERE, "mixed.qasm"), "w") as f:
+    f.write(dumpers.qasm(qc.ir))
+  print("wrote qft6.qasm mixed.qasm mixed_cirq.py.txt")
+
+
 def order_finding_case(number=15, a=4):
   """order_finding.py:152-183 recorded as IR through the reference's own functions, then run with
   its xgates build.  Only the readout is stored (see the module docstring)."""
@@ -366,8 +392,12 @@ if __name__ == "__main__":
   if len(sys.argv) > 1 and sys.argv[1] == "order":
     order_finding_case()
     sys.exit(0)
+  if len(sys.argv) > 1 and sys.argv[1] == "emitters":
+    emitter_cases()
+    sys.exit(0)
   dense_cases()
   acceleration_case()
   circuit_cases()
   libq_cases()
   order_finding_case()
+  emitter_cases()

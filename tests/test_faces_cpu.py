@@ -170,3 +170,46 @@ def test_order_finding_stream_matches_the_reference():
   assert np.array_equal(np.nonzero(p > 0.01)[0], z["labels"])
   assert np.abs(p[z["labels"]] - z["probs"]).max() < 1e-10
   assert np.abs(psi[z["sample_idx"]] - z["sample_amp"]).max() < 1e-10
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+  """bench.py --impl reference (the reference's own xgates build timed on the host, no GPU): one JSON
+  line with the keys the driver reads.  Small register here; the default is the 30-qubit workload."""
+  import json
+  import sys
+  from helpers import oracle
+  if not oracle.have_ref("libxgates.so"):
+    pytest.skip("oracle/_ref/libxgates.so not built (make -C oracle ref needs /root/reference)")
+  out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--qubits", "14",
+                        "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=300, check=True).stdout
+  d = json.loads(out.strip().splitlines()[-1])
+  assert d["impl"] == "reference" and d["metric"] == "gate-applies/sec" and d["unit"] == "gates/s"
+  assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 2 and d["warmup"] == 1
+  assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] == 1
+  assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
+  assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+  assert d["config"]["workload"] == "qft30" and d["dtype"] == "f64"
+
+
+def test_qasm_and_cirq_text_match_the_reference():
+  """byte-identical OPENQASM text (dumpers.py:20-37) for the QFT-6 circuit and a
+  two-register circuit, byte-identical Cirq text (dumpers.py:89-161) for the gate names the reference's
+  cirq emitter can actually print (h x y z cx cz u1 -- on cu1 / cv it trips over its own ir.py assert)."""
+  import math
+  qc = circuit.qc("qft6", eager=False)
+  r = qc.reg(6, 0b101101)
+  qc.qft(r)
+  assert qc.qasm() == open(os.path.join(GOLDEN, "qft6.qasm")).read()
+  qc = circuit.qc("mixed", eager=False)
+  a = qc.reg(3, 0b101, name="a")
+  b = qc.reg(2, 0, name="b")
+  qc.h(a[0]); qc.x(a[1]); qc.y(a[2]); qc.z(b[0])
+  qc.cx(a[0], b[1]); qc.cz(a[2], b[0]); qc.u1(b[1], math.pi / 8)
+  assert qc.cirq() == open(os.path.join(GOLDEN, "mixed_cirq.py.txt")).read()
+  qc.cu1(a[1], b[0], -math.pi / 4); qc.cv(a[0], a[2]); qc.cu1(b[1], a[0], 0.3)
+  assert qc.qasm() == open(os.path.join(GOLDEN, "mixed.qasm")).read()
+  # the controlled-matrix forms, which only our emitter can print: control index first
+  text = qc.cirq()
+  assert "qc.append(cirq.MatrixGate(m).controlled()(r[1], r[3]))" in text
+  assert "m = np.array([(1+1j, 1-1j), (1-1j, 1+1j)]) * 0.5\nqc.append(cirq.MatrixGate(m).controlled()(r[0], r[2]))" in text
+  assert "cmath.exp(1j * -pi/4)" in text and text.endswith("print(res_str.encode('utf-8'))\n")
