@@ -83,6 +83,10 @@ struct qb_state {
   size_t xbuf_bytes = 0;
   cudaStream_t xstream = nullptr; // copy-back of received pieces overlaps the next piece's transfer
   std::vector<cudaEvent_t> xevents;
+  // peer-memory exchange (QCC_B200_PEER_SWAP=1): CUDA IPC mappings of the other ranks' state vectors
+  int peer_state = 0;              // 0 not tried, 1 mapped on every rank, -1 unavailable (NCCL path)
+  std::vector<double2 *> peer_psi; // [rank] -> mapping (nullptr for ourselves)
+  double *d_sync = nullptr;        // scratch of the stream-ordered cross-rank barrier
   cudaStream_t stream = nullptr;
   double2 *psi = nullptr;
   bool fusion = true;
@@ -253,12 +257,82 @@ int run_local(qb_state *s, const std::vector<QbGate> &q) {
 // of its shard whose victim bit differs from its own rank bit with rank ^ (1 << rank_bit).
 // The half is 2^(n-1-victim) contiguous runs of 2^victim amplitudes; they are received into
 // xbuf (NCCL must not write into memory it is still sending from) and copied back in place.
+// Map every other rank's state vector into this process (CUDA IPC over NVLink peer access).  Collective:
+// all ranks call it at the same point; the outcome is agreed on (min over ranks), so either every rank
+// uses the peer path or none does.  Opt-in until measured on hardware: QCC_B200_PEER_SWAP=1.
+int ensure_peer_maps(qb_state *s, const qb::NcclApi *nc) {
+  if (s->peer_state != 0) return QB_OK;
+  s->peer_state = -1;
+  const char *env = getenv("QCC_B200_PEER_SWAP");
+  if (!env || atoi(env) == 0) return QB_OK;
+  s->peer_psi.assign(size_t(s->nranks), nullptr);
+  std::vector<cudaIpcMemHandle_t> handles(static_cast<size_t>(s->nranks));
+  unsigned char *dh = nullptr;
+  CU(cudaMalloc(&dh, sizeof(cudaIpcMemHandle_t) * size_t(s->nranks)));
+  if (!s->d_sync) CU(cudaMalloc(&s->d_sync, sizeof(double)));
+  double ok = 1.0;
+  cudaIpcMemHandle_t mine;
+  if (cudaIpcGetMemHandle(&mine, s->psi) != cudaSuccess) {
+    cudaGetLastError();
+    memset(&mine, 0, sizeof mine);
+    ok = 0.0;
+  }
+  CU(cudaMemcpyAsync(dh + sizeof mine * size_t(s->rank), &mine, sizeof mine, cudaMemcpyHostToDevice, s->stream));
+  NC(nc, nc->AllGather(dh + sizeof mine * size_t(s->rank), dh, sizeof mine, ncclUint8, s->comm, s->stream));
+  CU(cudaMemcpyAsync(handles.data(), dh, sizeof mine * size_t(s->nranks), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  cudaFree(dh);
+  for (int r = 0; r < s->nranks && ok != 0.0; ++r) {
+    if (r == s->rank) continue;
+    void *ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, handles[size_t(r)], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0.0;
+      break;
+    }
+    s->peer_psi[size_t(r)] = static_cast<double2 *>(ptr);
+  }
+  // agree: the peer path only if every rank mapped every other rank
+  CU(cudaMemcpyAsync(s->d_sync, &ok, sizeof ok, cudaMemcpyHostToDevice, s->stream));
+  NC(nc, nc->AllReduce(s->d_sync, s->d_sync, 1, ncclDouble, ncclMin, s->comm, s->stream));
+  CU(cudaMemcpyAsync(&ok, s->d_sync, sizeof ok, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  if (ok != 0.0) {
+    s->peer_state = 1;
+  } else {
+    for (auto &p : s->peer_psi)
+      if (p) {
+        cudaIpcCloseMemHandle(p);
+        p = nullptr;
+      }
+    if (s->rank == 0) fprintf(stderr, "qcc_b200: QCC_B200_PEER_SWAP: peer mapping unavailable, using NCCL send/recv\n");
+  }
+  return QB_OK;
+}
+
 int do_exchange(qb_state *s, int rank_bit, int victim) {
   std::string why;
   const qb::NcclApi *nc = qb::nccl_api(&why);
   if (!nc || !s->comm) return fail(QB_ERR_COMM, "exchange without a communicator: %s", why.c_str());
   const int b = (s->rank >> rank_bit) & 1;
   const int partner = s->rank ^ (1 << rank_bit);
+  QB(ensure_peer_maps(s, nc));
+  if (s->peer_state == 1) {
+    // ONE kernel swaps our outgoing half with the partner's in place, through the peer mapping: no
+    // receive buffer, no copy-back, both NVLink directions busy (we read and write the partner's shard
+    // for one half of the elements, it reads and writes ours for the other half).  The two stream-ordered
+    // all-reduces fence it: nobody touches a shard its owner is still computing on, and nobody computes
+    // on a shard its partner is still swapping into.
+    const size_t half_bytes_p = size_t(s->len / 2) * sizeof(double2);
+    ProfScope ps(s, QB_KCLASS_EXCHANGE, double(half_bytes_p));
+    NC(nc, nc->AllReduce(s->d_sync, s->d_sync, 1, ncclDouble, ncclMin, s->comm, s->stream));
+    CU(qb::launch_pair_swap(s->psi, s->peer_psi[size_t(partner)], s->n, victim, b ? 0 : 1, b, s->stream));
+    NC(nc, nc->AllReduce(s->d_sync, s->d_sync, 1, ncclDouble, ncclMin, s->comm, s->stream));
+    s->cnt.exchanges += 1;
+    s->cnt.bytes_exchanged += half_bytes_p;
+    s->cnt.kernel_launches += 1;
+    return QB_OK;
+  }
   const uint64_t run = uint64_t(1) << victim;
   const uint64_t nruns = uint64_t(1) << (s->n - 1 - victim);
   const uint64_t sel = b ? 0 : 1;  // we give away the half whose victim bit is NOT our rank bit
@@ -551,6 +625,9 @@ int qb_state_destroy(qb_state *s) {
     if (nc) nc->CommDestroy(s->comm);
   }
   if (s->xbuf) cudaFree(s->xbuf);
+  for (auto p : s->peer_psi)
+    if (p) cudaIpcCloseMemHandle(p);
+  if (s->d_sync) cudaFree(s->d_sync);
   for (auto e : s->xevents) cudaEventDestroy(e);
   if (s->xstream) cudaStreamDestroy(s->xstream);
   if (s->psi) cudaFree(s->psi);

@@ -20,6 +20,8 @@
 // Grids are sized from the pair count; at 30 qubits that is 2^19 CTAs of 256
 // threads, i.e. thousands of waves over the 148 SMs, so no tail effect.
 #include <cuda_runtime.h>
+
+#include <algorithm>
 #include <stdint.h>
 
 #include "kernels.h"
@@ -331,6 +333,58 @@ cudaError_t launch_list_above(const double2 *psi, uint64_t n, double thr, uint64
   cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
   if (e != cudaSuccess) return e;
   k_list_above<<<stride_blocks(n), kThreads, 0, st>>>(psi, n, thr, cap, counter, labels, amps);
+  return cudaGetLastError();
+}
+
+// ---- pair exchange over peer memory --------------------------------------------------------------
+// Flattened element number k = h * 2^victim + w addresses the k-th amplitude of a half shard: local index
+// (h << (victim + 1)) | (sel << victim) | w.  The kernel swaps local[(h, sel, w)] with peer[(h, 1 - sel, w)]
+// for k in this rank's half of [0, 2^(nbits-1)).  Two elements per thread per iteration, both loads of
+// both sides issued before any store: the remote side is an NVLink round trip away.
+namespace {
+__global__ void __launch_bounds__(256) k_pair_swap(double2 *__restrict__ local, double2 *__restrict__ peer, int victim,
+                                                   uint64_t sel_local, uint64_t k_begin, uint64_t k_end) {
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  const uint64_t lowmask = (uint64_t(1) << victim) - 1;
+  uint64_t k = k_begin + uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; k + stride < k_end; k += 2 * stride) {
+    const uint64_t k2 = k + stride;
+    const uint64_t i0 = ((k >> victim) << (victim + 1)) | (k & lowmask);
+    const uint64_t i1 = ((k2 >> victim) << (victim + 1)) | (k2 & lowmask);
+    const uint64_t l0 = i0 | (sel_local << victim), r0 = i0 | ((sel_local ^ 1) << victim);
+    const uint64_t l1 = i1 | (sel_local << victim), r1 = i1 | ((sel_local ^ 1) << victim);
+    const double2 a0 = local[l0], b0 = peer[r0], a1 = local[l1], b1 = peer[r1];
+    local[l0] = b0;
+    peer[r0] = a0;
+    local[l1] = b1;
+    peer[r1] = a1;
+  }
+  if (k < k_end) {
+    const uint64_t i0 = ((k >> victim) << (victim + 1)) | (k & lowmask);
+    const uint64_t l0 = i0 | (sel_local << victim), r0 = i0 | ((sel_local ^ 1) << victim);
+    const double2 a0 = local[l0], b0 = peer[r0];
+    local[l0] = b0;
+    peer[r0] = a0;
+  }
+}
+}  // namespace
+
+cudaError_t launch_pair_swap(double2 *local, double2 *peer, int nbits, int victim, int sel_local, int upper,
+                             cudaStream_t st) {
+  if (nbits < 1 || victim < 0 || victim >= nbits) return cudaErrorInvalidValue;
+  const uint64_t half = uint64_t(1) << (nbits - 1);     // elements in a half shard
+  const uint64_t k_begin = upper ? half / 2 : 0, k_end = upper ? half : half / 2;
+  if (k_end == k_begin) {                                // a 1-amplitude half: the lower rank swaps it
+    if (upper) return cudaSuccess;
+    k_pair_swap<<<1, 256, 0, st>>>(local, peer, victim, uint64_t(sel_local), 0, half);
+    return cudaGetLastError();
+  }
+  int sms = 148;
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const uint64_t want = (k_end - k_begin + 511) / 512;
+  const unsigned blocks = unsigned(std::min<uint64_t>(want, uint64_t(sms) * 8));
+  k_pair_swap<<<blocks, 256, 0, st>>>(local, peer, victim, uint64_t(sel_local), k_begin, k_end);
   return cudaGetLastError();
 }
 

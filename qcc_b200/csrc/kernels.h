@@ -32,6 +32,13 @@ cudaError_t launch_argmax(const double2 *psi, uint64_t n, double *blk_prob, uint
 cudaError_t launch_list_above(const double2 *psi, uint64_t n, double thr, uint64_t cap,
                               unsigned long long *counter, uint64_t *labels, double2 *amps,
                               cudaStream_t st);
+// Pair exchange through peer memory (engine.cu do_exchange, QCC_B200_PEER_SWAP): swaps this rank's outgoing
+// half -- the amplitudes whose bit `victim` equals `sel_local` -- element by element with the partner's
+// outgoing half (bit `victim` == 1 - sel_local) in the partner's shard, reached through `peer` (a CUDA IPC
+// mapping of its state vector).  Each rank of the pair handles one half of the element range (`upper`),
+// so every element pair is swapped exactly once and nothing is staged.
+cudaError_t launch_pair_swap(double2 *local, double2 *peer, int nbits, int victim, int sel_local, int upper,
+                             cudaStream_t st);
 cudaError_t launch_cvt_f2d(const float2 *in, double2 *out, uint64_t n, cudaStream_t st);
 
 // ---- fused tile-resident pass (fused.cu) ---------------------------------------

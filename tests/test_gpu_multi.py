@@ -108,10 +108,15 @@ def _worker(rank, world, port, n, out_dir):
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_state_matches_oracle(world, tmp_path):
+@pytest.mark.parametrize("exchange", ["nccl", "peer"])
+def test_sharded_state_matches_oracle(world, exchange, tmp_path, monkeypatch):
+  """exchange = "peer": QCC_B200_PEER_SWAP=1 -- the pair exchange as ONE kernel swapping the two half
+  shards in place through CUDA IPC peer mappings (falls back to NCCL send/recv, on every rank alike,
+  where the mapping is unavailable)."""
   if _ngpus() < world:
     pytest.skip(f"needs {world} GPUs")
   import torch.multiprocessing as mp
+  monkeypatch.setenv("QCC_B200_PEER_SWAP", "1" if exchange == "peer" else "0")   # inherited by the workers
   n = 18
   mp.spawn(_worker, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
   for name in ("qft", "random", "larose"):
