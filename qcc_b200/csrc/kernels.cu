@@ -374,7 +374,7 @@ cudaError_t launch_pair_swap(double2 *local, double2 *peer, int nbits, int victi
   if (nbits < 1 || victim < 0 || victim >= nbits) return cudaErrorInvalidValue;
   const uint64_t half = uint64_t(1) << (nbits - 1);     // elements in a half shard
   const uint64_t k_begin = upper ? half / 2 : 0, k_end = upper ? half : half / 2;
-  if (k_end == k_begin) {                                // a 1-amplitude half: the lower rank swaps it
+  if (half == 1) {                                       // a 1-amplitude half: the lower rank swaps it
     if (upper) return cudaSuccess;
     k_pair_swap<<<1, 256, 0, st>>>(local, peer, victim, uint64_t(sel_local), 0, half);
     return cudaGetLastError();
