@@ -78,6 +78,7 @@ struct qb_state {
   // sharding (shard.h): rank bits are the top physical index bits
   int rank = 0, nranks = 1, p = 0;
   std::vector<int> perm;          // logical index bit -> physical index bit
+  uint32_t flip = 0;              // relabelled rank bits (shard.h): rank bit k carries the negated qubit
   ncclComm_t comm = nullptr;
   double2 *xbuf = nullptr;        // half-shard receive buffer for exchanges
   size_t xbuf_bytes = 0;
@@ -404,9 +405,11 @@ int flush(qb_state *s) {
   L.p = s->p;
   L.rank = s->rank;
   L.perm = s->perm;
+  L.flip = s->flip;
   std::vector<qb::ShardStep> steps;
   qb::lower_for_rank(&L, q.data(), int64_t(q.size()), &steps);
   s->perm = L.perm;
+  s->flip = L.flip;
   return run_steps(s, steps);
 }
 
@@ -415,12 +418,12 @@ void locate(const qb_state *s, uint64_t logical, int *rank, uint64_t *local) {
   uint64_t phys = 0;
   for (int b = 0; b < s->nq; ++b)
     if (logical >> b & 1) phys |= uint64_t(1) << s->perm[size_t(b)];
-  *rank = int(phys >> s->n);
+  *rank = int((phys >> s->n) ^ s->flip);   // a relabelled rank bit holds the negated qubit
   *local = phys & (s->len - 1);
 }
 
 uint64_t logical_of(const qb_state *s, int rank, uint64_t local) {
-  const uint64_t phys = (uint64_t(rank) << s->n) | local;
+  const uint64_t phys = (uint64_t(uint32_t(rank) ^ s->flip) << s->n) | local;
   uint64_t logical = 0;
   for (int b = 0; b < s->nq; ++b)
     if (phys >> s->perm[size_t(b)] & 1) logical |= uint64_t(1) << b;
@@ -657,6 +660,7 @@ int qb_set_basis(qb_state *s, uint64_t label) {
   CU(cudaSetDevice(s->device));
   s->queue.clear();
   for (int b = 0; b < s->nq; ++b) s->perm[size_t(b)] = b;
+  s->flip = 0;
   CU(cudaMemsetAsync(s->psi, 0, size_t(s->len) * sizeof(double2), s->stream));
   const double2 one = make_double2(1.0, 0.0);
   if (int(label >> s->n) == s->rank)
@@ -671,6 +675,7 @@ int qb_fill_random(qb_state *s, uint64_t seed) {
   CU(cudaSetDevice(s->device));
   s->queue.clear();
   for (int b = 0; b < s->nq; ++b) s->perm[size_t(b)] = b;
+  s->flip = 0;
   CU(qb::launch_fill_random(s->psi, s->len, uint64_t(s->rank) << s->n, seed, s->stream));
   double n2 = 0.0;
   CU(qb::launch_norm2(s->psi, s->len, s->d_scalar, s->stream));
@@ -817,7 +822,7 @@ int qb_prob_bit(qb_state *s, int bit, double *p_one) {
     const int pb = s->perm[size_t(bit)];
     if (pb < s->n) {
       CU(qb::launch_prob_mask(s->psi, s->len, uint64_t(1) << pb, s->d_scalar, s->stream));
-    } else if ((s->rank >> (pb - s->n)) & 1) {
+    } else if (((uint32_t(s->rank) ^ s->flip) >> (pb - s->n)) & 1u) {
       CU(qb::launch_norm2(s->psi, s->len, s->d_scalar, s->stream));  // the bit is 1 on this whole shard
     } else {
       CU(cudaMemsetAsync(s->d_scalar, 0, sizeof(double), s->stream));
@@ -1104,9 +1109,11 @@ int qb_canonicalize(qb_state *s) {
   L.p = s->p;
   L.rank = s->rank;
   L.perm = s->perm;
+  L.flip = s->flip;
   std::vector<qb::ShardStep> steps;
   qb::canonicalize_steps(&L, &steps);
   s->perm = L.perm;
+  s->flip = L.flip;
   const uint64_t before = s->cnt.gates_applied;
   int rc = run_steps(s, steps);
   s->cnt.gates_applied = before;  // layout moves are not gates of the caller's circuit

@@ -2,6 +2,7 @@
 #include "shard.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -37,6 +38,31 @@ void push_exchange(ShardLayout *L, int global_pos, int victim, std::vector<Shard
 
 bool nondiagonal(int kind) { return kind == QB_K_U || kind == QB_K_PERM || kind == QB_K_SWAP; }
 
+bool is_plain_x(const QbGate &g) {
+  return g.ctl_mask == 0 && (g.kind == QB_K_PERM || g.kind == QB_K_SWAP) && g.m[2] == 1.0 && g.m[3] == 0.0 &&
+         g.m[4] == 1.0 && g.m[5] == 0.0;
+}
+
+// value of the LOGICAL qubit that lives at global physical position pb, on this rank
+int global_bit(const ShardLayout &L, int pb) { return int(((uint32_t(L.rank) ^ L.flip) >> (pb - L.nl)) & 1u); }
+
+// exchange global position <-> local victim; a relabelled (flipped) rank bit arrives in the victim bit
+// as the negation of its qubit: one local x puts it right, and the new occupant of the rank bit is plain
+void exchange_bits(ShardLayout *L, int global_pos, int victim, ShardStep *cur, std::vector<ShardStep> *steps) {
+  close_step(cur, steps);
+  push_exchange(L, global_pos, victim, steps);
+  const uint32_t fb = 1u << (global_pos - L->nl);
+  if (L->flip & fb) {
+    L->flip &= ~fb;
+    QbGate x{};
+    x.ctl_mask = 0;
+    x.target = victim;
+    x.kind = QB_K_PERM;
+    memcpy(x.m, kX, sizeof kX);
+    cur->gates.push_back(x);
+  }
+}
+
 // Belady: among the top local bits, evict the qubit whose next use as a mixing target is farthest.
 int choose_victim(const ShardLayout &L, const QbGate *gates, int64_t ngates, int64_t from) {
   std::vector<int> inv = inverse_of(L.perm);
@@ -70,9 +96,14 @@ void lower_for_rank(ShardLayout *L, const QbGate *gates, int64_t ngates, std::ve
       continue;
     }
     if (nondiagonal(g.kind) && L->perm[size_t(g.target)] >= nl) {
+      static const bool no_relabel = getenv("QCC_B200_NO_RELABEL") != nullptr;
+      if (is_plain_x(g) && !no_relabel) {   // x on a sharded qubit: relabel the rank bit, move nothing
+        L->flip ^= 1u << (L->perm[size_t(g.target)] - nl);
+        cur.retired += 1;
+        continue;
+      }
       const int victim = choose_victim(*L, gates, ngates, i);
-      close_step(&cur, steps);
-      push_exchange(L, L->perm[size_t(g.target)], victim, steps);
+      exchange_bits(L, L->perm[size_t(g.target)], victim, &cur, steps);
     }
     const int pt = L->perm[size_t(g.target)];
     uint64_t lm = 0;
@@ -81,7 +112,7 @@ void lower_for_rank(ShardLayout *L, const QbGate *gates, int64_t ngates, std::ve
       if (!(g.ctl_mask >> b & 1)) continue;
       const int pb = L->perm[size_t(b)];
       if (pb < nl) lm |= uint64_t(1) << pb;
-      else if (!((L->rank >> (pb - nl)) & 1)) active = false;
+      else if (!global_bit(*L, pb)) active = false;
     }
     cur.retired += 1;
     if (!active) continue;  // a global control bit is 0 on this rank: the gate touches nothing here
@@ -94,7 +125,7 @@ void lower_for_rank(ShardLayout *L, const QbGate *gates, int64_t ngates, std::ve
       continue;
     }
     // diagonal gate whose target bit is a rank bit: a phase on the remaining local bits
-    const int tb = (L->rank >> (pt - nl)) & 1;
+    const int tb = global_bit(*L, pt);
     double pr, pi;
     if (g.kind == QB_K_PHASE) {
       if (!tb) continue;
@@ -140,20 +171,22 @@ void canonicalize_steps(ShardLayout *L, std::vector<ShardStep> *steps) {
     L->perm[size_t(la)] = b;
     L->perm[size_t(lb)] = a;
   };
+  // relabelled rank bits first: bring each one local (the exchange un-flips it with a local x); the loop
+  // below then puts every qubit back where it belongs
+  for (int G = nl; G < n; ++G)
+    if (L->flip >> (G - nl) & 1u) exchange_bits(L, G, nl - 1, &cur, steps);
   for (int G = nl; G < n; ++G) {
     if (L->perm[size_t(G)] == G) continue;
     int where = L->perm[size_t(G)];  // physical position of logical bit G
     if (where >= nl) {               // sitting in another rank bit: bring it local first
-      close_step(&cur, steps);
-      push_exchange(L, where, nl - 1, steps);
+      exchange_bits(L, where, nl - 1, &cur, steps);
       where = nl - 1;
     }
     if (where < nl - kVictimWindow) {  // keep the exchanged half shard in few contiguous runs
       local_swap(where, nl - 1);
       where = nl - 1;
     }
-    close_step(&cur, steps);
-    push_exchange(L, G, where, steps);
+    exchange_bits(L, G, where, &cur, steps);
   }
   for (int q = 0; q < nl; ++q)
     while (L->perm[size_t(q)] != q) local_swap(q, L->perm[size_t(q)]);
@@ -165,7 +198,7 @@ std::string steps_to_json(const ShardLayout &L, const std::vector<ShardStep> &st
                   std::to_string(L.rank) + ",\"perm\":[";
   char buf[256];
   for (size_t b = 0; b < L.perm.size(); ++b) s += (b ? "," : "") + std::to_string(L.perm[b]);
-  s += "],\"steps\":[";
+  s += "],\"flip\":" + std::to_string(L.flip) + ",\"steps\":[";
   for (size_t k = 0; k < steps.size(); ++k) {
     const ShardStep &st = steps[k];
     if (k) s += ",";

@@ -48,7 +48,33 @@ def _circuits(n):
     larose += [(0, n - 1 - bit, H), (0, n - 1 - bit, V)]
     if bit:
       larose.append((1 << (n - 1 - bit), n - 1, X))
-  return {"qft": qft, "random": rnd, "larose": larose}
+  # grover.py-style x layers on qubits that serve as controls in between (they stay sharded: the x is a
+  # rank relabel, no exchange), plus h on them now and then (exchange; the flip is undone by a local x)
+  xh = []
+  rng = np.random.default_rng(23)
+  top = [n - 1, n - 2, n - 3]
+  for rep in range(6):
+    for q in top:
+      if rng.random() < 0.7:
+        xh.append((0, q, X))
+    for _ in range(6):
+      t = int(rng.integers(0, n - 3))
+      ctl = 0
+      for q in top:
+        if rng.random() < 0.6:
+          ctl |= 1 << q
+      xh.append((ctl, t, oracle.GATES[names[rng.integers(len(names))]]))
+      xh.append((1 << top[int(rng.integers(3))], t, oracle.u1(float(rng.uniform(-3, 3)))))
+      xh.append((0, top[int(rng.integers(3))], oracle.u1(float(rng.uniform(-3, 3)))))   # diagonal on a sharded qubit
+    if rep % 2:
+      xh.append((0, top[rep % 3], H))
+    xh.append((1 << 0, top[(rep + 1) % 3], X))   # cx ONTO a sharded qubit: a real exchange
+  for q in range(n):                             # whatever ends up sharded is left relabelled ...
+    xh.append((0, q, X))
+  for q in range(n):                             # ... and read through the flip by these
+    xh.append((1 << q, (q + 1) % n, oracle.u1(0.1 * (q + 1))))
+    xh.append((0, q, oracle.GATES["t"]))
+  return {"qft": qft, "random": rnd, "larose": larose, "xlayers": xh}
 
 
 def _worker(rank, world, port, n, out_dir):
@@ -97,17 +123,19 @@ def _worker(rank, world, port, n, out_dir):
         if rank == 0:
           phys = np.concatenate([x.numpy().view(np.complex128) for x in parts])
           perm = plan["perm"]
+          flip = plan["flip"]            # relabelled rank bits carry the negated qubit
           if canon:
-            assert perm == list(range(n))
+            assert perm == list(range(n)) and flip == 0
           idx = np.arange(1 << n)
           pidx = np.zeros_like(idx)
           for bl in range(n):
-            pidx |= ((idx >> bl) & 1) << perm[bl]
+            f = (flip >> (perm[bl] - nl)) & 1 if perm[bl] >= nl else 0
+            pidx |= (((idx >> bl) & 1) ^ f) << perm[bl]
           got = phys[pidx]
           want = run_bits(psi0.copy(), n, gates)
           err = float(np.abs(got - want).max())
           with open(os.path.join(out_dir, f"{name}_{int(canon)}.txt"), "w") as f:
-            f.write(f"{err} {sum(1 for s in plan['steps'] if s['kind'] == 1)}")
+            f.write(f"{err} {sum(1 for s in plan['steps'] if s['kind'] == 1)} {flip}")
     dist.barrier()
   finally:
     dist.destroy_process_group()
@@ -118,10 +146,13 @@ def test_sharded_lowering_over_gloo(world, n, tmp_path):
   import torch.multiprocessing as mp
   port = _free_port()
   mp.spawn(_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
-  for name in ("qft", "random", "larose"):
+  flips_seen = 0
+  for name in ("qft", "random", "larose", "xlayers"):
     for canon in (1, 0):
-      err, nex = open(tmp_path / f"{name}_{canon}.txt").read().split()
+      err, nex, flip = open(tmp_path / f"{name}_{canon}.txt").read().split()
       assert float(err) <= 1e-12, (name, canon, err)
+      flips_seen += int(flip) != 0
+  assert flips_seen > 0   # the x layers leave relabelled rank bits behind (uncanonicalised run)
   # QFT touches each sharded bit as a non-diagonal target exactly once: one exchange per global bit
   assert int(open(tmp_path / "qft_0.txt").read().split()[1]) == int(math.log2(world))
 
@@ -133,4 +164,4 @@ def test_lowering_is_identical_in_structure_on_every_rank():
   plans = [json.loads(_cabi.shard_lower_json(n, world, r, gates, canonicalize=True)) for r in range(world)]
   shape = lambda p: [(s["kind"], s.get("rank_bit"), s.get("victim")) for s in p["steps"]]
   assert all(shape(p) == shape(plans[0]) for p in plans)
-  assert all(p["perm"] == plans[0]["perm"] for p in plans)
+  assert all(p["perm"] == plans[0]["perm"] and p["flip"] == plans[0]["flip"] for p in plans)
