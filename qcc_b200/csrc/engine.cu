@@ -79,6 +79,7 @@ struct qb_state {
   int rank = 0, nranks = 1, p = 0;
   std::vector<int> perm;          // logical index bit -> physical index bit
   uint32_t flip = 0;              // relabelled rank bits (shard.h): rank bit k carries the negated qubit
+  int victim_window = qb::kVictimWindow;  // wider when exchanges go through the peer-swap kernel
   ncclComm_t comm = nullptr;
   double2 *xbuf = nullptr;        // half-shard receive buffer for exchanges
   size_t xbuf_bytes = 0;
@@ -406,6 +407,7 @@ int flush(qb_state *s) {
   L.rank = s->rank;
   L.perm = s->perm;
   L.flip = s->flip;
+  L.window = s->victim_window;
   std::vector<qb::ShardStep> steps;
   qb::lower_for_rank(&L, q.data(), int64_t(q.size()), &steps);
   s->perm = L.perm;
@@ -604,6 +606,16 @@ static int create_impl(int nqubits, uint64_t init_label, int device, int rank, i
       qb_state_destroy(s);
       return rc;
     }
+  }
+  if (nranks > 1) {
+    // QCC_B200_PEER_SWAP=1: map the peers now (collective), so that the lowering knows from the first
+    // gate on whether victims have to keep the exchanged half in few contiguous runs
+    int prc = ensure_peer_maps(s, qb::nccl_api(nullptr));
+    if (prc != QB_OK) {
+      qb_state_destroy(s);
+      return prc;
+    }
+    if (s->peer_state == 1) s->victim_window = std::max(qb::kVictimWindow, s->n - qb::kPeerSwapMinVictim);
   }
   int rc = qb_set_basis(s, init_label);
   if (rc != QB_OK) {
@@ -1110,6 +1122,7 @@ int qb_canonicalize(qb_state *s) {
   L.rank = s->rank;
   L.perm = s->perm;
   L.flip = s->flip;
+  L.window = s->victim_window;
   std::vector<qb::ShardStep> steps;
   qb::canonicalize_steps(&L, &steps);
   s->perm = L.perm;
@@ -1146,6 +1159,7 @@ int qb_shard_lower_json(int nqubits, int nranks, int rank, const qb_gate *gates,
   L.rank = rank;
   L.perm.resize(size_t(nqubits));
   for (int b = 0; b < nqubits; ++b) L.perm[size_t(b)] = b;
+  if (const char *w = getenv("QCC_B200_VICTIM_WINDOW")) L.window = std::max(1, atoi(w));  // tests: the peer-swap window
   std::vector<qb::ShardStep> steps;
   qb::lower_for_rank(&L, q.data(), ngates, &steps);
   if (canonicalize) qb::canonicalize_steps(&L, &steps);

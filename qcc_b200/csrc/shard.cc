@@ -68,7 +68,7 @@ int choose_victim(const ShardLayout &L, const QbGate *gates, int64_t ngates, int
   std::vector<int> inv = inverse_of(L.perm);
   int best = L.nl - 1;
   int64_t best_dist = -1;
-  for (int v = L.nl - 1; v >= std::max(0, L.nl - kVictimWindow); --v) {
+  for (int v = L.nl - 1; v >= std::max(0, L.nl - L.window); --v) {
     const int lv = inv[size_t(v)];
     int64_t dist = ngates + 1;
     for (int64_t j = from + 1; j < ngates; ++j)
@@ -182,7 +182,7 @@ void canonicalize_steps(ShardLayout *L, std::vector<ShardStep> *steps) {
       exchange_bits(L, where, nl - 1, &cur, steps);
       where = nl - 1;
     }
-    if (where < nl - kVictimWindow) {  // keep the exchanged half shard in few contiguous runs
+    if (where < nl - L->window) {  // keep the exchanged half shard in few contiguous runs
       local_swap(where, nl - 1);
       where = nl - 1;
     }

@@ -48,11 +48,16 @@ struct ShardLayout {
   int rank = 0;
   std::vector<int> perm;  // logical bit -> physical bit
   uint32_t flip = 0;      // bit k set: rank bit k carries the NEGATION of the logical qubit mapped to it
+  int window = 6;         // victims come from the top `window` local bits (kVictimWindow unless the exchange
+                          // does not care about contiguity: the peer-swap kernel, engine.cu)
 };
 
 // Victims are taken from the top `kVictimWindow` local bits so that the exchanged half
-// shard is made of at most 2^(kVictimWindow-1) contiguous runs.
+// shard is made of at most 2^(kVictimWindow-1) contiguous runs (one NCCL send / recv each).  The
+// peer-swap kernel only needs runs of a few hundred bytes: its window is everything above bit
+// kPeerSwapMinVictim.
 constexpr int kVictimWindow = 6;
+constexpr int kPeerSwapMinVictim = 5;
 
 // Lowers `gates` (LOGICAL index bits, kinds already classified) for layout->rank, updating
 // layout->perm as exchanges are scheduled.

@@ -141,9 +141,12 @@ def _worker(rank, world, port, n, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n", [(2, 9), (4, 10)])
-def test_sharded_lowering_over_gloo(world, n, tmp_path):
+@pytest.mark.parametrize("world,n,window", [(2, 9, None), (4, 10, None), (4, 10, 30)])
+def test_sharded_lowering_over_gloo(world, n, window, tmp_path, monkeypatch):
+  """window = 30: the victim window of the peer-swap exchange (any local bit), QCC_B200_VICTIM_WINDOW."""
   import torch.multiprocessing as mp
+  if window:
+    monkeypatch.setenv("QCC_B200_VICTIM_WINDOW", str(window))
   port = _free_port()
   mp.spawn(_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
   flips_seen = 0
