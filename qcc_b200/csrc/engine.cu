@@ -408,6 +408,8 @@ int flush(qb_state *s) {
   L.perm = s->perm;
   L.flip = s->flip;
   L.window = s->victim_window;
+  L.hoist = s->peer_state == 1 ? 1 : 0;
+  L.pass_targets = std::max(1, s->tile_bits - QB_TILE_LOW);
   std::vector<qb::ShardStep> steps;
   qb::lower_for_rank(&L, q.data(), int64_t(q.size()), &steps);
   s->perm = L.perm;
@@ -1123,6 +1125,8 @@ int qb_canonicalize(qb_state *s) {
   L.perm = s->perm;
   L.flip = s->flip;
   L.window = s->victim_window;
+  L.hoist = s->peer_state == 1 ? 1 : 0;
+  L.pass_targets = std::max(1, s->tile_bits - QB_TILE_LOW);
   std::vector<qb::ShardStep> steps;
   qb::canonicalize_steps(&L, &steps);
   s->perm = L.perm;
@@ -1160,6 +1164,7 @@ int qb_shard_lower_json(int nqubits, int nranks, int rank, const qb_gate *gates,
   L.perm.resize(size_t(nqubits));
   for (int b = 0; b < nqubits; ++b) L.perm[size_t(b)] = b;
   if (const char *w = getenv("QCC_B200_VICTIM_WINDOW")) L.window = std::max(1, atoi(w));  // tests: the peer-swap window
+  if (const char *h = getenv("QCC_B200_HOIST")) L.hoist = atoi(h);                        // ... and its exchange hoisting
   std::vector<qb::ShardStep> steps;
   qb::lower_for_rank(&L, q.data(), ngates, &steps);
   if (canonicalize) qb::canonicalize_steps(&L, &steps);

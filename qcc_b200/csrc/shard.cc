@@ -63,11 +63,16 @@ void exchange_bits(ShardLayout *L, int global_pos, int victim, ShardStep *cur, s
   }
 }
 
+int64_t hoist_point(const ShardLayout &L, const QbGate *gates, int64_t seg_start, int64_t i, int victim);
+
 // Belady: among the top local bits, evict the qubit whose next use as a mixing target is farthest.
-int choose_victim(const ShardLayout &L, const QbGate *gates, int64_t ngates, int64_t from) {
+// With hoisting, among the equally far ones the victim that lets the exchange move back to a pass
+// boundary wins (a qubit whose own last mixing gate lies before that boundary), higher bits first.
+int choose_victim(const ShardLayout &L, const QbGate *gates, int64_t ngates, int64_t from, int64_t seg_start) {
   std::vector<int> inv = inverse_of(L.perm);
   int best = L.nl - 1;
   int64_t best_dist = -1;
+  bool best_hoists = false;
   for (int v = L.nl - 1; v >= std::max(0, L.nl - L.window); --v) {
     const int lv = inv[size_t(v)];
     int64_t dist = ngates + 1;
@@ -76,12 +81,49 @@ int choose_victim(const ShardLayout &L, const QbGate *gates, int64_t ngates, int
         dist = j - from;
         break;
       }
-    if (dist > best_dist) {
+    if (dist < best_dist) continue;
+    const bool hoists = L.hoist && hoist_point(L, gates, seg_start, from, v) < from;
+    if (dist > best_dist || (hoists && !best_hoists)) {
       best_dist = dist;
       best = v;
+      best_hoists = hoists;
     }
   }
   return best;
+}
+
+// Where to put the exchange that gate i needs: the latest pass boundary of the local stream in
+// [seg_start, i] from which on the victim's qubit is not a mixing target any more (it becomes sharded
+// at that point).  Pass boundaries are estimated the way the fusion planner cuts: a new pass when one
+// more distinct target bit above QB_TILE_LOW would not fit.  Depends on the stream, the permutation
+// and the victim only, so every rank finds the same point.
+int64_t hoist_point(const ShardLayout &L, const QbGate *gates, int64_t seg_start, int64_t i, int victim) {
+  std::vector<int> inv = inverse_of(L.perm);
+  const int lv = inv[size_t(victim)];
+  int64_t j0 = seg_start;
+  for (int64_t k = i - 1; k >= seg_start; --k)
+    if (nondiagonal(gates[k].kind) && gates[k].target == lv) {
+      j0 = k + 1;
+      break;
+    }
+  int64_t best = i;
+  bool found = false;
+  std::vector<int> targets;
+  for (int64_t k = seg_start; k < i; ++k) {
+    if (!nondiagonal(gates[k].kind)) continue;
+    const int pt = L.perm[size_t(gates[k].target)];
+    if (pt >= L.nl || pt < QB_TILE_LOW) continue;   // relabelled x on a sharded bit / always-resident low bits
+    if (std::find(targets.begin(), targets.end(), pt) != targets.end()) continue;
+    if (int(targets.size()) == L.pass_targets) {
+      targets.clear();
+      if (k >= j0) {
+        best = k;
+        found = true;
+      }
+    }
+    targets.push_back(pt);
+  }
+  return found ? best : i;
 }
 
 }  // namespace
@@ -89,8 +131,17 @@ int choose_victim(const ShardLayout &L, const QbGate *gates, int64_t ngates, int
 void lower_for_rank(ShardLayout *L, const QbGate *gates, int64_t ngates, std::vector<ShardStep> *steps) {
   ShardStep cur;
   const int nl = L->nl;
+  // state of the open step before each gate since seg_start (for rolling back to a hoisted exchange point)
+  struct Mark {
+    size_t ngates;
+    int64_t retired;
+    uint32_t flip;
+  };
+  std::vector<Mark> marks;
+  int64_t seg_start = 0;
   for (int64_t i = 0; i < ngates; ++i) {
     const QbGate &g = gates[i];
+    marks.push_back(Mark{cur.gates.size(), cur.retired, L->flip});
     if (g.kind == QB_K_NOP) {
       cur.retired += 1;
       continue;
@@ -102,8 +153,19 @@ void lower_for_rank(ShardLayout *L, const QbGate *gates, int64_t ngates, std::ve
         cur.retired += 1;
         continue;
       }
-      const int victim = choose_victim(*L, gates, ngates, i);
+      const int victim = choose_victim(*L, gates, ngates, i, seg_start);
+      const int64_t j = L->hoist ? hoist_point(*L, gates, seg_start, i, victim) : i;
+      if (j < i) {   // undo what the open step holds of gates j .. i-1; they are lowered again below
+        const Mark &mk = marks[size_t(j - seg_start)];
+        cur.gates.resize(mk.ngates);
+        cur.retired = mk.retired;
+        L->flip = mk.flip;
+      }
       exchange_bits(L, L->perm[size_t(g.target)], victim, &cur, steps);
+      seg_start = j;
+      marks.clear();
+      i = j - 1;     // resume at gate j under the new layout (gate i itself now finds its target local)
+      continue;
     }
     const int pt = L->perm[size_t(g.target)];
     uint64_t lm = 0;

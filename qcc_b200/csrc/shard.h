@@ -50,6 +50,13 @@ struct ShardLayout {
   uint32_t flip = 0;      // bit k set: rank bit k carries the NEGATION of the logical qubit mapped to it
   int window = 6;         // victims come from the top `window` local bits (kVictimWindow unless the exchange
                           // does not care about contiguity: the peer-swap kernel, engine.cu)
+  // hoist = 1: an exchange is moved back from the gate that needs it to the latest point where the fusion
+  // planner would start a new pass anyway (pass_targets new target bits per pass), as far as the victim
+  // allows -- the stream is then planned in whole passes on both sides of the exchange instead of ending
+  // one segment with a fragment.  Pays off with the wide victim window (the victim can be a qubit that
+  // is long done); off with NCCL's narrow one.
+  int hoist = 0;
+  int pass_targets = 9;
 };
 
 // Victims are taken from the top `kVictimWindow` local bits so that the exchanged half

@@ -141,12 +141,16 @@ def _worker(rank, world, port, n, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n,window", [(2, 9, None), (4, 10, None), (4, 10, 30)])
-def test_sharded_lowering_over_gloo(world, n, window, tmp_path, monkeypatch):
-  """window = 30: the victim window of the peer-swap exchange (any local bit), QCC_B200_VICTIM_WINDOW."""
+@pytest.mark.parametrize("world,n,window,hoist", [(2, 9, None, 0), (4, 10, None, 0), (4, 10, 30, 0), (4, 10, 30, 1),
+                                                  (2, 12, 30, 1)])
+def test_sharded_lowering_over_gloo(world, n, window, hoist, tmp_path, monkeypatch):
+  """window = 30: the victim window of the peer-swap exchange (any local bit), QCC_B200_VICTIM_WINDOW;
+  hoist = 1: exchanges moved back to pass boundaries (QCC_B200_HOIST), gates in between lowered again."""
   import torch.multiprocessing as mp
   if window:
     monkeypatch.setenv("QCC_B200_VICTIM_WINDOW", str(window))
+  if hoist:
+    monkeypatch.setenv("QCC_B200_HOIST", "1")
   port = _free_port()
   mp.spawn(_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
   flips_seen = 0
@@ -168,3 +172,31 @@ def test_lowering_is_identical_in_structure_on_every_rank():
   shape = lambda p: [(s["kind"], s.get("rank_bit"), s.get("victim")) for s in p["steps"]]
   assert all(shape(p) == shape(plans[0]) for p in plans)
   assert all(p["perm"] == plans[0]["perm"] and p["flip"] == plans[0]["flip"] for p in plans)
+
+
+def test_hoisted_exchange_keeps_sharded_qft_at_three_passes(monkeypatch):
+  """QFT-30 over 2 ranks (29 local bits), victim window of the peer-swap exchange + hoisting: the one
+  exchange sits on a pass boundary, so both segments plan into whole passes -- 3 in total, the
+  single-GPU count -- instead of 3 + a fragment."""
+  from qcc_b200 import _cabi
+  n, world = 30, 2
+  gates = _circuits(n)["qft"]
+
+  def passes(env):
+    for k, v in env.items():
+      monkeypatch.setenv(k, v)
+    plan = json.loads(_cabi.shard_lower_json(n, world, 1, gates, canonicalize=False))
+    for k in env:
+      monkeypatch.delenv(k)
+    total, nex = 0, 0
+    for st in plan["steps"]:
+      if st["kind"] == 1:
+        nex += 1
+        continue
+      g = [(x["ctl_mask"], x["target"], np.array([complex(x["m"][2 * i], x["m"][2 * i + 1]) for i in range(4)]))
+           for x in st["gates"]]
+      total += len(json.loads(_cabi.plan_json(n - 1, g, 12))["passes"])
+    return total, nex
+
+  assert passes({}) == (4, 1)
+  assert passes({"QCC_B200_VICTIM_WINDOW": "30", "QCC_B200_HOIST": "1"}) == (3, 1)
