@@ -637,13 +637,22 @@ int qb_state_destroy(qb_state *s) {
     cudaEventDestroy(r.e1);
   }
   for (auto e : s->event_pool) cudaEventDestroy(e);
+  // peer mappings: every rank unmaps the others' vectors BEFORE anybody frees its own (collective)
+  for (auto &p : s->peer_psi)
+    if (p) {
+      cudaIpcCloseMemHandle(p);
+      p = nullptr;
+    }
+  if (s->peer_state == 1 && s->comm && s->d_sync) {
+    const qb::NcclApi *nc = qb::nccl_api(nullptr);
+    if (nc && nc->AllReduce(s->d_sync, s->d_sync, 1, ncclDouble, ncclMin, s->comm, s->stream) == ncclSuccess)
+      cudaStreamSynchronize(s->stream);
+  }
   if (s->comm) {
     const qb::NcclApi *nc = qb::nccl_api(nullptr);
     if (nc) nc->CommDestroy(s->comm);
   }
   if (s->xbuf) cudaFree(s->xbuf);
-  for (auto p : s->peer_psi)
-    if (p) cudaIpcCloseMemHandle(p);
   if (s->d_sync) cudaFree(s->d_sync);
   for (auto e : s->xevents) cudaEventDestroy(e);
   if (s->xstream) cudaStreamDestroy(s->xstream);
