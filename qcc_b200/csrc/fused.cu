@@ -1,27 +1,29 @@
 // fused.cu -- tile-resident fused pass for sm_100a: many gates per HBM sweep.
 //
-// PERSISTENT kernel: one CTA of 512 threads per SM walks over TILES of 2^K amplitudes
-// (K <= 13, default 12 = 64 KiB; see qb_types.h) with a two-deep shared-memory ring: while
-// tile i is being computed on, tile i+1 is already streaming in through cp.async (LDGSTS,
-// 16 B per request, L2-only), so HBM latency is hidden behind the fp64 work instead of being
-// paid twice per tile.  (With one-shot CTAs the resident CTAs of an SM ran in lockstep --
-// all loading, then all computing -- and the phases simply added up: 9.4 + 3.7 + 6 ms.)
+// One CTA of 256 threads = one TILE of 2^K amplitudes (K <= 13, default 12 = 64 KiB; see qb_types.h).
+// Up to three CTAs are resident per SM (80 registers, 64 KiB tile + <= 9 KiB of ladder tables each), and
+// because they start and finish at different times one streams its tile while the others compute.
+// (A persistent CTA per SM with a ring of tile buffers -- k_fused_pipe below, kept as a measured
+// experiment -- loses: warps that move through the rounds in lockstep cover the fp64 and
+// shared-memory latencies worse than warps of different CTAs in different phases.)
 //
-//   0. STAGE  the pass's op and round descriptors (<= 48 x 128 B) are copied into shared
-//             memory once, so the per-op decode in the hot loop is LDS broadcasts, not
-//             dependent global loads.
-//   1. LOAD   the tile is gathered from HBM straight into (swizzled) shared memory with
-//             cp.async: thread t of 512 takes tile-local indices t, t+512, ...; 8
-//             consecutive lanes fetch one 128-byte run, and the planner pads the tile with
-//             the lowest free index bits so the runs of one tile are mostly adjacent (a
-//             tile whose bits are 0..K-1 is one contiguous 64 KiB block).  No registers are
-//             staged and nobody waits: the copy of the NEXT tile is issued before the
-//             rounds of the current one start.
-//   2. ROUNDS each thread owns one group of 8 amplitudes that differ only in the round's 3
-//             tile-local bits, pulls it into 16 fp64 registers, runs every op of the round
-//             on registers and writes it back: ONE shared-memory round trip for any number
-//             of gates on those 3 qubits, plus every diagonal gate queued in between.
-//   3. STORE  shared -> HBM with streaming 128-bit stores (fire and forget).
+//   1. LOAD   the tile is gathered from HBM straight into (swizzled) shared memory with cp.async
+//             (LDGSTS, 16 B per request, L2-only): 8 consecutive lanes fetch one 128-byte run, and the
+//             planner pads the tile with the lowest free index bits so the runs of one tile are mostly
+//             adjacent (a tile whose bits are 0..K-1 is one contiguous 64 KiB block).  With warp_io
+//             (K >= 12) every warp copies exactly the sub-cube it will work on and waits for its own
+//             copies only.  Meanwhile the ladder tables are staged and the per-tile ladder constants
+//             computed.
+//   2. ROUNDS each thread owns groups of 8 amplitudes that differ only in the round's 3 tile-local
+//             bits, pulls one into 16 fp64 registers, runs every op of the round on registers and
+//             writes it back: ONE shared-memory round trip for any number of gates on those 3 qubits,
+//             plus every diagonal gate queued in between.  Rounds of one run keep each warp inside its
+//             own sub-cube (warp sync only); a CTA barrier separates runs.  Code paths: the unrolled
+//             Hadamard+ladder program (HL3, every round of a QFT), the UX program (straight-line
+//             butterflies + a lean predicate-light interpreter: everything Grover, order finding, larose
+//             and the supremacy circuits need), and the generic interpreter.
+//   3. STORE  the last round writes its groups straight to HBM with streaming stores when it can
+//             (st_direct); otherwise each warp stores the sub-cube of the last run from shared memory.
 //
 // Shared-memory layout: the tile is stored XOR-swizzled, slot(j) = j ^ (fold(j >> 3) & 7)
 // with fold(x) = x ^ x>>3 ^ x>>6 ^ x>>9, in 16-byte units.  The 16-byte bank group of j is
@@ -29,17 +31,18 @@
 // conflict free, and (b) for ANY choice of round bits the planner can hand group-index
 // bits 0..2 to one free local bit of each class (QbRound::qmap), which makes every
 // quarter-warp of an LDS.128/STS.128 hit 8 distinct bank groups.  The swizzle is linear
-// over XOR, so slot(base | spread(e)) = slot(base) ^ slot(spread(e)): one XOR per register.
+// over XOR, so slot(base | spread(e)) = slot(base) ^ slot(spread(e)): one XOR per register, and
+// every thread / iteration / round-bit term of an address is a host-computed constant.
 //
-// Arithmetic is fp64 on the CUDA cores (no tensor cores: 0.5-3 flop/B).  At 12 fused
-// h+ladder stages per sweep the fp64 pipe, not HBM, is the limiter, so the op forms are
-// chosen to minimise DFMA/DMUL count: real matrices (h, ry) cost 8 instead of 20 per pair;
-// h followed by its cu1 ladder is ONE op (ULADDER): y' = (c x + d y) * phase.
+// Arithmetic is fp64 on the CUDA cores (no tensor cores: 0.5-3 flop/B).  The op forms are chosen to
+// minimise DFMA/DMUL count: real matrices (h, ry) cost 8 instead of 16 per pair, a matrix with a
+// real and an imaginary column (h.v = H.S) 8 too; h followed by its cu1 ladder is ONE op (ULADDER):
+// y' = (c x + d y) * phase.
 //
-// Phase ladders: the phase of an amplitude is C_tile * T_lo[j & 63] * T_hi[j >> 6] * F[e];
-// C_tile = product over partner bits outside the tile (one warp per ladder, once per tile,
-// folded into that tile's copy of T_lo), T_* = host-built 64-entry tables over the tile-local
-// partner bits, F = the 8 combinations of the round's own bits (constant bank).
+// Phase ladders: the phase of an amplitude is T_a[lane] * T_b[q >> 5] * F[e]; T_* = host-built
+// tables over the group number q, F = the 8 combinations of the round's own bits (constant bank);
+// the product over partner bits outside the tile (one warp per ladder, once per tile) is folded into
+// that tile's copy of T_b.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
