@@ -18,7 +18,8 @@ C-ABI path (pinned host state -> qb_copy_in -> gates -> qb_copy_out) every step.
 `roofline` is the dominant kernel's algorithmic bytes / its summed CUDA-event time, measured
 in the same timed region (qb_profile_*), against MEASURED_PEAKS.json's hbm_gbs.
 `cpu_baseline` times the reference's own xgates build (oracle/_ref/libxgates.so, 1 thread --
-the reference has no threading) on a bounded sample of the same gate stream.
+the reference has no threading) on a bounded sample of the same gate stream; `cpu_baseline.libq`
+adds the reference's other implementation, stock libq, on a dense 24-qubit register (it stops at 28).
 
 N > 1 (torchrun): the SAME workload (same qubit count, same gate stream) with its state sharded
 over the N GPUs by the top log2(N) index bits -- strong scaling, so metric and config do not
@@ -191,6 +192,35 @@ def cpu_reference_sample(n, stream, budget_s=20.0, max_gates=8):
   if nn != n:
     desc += f"; host RAM could not hold {n} qubits: scaled by 4^-{(n - nn) // 2} (time ~ 2^n)"
   return gps, desc
+
+
+def cpu_reference_libq_sample(width=24, ngates=26):
+  """The reference's OTHER implementation of the path, stock libq (sparse, complex64; SURVEY 8d asks for
+  it beside xgates): a dense `width`-qubit register (walsh first, since libq's cost follows the number of
+  non-zero states) and the first gates of that width's QFT -- h is libq_gate1 (apply.cc:78-176, a hash
+  rebuild per gate), cu1 a linear scan (gates.cc:85-94).  Timed as (walsh + gates) - (walsh), 1 thread."""
+  import math
+  from oracle import oracle
+  if not oracle.have_ref("libq_ref.so"):
+    return None
+  lq = oracle.RefLibq(double=False)
+  ops = []
+  for i in reversed(range(width)):          # circuit.py:320-326 in libq qubit numbers
+    ops.append(("h", i))
+    for j in reversed(range(i)):
+      ops.append(("cu1", i, j, math.pi / 2 ** (i - j)))
+  ops = ops[:ngates]
+  t0 = time.perf_counter()
+  lq.run(width, 0, [("walsh", width)])
+  t1 = time.perf_counter()
+  lq.run(width, 0, [("walsh", width)] + ops)
+  t2 = time.perf_counter()
+  dt = max((t2 - t1) - (t1 - t0), 1e-9)
+  nh = sum(1 for o in ops if o[0] == "h")
+  return {"value": len(ops) / dt, "unit": "gates/s", "cores": 1, "kind": "reference", "qubits": width,
+          "sample": (f"stock libq (src/libq, float, -O3 -ffast-math) on a dense {width}-qubit register: first "
+                     f"{len(ops)} gates of QFT-{width} ({nh} h + {len(ops) - nh} cu1) in {dt:.2f} s after a walsh "
+                     f"of {t1 - t0:.2f} s; libq stops at 28 qubits and its time grows with 2^n")}
 
 
 def run_reference_arm(args, wl, stream):
@@ -496,6 +526,11 @@ def main():
         cpu = {"value": None, "unit": "gates/s", "cores": 1, "kind": "reference", "sample": desc}
     except Exception as ex:  # pylint: disable=broad-except
       cpu = {"value": None, "unit": "gates/s", "cores": 1, "kind": "reference", "sample": f"failed: {ex}"[:200]}
+    try:
+      if cpu is not None:
+        cpu["libq"] = cpu_reference_libq_sample()
+    except Exception as ex:  # pylint: disable=broad-except
+      cpu["libq"] = {"value": None, "sample": f"failed: {ex}"[:200]}
 
   if rank == 0:
     value = ngates * args.steps / (ms * 1e-3)
