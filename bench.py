@@ -527,8 +527,12 @@ def main():
     except Exception as ex:  # pylint: disable=broad-except
       cpu = {"value": None, "unit": "gates/s", "cores": 1, "kind": "reference", "sample": f"failed: {ex}"[:200]}
     try:
-      if cpu is not None:
-        cpu["libq"] = cpu_reference_libq_sample()
+      # in a child process: the reference's C code must not be able to take the bench line down with it
+      out = subprocess.run([sys.executable, "-c",
+                            "import json, bench; print(json.dumps(bench.cpu_reference_libq_sample()))"],
+                           capture_output=True, text=True, timeout=120, cwd=ROOT)
+      cpu["libq"] = json.loads(out.stdout.strip().splitlines()[-1]) if out.returncode == 0 else {
+          "value": None, "sample": f"child exited {out.returncode}"}
     except Exception as ex:  # pylint: disable=broad-except
       cpu["libq"] = {"value": None, "sample": f"failed: {ex}"[:200]}
 
