@@ -200,3 +200,29 @@ def test_hoisted_exchange_keeps_sharded_qft_at_three_passes(monkeypatch):
 
   assert passes({}) == (4, 1)
   assert passes({"QCC_B200_VICTIM_WINDOW": "30", "QCC_B200_HOIST": "1"}) == (3, 1)
+
+
+def test_pair_swap_index_math_equals_send_recv_layout():
+  """k_pair_swap (kernels.cu) swaps local[(h, sel, w)] with peer[(h, 1 - sel, w)] for the flattened element
+  numbers k = h * 2^victim + w of ONE half of [0, 2^(nl-1)) per rank.  Restated in numpy, both ranks'
+  swaps together must leave exactly what do_exchange's send/recv + copy-back leaves (the layout the gloo
+  test above executes)."""
+  rng = np.random.default_rng(3)
+  for nl in (2, 3, 5, 7):
+    for victim in range(nl):
+      sh = [rng.normal(size=1 << nl) + 1j * rng.normal(size=1 << nl) for _ in range(2)]
+      run, nruns = 1 << victim, 1 << (nl - 1 - victim)
+      want = [x.copy() for x in sh]
+      for r in (0, 1):                       # send/recv: rank r gives away the half with victim bit != its rank bit
+        sel = 0 if r else 1
+        want[r].reshape(nruns, 2, run)[:, sel, :] = sh[1 - r].reshape(nruns, 2, run)[:, 1 - sel, :]
+      got = [x.copy() for x in sh]
+      half, low = 1 << (nl - 1), (1 << victim) - 1
+      for r in (0, 1):                       # the kernel: rank bit 0 takes k < half / 2, rank bit 1 the rest
+        sel = 0 if r else 1
+        k = np.arange(half // 2, half) if r else np.arange(0, half // 2)
+        i0 = ((k >> victim) << (victim + 1)) | (k & low)
+        l, p = i0 | (sel << victim), i0 | ((sel ^ 1) << victim)
+        a, b = got[r][l].copy(), got[1 - r][p].copy()
+        got[r][l], got[1 - r][p] = b, a
+      assert all(np.array_equal(got[r], want[r]) for r in (0, 1)), (nl, victim)
