@@ -24,6 +24,9 @@ except Exception as e:
   print("N=$n FAILED", e, open("gpurun_out/scale_qft_$n.json").read()[-800:])
 PY
 done
+# BASELINE.json north_star: "8-GPU 34-qubit QFT wall time and NVLink GB/s" (32 GiB shards)
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29619 \
+  bench.py --gpus 8 --qubits 34 --steps 3 --warmup 2 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | tee gpurun_out/qft34_8gpu.json
 timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29620 \
   bench.py --gpus 8 --workload supremacy --qubits 34 --depth 20 2>&1 | tail -1 | tee gpurun_out/supremacy34_8gpu.json
 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29621 \
