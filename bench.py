@@ -344,6 +344,9 @@ def main():
   ap.add_argument("--no-e2e", action="store_true")
   ap.add_argument("--no-secondary", action="store_true")
   ap.add_argument("--weak", action="store_true", help="N > 1: grow the state to n + log2(N) qubits")
+  ap.add_argument("--flush-per-step", action="store_true",
+                  help="flush the gate queue after every step instead of once at the end of the timed region "
+                       "(sharded states: the lowering then cannot place exchange events across step boundaries)")
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
   if args.workload in ALGOS:
@@ -398,7 +401,8 @@ def main():
 
   for _ in range(args.warmup):
     s.xg_apply_gates(packed)
-    s.flush()
+    if args.flush_per_step:
+      s.flush()
   barrier()
   sampler = ClockSampler(local_rank)
   sampler.start()
@@ -408,9 +412,10 @@ def main():
   t_wall0 = time.perf_counter()
   s.timer_start()
   for _ in range(args.steps):
-    s.xg_apply_gates(packed)
-    s.flush()
-  ms = s.timer_stop()
+    s.xg_apply_gates(packed)     # queued (the C ABI's deferred-gate protocol, gates_jit.cc:53-132) ...
+    if args.flush_per_step:
+      s.flush()
+  ms = s.timer_stop()            # ... and flushed here at the latest: plans, launches, waits for the device
   barrier()
   wall = time.perf_counter() - t_wall0
   prof = s.profile_read(reset=True)
@@ -426,7 +431,7 @@ def main():
 
   # ---- roofline of the dominant kernel class --------------------------------------------
   peak, peak_src = hbm_peak()
-  dom = max((k for k in prof if k != "exchange"), key=lambda k: prof[k]["ms"])
+  dom = max((k for k in prof if k not in ("exchange", "fused_push")), key=lambda k: prof[k]["ms"])
   d = prof[dom]
   roof = None
   if d["launches"]:
@@ -539,14 +544,25 @@ def main():
   if rank == 0:
     value = ngates * args.steps / (ms * 1e-3)
     xch = prof.get("exchange", {"launches": 0, "ms": 0.0, "bytes": 0.0})
+    fpush = prof.get("fused_push", {"launches": 0, "ms": 0.0, "bytes": 0.0})
     exchange = None
     if world > 1:
-      exchange = {"per_step": (c1["exchanges"] - c0["exchanges"]) / args.steps,
-                  "bytes_per_rank_per_step": (c1["bytes_exchanged"] - c0["bytes_exchanged"]) / args.steps,
-                  "ms_per_step_rank0": xch["ms"] / args.steps,
-                  "nvlink_gbs_per_direction_rank0": (xch["bytes"] / (xch["ms"] * 1e-3) / 1e9) if xch["ms"] else None,
-                  "note": "each exchange sends and receives half a shard per rank (ncclSend/ncclRecv pair) "
-                          "and copies the received half back in place"}
+      mode = s.exchange_mode()
+      sent = c1["bytes_exchanged"] - c0["bytes_exchanged"]
+      carrier_ms = xch["ms"] + fpush["ms"]     # kernels that carried exchange traffic (+ their barriers)
+      exchange = {"mode": mode, "events_per_step": (c1["exchanges"] - c0["exchanges"]) / args.steps,
+                  "bytes_sent_per_rank_per_step": sent / args.steps,
+                  "fused_push_passes_per_step": fpush["launches"] / args.steps,
+                  "fused_push_pass_avg_ms_rank0": fpush["ms"] / fpush["launches"] if fpush["launches"] else None,
+                  "standalone_ms_per_step_rank0": xch["ms"] / args.steps,
+                  "nvlink_gbs_per_direction_rank0": (sent / (carrier_ms * 1e-3) / 1e9) if carrier_ms else None,
+                  "note": {"push": "an exchange event swaps k sharded bits with k local ones in ONE all-to-all: the "
+                                   "store stage of the fused pass before it writes every amplitude to its "
+                                   "destination rank's alternate buffer through CUDA IPC peer mappings (NVLink "
+                                   "posted writes); bytes sent = (1 - 2^-k) of a shard per event; GB/s = bytes "
+                                   "sent / time of the kernels that carried them (a pass + its exchange)",
+                           "swap": "one in-place pair-swap kernel per (sharded bit, local bit) pair over peer mappings",
+                           "nccl": "ncclSend/ncclRecv of half a shard per pair + copy-back"}[mode]}
     line = {
         "metric": "gate-applies/sec", "value": value, "unit": "gates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -558,7 +574,9 @@ def main():
                    "shard_qubits": n_shard,
                    "parallelism": "1 GPU" if world == 1 else
                    f"one {n}-qubit state sharded over {world} GPUs by its top {int(np.log2(world))} index bits; "
-                   "NCCL send/recv pair exchange for gates on sharded qubits"},
+                   "gates on sharded qubits cost an exchange event over NVLink (see exchange.mode)",
+                   "queue": "flush per step" if args.flush_per_step else
+                   "the K steps are queued and flushed once inside the timed region"},
         "passes_per_step": (c1["passes"] - c0["passes"]) / args.steps,
         "gpu_launches": c1["kernel_launches"] - c0["kernel_launches"],
         "achieved_gbs_algorithmic_by_gate": by_gate_alg,

@@ -62,7 +62,7 @@ extern "C" {
 #define QB_ERR_COMM (-4)     /* multi-GPU communicator error */
 #define QB_ERR_UNSUPPORTED (-5)
 
-#define QB_ABI_VERSION 1
+#define QB_ABI_VERSION 2
 
 typedef struct qb_state qb_state; /* opaque */
 
@@ -101,8 +101,10 @@ typedef struct qb_counters {
 #define QB_KCLASS_PHASE 1    /* single diagonal gate */
 #define QB_KCLASS_FUSED 2    /* tile-resident fused pass */
 #define QB_KCLASS_AUX 3      /* init / reductions / compaction */
-#define QB_KCLASS_EXCHANGE 4 /* multi-GPU half-shard exchange (NCCL send/recv + copy-back) */
-#define QB_KCLASS_COUNT 5
+#define QB_KCLASS_EXCHANGE 4 /* multi-GPU exchange on its own: NCCL send/recv + copy-back, in-place pair
+                              * swap or out-of-place push kernel, and the barriers that fence them */
+#define QB_KCLASS_FUSED_PUSH 5 /* fused pass whose store stage carries an exchange event (peer writes over NVLink) */
+#define QB_KCLASS_COUNT 6
 typedef struct qb_profile {
   uint64_t launches[QB_KCLASS_COUNT];
   double ms[QB_KCLASS_COUNT];          /* summed CUDA-event durations */
@@ -125,15 +127,21 @@ int qb_state_create(int nqubits, uint64_t init_label, int device, qb_state **out
  * rank; id128 is the 128-byte communicator id rank 0 obtained from qb_comm_get_unique_id and
  * passed to the others out of band (bench.py: torch.distributed broadcast).  On a sharded state
  * every gate call, flush and readout is COLLECTIVE: all ranks must make the same calls in the
- * same order.  Gates whose target is a sharded bit trigger a pairwise half-shard exchange
- * (ncclSend/ncclRecv) and a logical->physical bit remap; diagonal gates and controls on
- * sharded bits need no communication.  qb_copy_in/out and qb_list_above address the LOCAL
- * shard (call qb_canonicalize first to undo the bit remap). */
+ * same order.  Gates whose target is a sharded bit trigger an exchange event (sharded bits
+ * swapped with local ones: one all-to-all over NVLink peer memory written by the store stage of the
+ * preceding fused pass; ncclSend/ncclRecv pair exchanges where peer mappings are unavailable) and a
+ * logical->physical bit remap; diagonal gates and controls on sharded bits need no communication.  qb_copy_in/out address this rank's
+ * slice of the canonical vector (they undo the bit remap first, collectively); qb_list_above lists
+ * this rank's entries under their logical labels. */
 int qb_comm_get_unique_id(void *id128);
 int qb_state_create_sharded(int nqubits, uint64_t init_label, int device, int rank, int nranks,
                             const void *id128, qb_state **out);
 /* nlocal: index bits held per rank; perm[b] (nqubits ints): physical bit of logical bit b. */
 int qb_state_layout(qb_state *s, int *nlocal, int *rank, int *nranks, int *perm);
+/* How exchange events run on this state: 0 ncclSend/ncclRecv per pair, 1 in-place peer-memory swap per
+ * pair, 2 push (double-buffered, one all-to-all per event fused into the preceding pass); -1 not sharded.
+ * QCC_B200_EXCHANGE=nccl|swap|push asks for one; the outcome is agreed on by all ranks at creation. */
+int qb_state_exchange_mode(qb_state *s, int *mode);
 /* Exchanges / local bit swaps that bring perm back to the identity. */
 int qb_canonicalize(qb_state *s);
 int qb_state_destroy(qb_state *s);
@@ -210,6 +218,12 @@ int qb_plan_json(int nqubits, const qb_gate *gates, int64_t ngates, int tile_bit
  * identity layout.  Host only: the CPU tests execute it with numpy shards + gloo send/recv. */
 int qb_shard_lower_json(int nqubits, int nranks, int rank, const qb_gate *gates, int64_t ngates,
                         int canonicalize, char *buf, size_t cap, size_t *needed);
+/* Where the push exchange of engine.cu writes: for one exchange event (npairs pairs: rank bit k <-> local
+ * victim bit) and each local index of `rank`'s shard, the index in the DISTRIBUTED vector
+ * (destination rank << nlocal | destination local index).  Host only; the CPU tests check it against the
+ * pairwise send/recv layout. */
+int qb_shard_event_dest(int nlocal, int nranks, int rank, const int *rank_bits, const int *victims, int npairs,
+                        const uint64_t *local, uint64_t *dest, int64_t count);
 /* Tile size (log2 amplitudes per CTA tile, 4..13, default 12) used by qb_flush. */
 int qb_set_tile_bits(qb_state *s, int tile_bits);
 

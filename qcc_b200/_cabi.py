@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libqcc_b200.so")
 
 QB_OK = 0
-QB_KCLASS = {"apply1": 0, "phase": 1, "fused": 2, "aux": 3, "exchange": 4}
+QB_KCLASS = {"apply1": 0, "phase": 1, "fused": 2, "aux": 3, "exchange": 4, "fused_push": 5}
 
 
 class QbError(RuntimeError):
@@ -40,8 +40,8 @@ class qb_counters(ctypes.Structure):
 
 
 class qb_profile(ctypes.Structure):
-  _fields_ = [("launches", ctypes.c_uint64 * 5), ("ms", ctypes.c_double * 5),
-              ("bytes", ctypes.c_double * 5)]
+  _fields_ = [("launches", ctypes.c_uint64 * 6), ("ms", ctypes.c_double * 6),
+              ("bytes", ctypes.c_double * 6)]
 
 
 _P = ctypes.c_void_p
@@ -61,8 +61,10 @@ PROTOTYPES = {
     "qb_state_create_sharded": [_I, _U64, _I, _I, _I, _P, ctypes.POINTER(_P)],
     "qb_state_layout": [_P, ctypes.POINTER(_I), ctypes.POINTER(_I), ctypes.POINTER(_I), ctypes.POINTER(_I)],
     "qb_canonicalize": [_P],
+    "qb_state_exchange_mode": [_P, ctypes.POINTER(_I)],
     "qb_shard_lower_json": [_I, _I, _I, ctypes.POINTER(qb_gate), ctypes.c_int64, _I, ctypes.c_char_p,
                             ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)],
+    "qb_shard_event_dest": [_I, _I, _I, ctypes.POINTER(_I), ctypes.POINTER(_I), _I, _P, _P, ctypes.c_int64],
     "qb_state_destroy": [_P],
     "qb_state_nqubits": [_P, ctypes.POINTER(_I)],
     "qb_set_basis": [_P, _U64],
@@ -180,6 +182,17 @@ def shard_lower_json(nqubits: int, nranks: int, rank: int, gates, canonicalize: 
   return buf.value.decode()
 
 
+def shard_event_dest(nlocal: int, nranks: int, rank: int, pairs, local: np.ndarray) -> np.ndarray:
+  """Distributed destination index of each local index under one exchange event (host only)."""
+  rb = (ctypes.c_int * len(pairs))(*[int(p[0]) for p in pairs])
+  vb = (ctypes.c_int * len(pairs))(*[int(p[1]) for p in pairs])
+  local = np.ascontiguousarray(local, dtype=np.uint64)
+  dest = np.empty_like(local)
+  check(lib().qb_shard_event_dest(nlocal, nranks, rank, rb, vb, len(pairs), local.ctypes.data, dest.ctypes.data,
+                                  local.size))
+  return dest
+
+
 def comm_unique_id() -> bytes:
   buf = ctypes.create_string_buffer(128)
   check(lib().qb_comm_get_unique_id(buf))
@@ -290,6 +303,11 @@ class DeviceState:
     perm = (_I * self.nqubits)()
     check(lib().qb_state_layout(self._h, ctypes.byref(nl), ctypes.byref(r), ctypes.byref(nr), perm))
     return {"nlocal": nl.value, "rank": r.value, "nranks": nr.value, "perm": list(perm)}
+
+  def exchange_mode(self) -> str:
+    m = _I()
+    check(lib().qb_state_exchange_mode(self._h, ctypes.byref(m)))
+    return {-1: "none", 0: "nccl", 1: "swap", 2: "push"}[m.value]
 
   def canonicalize(self):
     check(lib().qb_canonicalize(self._h))

@@ -79,15 +79,22 @@ struct qb_state {
   int rank = 0, nranks = 1, p = 0;
   std::vector<int> perm;          // logical index bit -> physical index bit
   uint32_t flip = 0;              // relabelled rank bits (shard.h): rank bit k carries the negated qubit
-  int victim_window = qb::kVictimWindow;  // wider when exchanges go through the peer-swap kernel
+  int victim_window = qb::kVictimWindow;  // wider when exchanges go through peer memory
+  // How exchange events run (decided collectively at creation, QCC_B200_EXCHANGE=nccl|swap|push overrides):
+  //   QB_X_NCCL  ncclSend/ncclRecv per pair into a half-shard bounce buffer + copy-back
+  //   QB_X_SWAP  one in-place kernel per pair over CUDA IPC peer mappings (k_pair_swap)
+  //   QB_X_PUSH  the state is double-buffered; an event (any number of pairs) is ONE out-of-place all-to-all
+  //              written by the store stage of the last fused pass before it (or k_push_remap)
+  int xmode = 0;
+  double2 *base = nullptr;        // the allocation: one shard, or two (push)
+  int bufsel = 0;                 // push: which half of `base` psi is (all ranks flip together)
   ncclComm_t comm = nullptr;
   double2 *xbuf = nullptr;        // half-shard receive buffer for exchanges
   size_t xbuf_bytes = 0;
   cudaStream_t xstream = nullptr; // copy-back of received pieces overlaps the next piece's transfer
   std::vector<cudaEvent_t> xevents;
-  // peer-memory exchange (QCC_B200_PEER_SWAP=1): CUDA IPC mappings of the other ranks' state vectors
-  int peer_state = 0;              // 0 not tried, 1 mapped on every rank, -1 unavailable (NCCL path)
-  std::vector<double2 *> peer_psi; // [rank] -> mapping (nullptr for ourselves)
+  // CUDA IPC mappings of the other ranks' allocations (swap / push)
+  std::vector<double2 *> peer_base; // [rank] -> mapping of its `base` (our own pointer for ourselves)
   double *d_sync = nullptr;        // scratch of the stream-ordered cross-rank barrier
   cudaStream_t stream = nullptr;
   double2 *psi = nullptr;
@@ -204,8 +211,12 @@ int ensure_plan_buffers(qb_state *s, size_t bytes) {
   return QB_OK;
 }
 
-// Fused execution: plan the queue into tile-resident passes and launch one kernel per pass.
-int run_fused(qb_state *s, const std::vector<QbGate> &gates) {
+enum { QB_X_NCCL = 0, QB_X_SWAP = 1, QB_X_PUSH = 2 };
+
+// Fused execution: plan the queue into tile-resident passes and launch one kernel per pass.  With
+// `push` (an exchange event follows these gates, push mode) the LAST pass, when it is a fused pass,
+// stores through the event's bit permutation into the alternate buffers; *pushed says whether it did.
+int run_fused(qb_state *s, const std::vector<QbGate> &gates, const qb::PushMap *push, bool *pushed) {
   qb::Plan plan;
   qb::plan_gates(s->n, gates.data(), int64_t(gates.size()), s->tile_bits, &plan);
   // The staging buffers are reused flush after flush: wait until the previous plan's
@@ -233,11 +244,14 @@ int run_fused(qb_state *s, const std::vector<QbGate> &gates) {
     dp.outph = pp.outph.empty() ? nullptr : reinterpret_cast<const double2 *>(dbase + pp.outph_off);
     dp.jbtab = reinterpret_cast<const uint32_t *>(dbase + pp.jbtab_off);
     dp.noutbits = pp.noutbits;
+    const bool carry = push && k + 1 == plan.passes.size();
+    if (carry) dp.push = push;
     double sweep = double(s->len) * 32.0;
     {
-      ProfScope ps(s, QB_KCLASS_FUSED, sweep);
+      ProfScope ps(s, carry ? QB_KCLASS_FUSED_PUSH : QB_KCLASS_FUSED, sweep);
       CU(qb::launch_fused_pass(s->psi, s->n, dp, s->stream));
     }
+    if (carry && pushed) *pushed = true;
     s->cnt.kernel_launches += 1;
     s->cnt.passes += 1;
     s->cnt.bytes_swept += uint64_t(sweep);
@@ -248,33 +262,48 @@ int run_fused(qb_state *s, const std::vector<QbGate> &gates) {
   return QB_OK;
 }
 
-int run_local(qb_state *s, const std::vector<QbGate> &q) {
+int run_local(qb_state *s, const std::vector<QbGate> &q, const qb::PushMap *push = nullptr, bool *pushed = nullptr) {
   if (q.empty()) return QB_OK;
-  if (s->fusion && s->n > QB_TILE_LOW) return run_fused(s, q);
+  if (s->fusion && s->n > QB_TILE_LOW) return run_fused(s, q, push, pushed);
   for (const QbGate &g : q) QB(run_single(s, g));
   return QB_OK;
 }
 
-// Swap physical global bit (n + rank_bit) with local bit `victim`: every rank trades the half
-// of its shard whose victim bit differs from its own rank bit with rank ^ (1 << rank_bit).
-// The half is 2^(n-1-victim) contiguous runs of 2^victim amplitudes; they are received into
-// xbuf (NCCL must not write into memory it is still sending from) and copied back in place.
-// Map every other rank's state vector into this process (CUDA IPC over NVLink peer access).  Collective:
-// all ranks call it at the same point; the outcome is agreed on (min over ranks), so either every rank
-// uses the peer path or none does.  Opt-in until measured on hardware: QCC_B200_PEER_SWAP=1.
-int ensure_peer_maps(qb_state *s, const qb::NcclApi *nc) {
-  if (s->peer_state != 0) return QB_OK;
-  s->peer_state = -1;
-  const char *env = getenv("QCC_B200_PEER_SWAP");
-  if (!env || atoi(env) == 0) return QB_OK;
-  s->peer_psi.assign(size_t(s->nranks), nullptr);
+// min over ranks of *val (collective; synchronises the stream)
+int agree_min(qb_state *s, double *val) {
+  const qb::NcclApi *nc = qb::nccl_api(nullptr);
+  if (!nc || !s->comm) return fail(QB_ERR_COMM, "no communicator");
+  if (!s->d_sync) CU(cudaMalloc(&s->d_sync, sizeof(double)));
+  CU(cudaMemcpyAsync(s->d_sync, val, sizeof *val, cudaMemcpyHostToDevice, s->stream));
+  NC(nc, nc->AllReduce(s->d_sync, s->d_sync, 1, ncclDouble, ncclMin, s->comm, s->stream));
+  CU(cudaMemcpyAsync(val, s->d_sync, sizeof *val, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
+  return QB_OK;
+}
+
+// Stream-ordered barrier over all ranks: everything the ranks enqueued before it (their kernels' writes
+// into peer memory included -- a kernel's stores are performed when it completes) is done before anything
+// enqueued after it starts.
+int stream_barrier(qb_state *s) {
+  const qb::NcclApi *nc = qb::nccl_api(nullptr);
+  if (!nc || !s->comm) return fail(QB_ERR_COMM, "no communicator");
+  NC(nc, nc->AllReduce(s->d_sync, s->d_sync, 1, ncclDouble, ncclMin, s->comm, s->stream));
+  return QB_OK;
+}
+
+// Map every other rank's allocation into this process (CUDA IPC over NVLink peer access).  Collective:
+// the outcome is agreed on (min over ranks), so either every rank uses peer memory or none does.
+int map_peers(qb_state *s, bool *mapped) {
+  *mapped = false;
+  const qb::NcclApi *nc = qb::nccl_api(nullptr);
+  if (!nc || !s->comm) return fail(QB_ERR_COMM, "no communicator");
+  s->peer_base.assign(size_t(s->nranks), nullptr);
   std::vector<cudaIpcMemHandle_t> handles(static_cast<size_t>(s->nranks));
   unsigned char *dh = nullptr;
   CU(cudaMalloc(&dh, sizeof(cudaIpcMemHandle_t) * size_t(s->nranks)));
-  if (!s->d_sync) CU(cudaMalloc(&s->d_sync, sizeof(double)));
   double ok = 1.0;
   cudaIpcMemHandle_t mine;
-  if (cudaIpcGetMemHandle(&mine, s->psi) != cudaSuccess) {
+  if (cudaIpcGetMemHandle(&mine, s->base) != cudaSuccess) {
     cudaGetLastError();
     memset(&mine, 0, sizeof mine);
     ok = 0.0;
@@ -284,61 +313,65 @@ int ensure_peer_maps(qb_state *s, const qb::NcclApi *nc) {
   CU(cudaMemcpyAsync(handles.data(), dh, sizeof mine * size_t(s->nranks), cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
   cudaFree(dh);
-  for (int r = 0; r < s->nranks && ok != 0.0; ++r) {
-    if (r == s->rank) continue;
-    void *ptr = nullptr;
-    if (cudaIpcOpenMemHandle(&ptr, handles[size_t(r)], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-      cudaGetLastError();
-      ok = 0.0;
-      break;
-    }
-    s->peer_psi[size_t(r)] = static_cast<double2 *>(ptr);
-  }
-  // agree: the peer path only if every rank mapped every other rank
-  CU(cudaMemcpyAsync(s->d_sync, &ok, sizeof ok, cudaMemcpyHostToDevice, s->stream));
-  NC(nc, nc->AllReduce(s->d_sync, s->d_sync, 1, ncclDouble, ncclMin, s->comm, s->stream));
-  CU(cudaMemcpyAsync(&ok, s->d_sync, sizeof ok, cudaMemcpyDeviceToHost, s->stream));
-  CU(cudaStreamSynchronize(s->stream));
+  QB(agree_min(s, &ok));   // nobody opens a handle that some rank could not make
   if (ok != 0.0) {
-    s->peer_state = 1;
-  } else {
-    for (auto &p : s->peer_psi)
-      if (p) {
-        cudaIpcCloseMemHandle(p);
-        p = nullptr;
+    ok = 1.0;
+    for (int r = 0; r < s->nranks; ++r) {
+      if (r == s->rank) {
+        s->peer_base[size_t(r)] = s->base;
+        continue;
       }
-    if (s->rank == 0) fprintf(stderr, "qcc_b200: QCC_B200_PEER_SWAP: peer mapping unavailable, using NCCL send/recv\n");
+      void *ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, handles[size_t(r)], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0.0;
+        break;
+      }
+      s->peer_base[size_t(r)] = static_cast<double2 *>(ptr);
+    }
+    QB(agree_min(s, &ok));
   }
+  if (ok != 0.0) {
+    *mapped = true;
+    return QB_OK;
+  }
+  for (int r = 0; r < s->nranks; ++r)
+    if (r != s->rank && s->peer_base[size_t(r)]) cudaIpcCloseMemHandle(s->peer_base[size_t(r)]);
+  s->peer_base.clear();
+  if (s->rank == 0) fprintf(stderr, "qcc_b200: CUDA IPC peer mapping unavailable, exchanges use NCCL send/recv\n");
   return QB_OK;
 }
 
+// One pair of an event, in place: swap physical global bit (n + rank_bit) with local bit `victim` -- every
+// rank trades the half of its shard whose victim bit differs from its own rank bit with rank ^ (1 << rank_bit).
 int do_exchange(qb_state *s, int rank_bit, int victim) {
   std::string why;
   const qb::NcclApi *nc = qb::nccl_api(&why);
   if (!nc || !s->comm) return fail(QB_ERR_COMM, "exchange without a communicator: %s", why.c_str());
   const int b = (s->rank >> rank_bit) & 1;
   const int partner = s->rank ^ (1 << rank_bit);
-  QB(ensure_peer_maps(s, nc));
-  if (s->peer_state == 1) {
+  const size_t half_bytes = size_t(s->len / 2) * sizeof(double2);
+  if (s->xmode != QB_X_NCCL) {
     // ONE kernel swaps our outgoing half with the partner's in place, through the peer mapping: no
     // receive buffer, no copy-back, both NVLink directions busy (we read and write the partner's shard
     // for one half of the elements, it reads and writes ours for the other half).  The two stream-ordered
-    // all-reduces fence it: nobody touches a shard its owner is still computing on, and nobody computes
+    // barriers fence it: nobody touches a shard its owner is still computing on, and nobody computes
     // on a shard its partner is still swapping into.
-    const size_t half_bytes_p = size_t(s->len / 2) * sizeof(double2);
-    ProfScope ps(s, QB_KCLASS_EXCHANGE, double(half_bytes_p));
-    NC(nc, nc->AllReduce(s->d_sync, s->d_sync, 1, ncclDouble, ncclMin, s->comm, s->stream));
-    CU(qb::launch_pair_swap(s->psi, s->peer_psi[size_t(partner)], s->n, victim, b ? 0 : 1, b, s->stream));
-    NC(nc, nc->AllReduce(s->d_sync, s->d_sync, 1, ncclDouble, ncclMin, s->comm, s->stream));
+    ProfScope ps(s, QB_KCLASS_EXCHANGE, double(half_bytes));
+    double2 *peer = s->peer_base[size_t(partner)] + (s->bufsel ? s->len : 0);
+    QB(stream_barrier(s));
+    CU(qb::launch_pair_swap(s->psi, peer, s->n, victim, b ? 0 : 1, b, s->stream));
+    QB(stream_barrier(s));
     s->cnt.exchanges += 1;
-    s->cnt.bytes_exchanged += half_bytes_p;
+    s->cnt.bytes_exchanged += half_bytes;
     s->cnt.kernel_launches += 1;
     return QB_OK;
   }
+  // NCCL: the half is 2^(n-1-victim) contiguous runs of 2^victim amplitudes; they are received into
+  // xbuf (NCCL must not write into memory it is still sending from) and copied back in place.
   const uint64_t run = uint64_t(1) << victim;
   const uint64_t nruns = uint64_t(1) << (s->n - 1 - victim);
   const uint64_t sel = b ? 0 : 1;  // we give away the half whose victim bit is NOT our rank bit
-  const size_t half_bytes = size_t(s->len / 2) * sizeof(double2);
   if (s->xbuf_bytes < half_bytes) {
     if (s->xbuf) cudaFree(s->xbuf);
     s->xbuf = nullptr;
@@ -381,17 +414,106 @@ int do_exchange(qb_state *s, int rank_bit, int victim) {
   return QB_OK;
 }
 
-int run_steps(qb_state *s, const std::vector<qb::ShardStep> &steps) {
-  for (const qb::ShardStep &st : steps) {
-    if (st.kind == 1) {
-      QB(do_exchange(s, st.rank_bit, st.victim));
-      continue;
-    }
-    const uint64_t before = s->cnt.gates_applied;
-    QB(run_local(s, st.gates));
-    s->cnt.gates_applied = before + uint64_t(st.retired);
+// The bit permutation of an exchange event as the store map of one rank (push mode); out[] is left empty.
+int event_map(int nl, int p, int rank, const int *rank_bits, const int *victims, size_t np, qb::PushMap *m) {
+  *m = qb::PushMap();
+  if (np == 0 || np > size_t(qb::kPushMaxMoved)) return fail(QB_ERR_ARG, "exchange event with %zu pairs", np);
+  m->nl = nl;
+  m->nmoved = int(np);
+  uint64_t rt = 0;
+  for (int b = 0; b < p; ++b) {
+    int dest = nl + b;   // a rank bit outside the event stays a rank bit
+    for (size_t k = 0; k < np; ++k)
+      if (rank_bits[k] == b) dest = victims[k];
+    rt |= uint64_t((rank >> b) & 1) << dest;
+  }
+  m->rank_term = rt;
+  for (size_t k = 0; k < np; ++k) {
+    if (victims[k] < QB_TILE_LOW || victims[k] >= nl || rank_bits[k] < 0 || rank_bits[k] >= p)
+      return fail(QB_ERR_ARG, "exchange pair (rank bit %d, victim bit %d)", rank_bits[k], victims[k]);
+    for (size_t j = 0; j < k; ++j)
+      if (victims[j] == victims[k] || rank_bits[j] == rank_bits[k]) return fail(QB_ERR_ARG, "exchange pairs overlap");
+    m->src[k] = victims[k];
+    m->dst[k] = nl + rank_bits[k];
+    m->moved_mask |= uint64_t(1) << victims[k];
   }
   return QB_OK;
+}
+
+int make_push_map(const qb_state *s, const qb::ShardStep &ev, qb::PushMap *m) {
+  if (ev.rank_bits.size() != ev.victims.size()) return fail(QB_ERR_ARG, "bad exchange event");
+  QB(event_map(s->n, s->p, s->rank, ev.rank_bits.data(), ev.victims.data(), ev.rank_bits.size(), m));
+  for (int r = 0; r < s->nranks; ++r) m->out[r] = s->peer_base[size_t(r)] + (s->bufsel ? 0 : s->len);
+  return QB_OK;
+}
+
+// After every rank's push of an event has been enqueued: fence, then the alternate buffers are the state.
+int finish_push(qb_state *s, const qb::ShardStep &ev) {
+  {
+    ProfScope ps(s, QB_KCLASS_EXCHANGE, 0.0);
+    QB(stream_barrier(s));
+  }
+  s->bufsel ^= 1;
+  s->psi = s->base + (s->bufsel ? s->len : 0);
+  s->cnt.exchanges += 1;
+  const uint64_t shard_bytes = uint64_t(s->len) * sizeof(double2);
+  s->cnt.bytes_exchanged += shard_bytes - (shard_bytes >> ev.rank_bits.size());
+  return QB_OK;
+}
+
+int do_event(qb_state *s, const qb::ShardStep &ev) {
+  if (s->xmode != QB_X_PUSH) {
+    for (size_t k = 0; k < ev.rank_bits.size(); ++k) QB(do_exchange(s, ev.rank_bits[k], ev.victims[k]));
+    return QB_OK;
+  }
+  qb::PushMap pm;
+  QB(make_push_map(s, ev, &pm));
+  {
+    const double shard_bytes = double(s->len) * sizeof(double2);
+    ProfScope ps(s, QB_KCLASS_EXCHANGE, shard_bytes - shard_bytes / double(uint64_t(1) << ev.rank_bits.size()));
+    CU(qb::launch_push_remap(s->psi, pm, s->stream));
+  }
+  s->cnt.kernel_launches += 1;
+  return finish_push(s, ev);
+}
+
+int run_steps(qb_state *s, const std::vector<qb::ShardStep> &steps) {
+  for (size_t k = 0; k < steps.size(); ++k) {
+    const qb::ShardStep &st = steps[k];
+    if (st.kind == 1) {
+      QB(do_event(s, st));
+      continue;
+    }
+    // push mode: the event that follows these gates rides on the store stage of their last pass
+    const qb::ShardStep *ev = s->xmode == QB_X_PUSH && k + 1 < steps.size() && steps[k + 1].kind == 1 ? &steps[k + 1] : nullptr;
+    static const bool no_fuse = getenv("QCC_B200_NO_PUSH_FUSE") != nullptr;
+    if (no_fuse) ev = nullptr;
+    qb::PushMap pm;
+    if (ev) QB(make_push_map(s, *ev, &pm));
+    bool pushed = false;
+    const uint64_t before = s->cnt.gates_applied;
+    QB(run_local(s, st.gates, ev ? &pm : nullptr, &pushed));
+    s->cnt.gates_applied = before + uint64_t(st.retired);
+    if (pushed) {
+      QB(finish_push(s, *ev));
+      ++k;
+    }
+  }
+  return QB_OK;
+}
+
+void make_layout(const qb_state *s, qb::ShardLayout *L) {
+  L->n = s->nq;
+  L->nl = s->n;
+  L->p = s->p;
+  L->rank = s->rank;
+  L->perm = s->perm;
+  L->flip = s->flip;
+  L->window = s->victim_window;
+  L->hoist = s->xmode != QB_X_NCCL ? 1 : 0;
+  L->prefetch = s->xmode == QB_X_PUSH ? 1 : 0;
+  if (getenv("QCC_B200_NO_PREFETCH")) L->prefetch = 0;
+  L->pass_targets = std::max(1, s->tile_bits - QB_TILE_LOW);
 }
 
 int flush(qb_state *s) {
@@ -401,15 +523,7 @@ int flush(qb_state *s) {
   q.swap(s->queue);
   if (s->nranks == 1) return run_local(s, q);
   qb::ShardLayout L;
-  L.n = s->nq;
-  L.nl = s->n;
-  L.p = s->p;
-  L.rank = s->rank;
-  L.perm = s->perm;
-  L.flip = s->flip;
-  L.window = s->victim_window;
-  L.hoist = s->peer_state == 1 ? 1 : 0;
-  L.pass_targets = std::max(1, s->tile_bits - QB_TILE_LOW);
+  make_layout(s, &L);
   std::vector<qb::ShardStep> steps;
   qb::lower_for_rank(&L, q.data(), int64_t(q.size()), &steps);
   s->perm = L.perm;
@@ -575,14 +689,15 @@ static int create_impl(int nqubits, uint64_t init_label, int device, int rank, i
   for (int b = 0; b < nqubits; ++b) s->perm[size_t(b)] = b;
   size_t freeb = 0, totalb = 0;
   cudaMemGetInfo(&freeb, &totalb);
-  size_t need = size_t(s->len) * sizeof(double2);
-  if (need + (size_t(64) << 20) > freeb) {
+  const size_t need = size_t(s->len) * sizeof(double2);
+  const size_t margin = size_t(64) << 20;
+  if (nranks == 1 && need + margin > freeb) {
     delete s;
     return fail(QB_ERR_NOMEM, "state needs %zu MiB, device has %zu MiB free", need >> 20, freeb >> 20);
   }
   cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaMalloc(&s->psi, need);
   if (e == cudaSuccess) e = cudaMalloc(&s->d_scalar, sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&s->d_sync, sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&s->d_counter, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMalloc(&s->d_blk_prob, sizeof(double) * qb::argmax_blocks());
   if (e == cudaSuccess) e = cudaMalloc(&s->d_blk_idx, sizeof(uint64_t) * qb::argmax_blocks());
@@ -591,6 +706,7 @@ static int create_impl(int nqubits, uint64_t init_label, int device, int rank, i
   if (e == cudaSuccess) e = cudaEventCreate(&s->t0);
   if (e == cudaSuccess) e = cudaEventCreate(&s->t1);
   if (e == cudaSuccess) e = qb::fused_configure(device);
+  if (e == cudaSuccess && nranks == 1) e = cudaMalloc(&s->base, need);
   if (e != cudaSuccess) {
     int rc = fail(e == cudaErrorMemoryAllocation ? QB_ERR_NOMEM : QB_ERR_CUDA, "state allocation failed: %s",
                   cudaGetErrorString(e));
@@ -608,17 +724,55 @@ static int create_impl(int nqubits, uint64_t init_label, int device, int rank, i
       qb_state_destroy(s);
       return rc;
     }
-  }
-  if (nranks > 1) {
-    // QCC_B200_PEER_SWAP=1: map the peers now (collective), so that the lowering knows from the first
-    // gate on whether victims have to keep the exchanged half in few contiguous runs
-    int prc = ensure_peer_maps(s, qb::nccl_api(nullptr));
-    if (prc != QB_OK) {
-      qb_state_destroy(s);
-      return prc;
+    // Exchange mode.  Every decision below is collective (min over ranks), so all ranks end up in the same
+    // mode: push needs room for a second shard on every GPU and the peer mappings; swap only the mappings.
+    int mode = nranks <= qb::kPushMaxRanks ? QB_X_PUSH : QB_X_SWAP;
+    if (const char *env = getenv("QCC_B200_EXCHANGE")) {
+      if (!strcmp(env, "nccl")) mode = QB_X_NCCL;
+      else if (!strcmp(env, "swap")) mode = QB_X_SWAP;
+      else if (!strcmp(env, "push") && nranks <= qb::kPushMaxRanks) mode = QB_X_PUSH;
     }
-    if (s->peer_state == 1) s->victim_window = std::max(qb::kVictimWindow, s->n - qb::kPeerSwapMinVictim);
+    int rc = QB_OK;
+    if (mode == QB_X_PUSH) {
+      double ok = 2 * need + margin <= freeb ? 1.0 : 0.0;
+      if (ok != 0.0 && cudaMalloc(&s->base, 2 * need) != cudaSuccess) {
+        cudaGetLastError();
+        s->base = nullptr;
+        ok = 0.0;
+      }
+      rc = agree_min(s, &ok);
+      if (rc == QB_OK && ok == 0.0) {
+        if (s->base) cudaFree(s->base);
+        s->base = nullptr;
+        mode = QB_X_SWAP;
+      }
+    }
+    if (rc == QB_OK && !s->base) {
+      double ok = need + margin <= freeb ? 1.0 : 0.0;
+      if (ok != 0.0 && cudaMalloc(&s->base, need) != cudaSuccess) {
+        cudaGetLastError();
+        s->base = nullptr;
+        ok = 0.0;
+      }
+      rc = agree_min(s, &ok);
+      if (rc == QB_OK && ok == 0.0)
+        rc = fail(QB_ERR_NOMEM, "shard needs %zu MiB on every rank (this device has %zu MiB free)", need >> 20, freeb >> 20);
+    }
+    if (rc == QB_OK && mode != QB_X_NCCL) {
+      bool mapped = false;
+      rc = map_peers(s, &mapped);
+      if (!mapped) mode = QB_X_NCCL;
+    }
+    if (rc != QB_OK) {
+      qb_state_destroy(s);
+      return rc;
+    }
+    s->xmode = mode;
+    // peer-memory exchanges do not care how many contiguous runs the exchanged part is made of
+    if (mode != QB_X_NCCL) s->victim_window = std::max(qb::kVictimWindow, s->n - qb::kPeerSwapMinVictim);
+    if (mode == QB_X_PUSH) s->victim_window = std::min(s->victim_window, s->n - QB_TILE_LOW);  // bits 0..2 never move
   }
+  s->psi = s->base;
   int rc = qb_set_basis(s, init_label);
   if (rc != QB_OK) {
     qb_state_destroy(s);
@@ -638,12 +792,14 @@ int qb_state_destroy(qb_state *s) {
   }
   for (auto e : s->event_pool) cudaEventDestroy(e);
   // peer mappings: every rank unmaps the others' vectors BEFORE anybody frees its own (collective)
-  for (auto &p : s->peer_psi)
-    if (p) {
-      cudaIpcCloseMemHandle(p);
-      p = nullptr;
+  bool had_peers = false;
+  for (int r = 0; r < int(s->peer_base.size()); ++r)
+    if (r != s->rank && s->peer_base[size_t(r)]) {
+      cudaIpcCloseMemHandle(s->peer_base[size_t(r)]);
+      had_peers = true;
     }
-  if (s->peer_state == 1 && s->comm && s->d_sync) {
+  s->peer_base.clear();
+  if (had_peers && s->comm && s->d_sync) {
     const qb::NcclApi *nc = qb::nccl_api(nullptr);
     if (nc && nc->AllReduce(s->d_sync, s->d_sync, 1, ncclDouble, ncclMin, s->comm, s->stream) == ncclSuccess)
       cudaStreamSynchronize(s->stream);
@@ -656,7 +812,7 @@ int qb_state_destroy(qb_state *s) {
   if (s->d_sync) cudaFree(s->d_sync);
   for (auto e : s->xevents) cudaEventDestroy(e);
   if (s->xstream) cudaStreamDestroy(s->xstream);
-  if (s->psi) cudaFree(s->psi);
+  if (s->base) cudaFree(s->base);
   if (s->d_scalar) cudaFree(s->d_scalar);
   if (s->d_counter) cudaFree(s->d_counter);
   if (s->d_blk_prob) cudaFree(s->d_blk_prob);
@@ -710,10 +866,28 @@ int qb_fill_random(qb_state *s, uint64_t seed) {
   return QB_OK;
 }
 
+// Sharded states: the copies address this rank's slice of the CANONICAL vector (identity bit layout), so a
+// layout left behind by exchange events or rank relabels is undone first (collective, like every call on
+// a sharded state).  Overwriting the whole shard needs no data movement: the layout is simply reset.
+static bool layout_is_canonical(const qb_state *s) {
+  if (s->flip) return false;
+  for (int b = 0; b < s->nq; ++b)
+    if (s->perm[size_t(b)] != b) return false;
+  return true;
+}
+
 int qb_copy_in(qb_state *s, uint64_t first, uint64_t count, const double *host) {
   if (!s || !host) return fail(QB_ERR_ARG, "null pointer");
   if (first > s->len || count > s->len - first) return fail(QB_ERR_ARG, "range out of bounds");
   QB(flush(s));
+  if (s->nranks > 1 && !layout_is_canonical(s)) {
+    if (first == 0 && count == s->len) {
+      for (int b = 0; b < s->nq; ++b) s->perm[size_t(b)] = b;
+      s->flip = 0;
+    } else {
+      QB(qb_canonicalize(s));
+    }
+  }
   CU(cudaMemcpyAsync(s->psi + first, host, size_t(count) * sizeof(double2), cudaMemcpyHostToDevice, s->stream));
   CU(cudaStreamSynchronize(s->stream));
   return QB_OK;
@@ -723,6 +897,7 @@ int qb_copy_out(qb_state *s, uint64_t first, uint64_t count, double *host) {
   if (!s || !host) return fail(QB_ERR_ARG, "null pointer");
   if (first > s->len || count > s->len - first) return fail(QB_ERR_ARG, "range out of bounds");
   QB(flush(s));
+  if (s->nranks > 1 && !layout_is_canonical(s)) QB(qb_canonicalize(s));
   CU(cudaMemcpyAsync(host, s->psi + first, size_t(count) * sizeof(double2), cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
   return QB_OK;
@@ -1122,20 +1297,18 @@ int qb_state_layout(qb_state *s, int *nlocal, int *rank, int *nranks, int *perm)
   return QB_OK;
 }
 
+int qb_state_exchange_mode(qb_state *s, int *mode) {
+  if (!s || !mode) return fail(QB_ERR_ARG, "null pointer");
+  *mode = s->nranks > 1 ? s->xmode : -1;
+  return QB_OK;
+}
+
 int qb_canonicalize(qb_state *s) {
   if (!s) return fail(QB_ERR_ARG, "null state");
   QB(flush(s));
   if (s->nranks == 1) return QB_OK;
   qb::ShardLayout L;
-  L.n = s->nq;
-  L.nl = s->n;
-  L.p = s->p;
-  L.rank = s->rank;
-  L.perm = s->perm;
-  L.flip = s->flip;
-  L.window = s->victim_window;
-  L.hoist = s->peer_state == 1 ? 1 : 0;
-  L.pass_targets = std::max(1, s->tile_bits - QB_TILE_LOW);
+  make_layout(s, &L);
   std::vector<qb::ShardStep> steps;
   qb::canonicalize_steps(&L, &steps);
   s->perm = L.perm;
@@ -1174,12 +1347,25 @@ int qb_shard_lower_json(int nqubits, int nranks, int rank, const qb_gate *gates,
   for (int b = 0; b < nqubits; ++b) L.perm[size_t(b)] = b;
   if (const char *w = getenv("QCC_B200_VICTIM_WINDOW")) L.window = std::max(1, atoi(w));  // tests: the peer-swap window
   if (const char *h = getenv("QCC_B200_HOIST")) L.hoist = atoi(h);                        // ... and its exchange hoisting
+  if (const char *h = getenv("QCC_B200_PREFETCH")) L.prefetch = atoi(h);                  // ... and multi-bit events
   std::vector<qb::ShardStep> steps;
   qb::lower_for_rank(&L, q.data(), ngates, &steps);
   if (canonicalize) qb::canonicalize_steps(&L, &steps);
   std::string js = qb::steps_to_json(L, steps);
   *needed = js.size() + 1;
   if (buf && cap >= js.size() + 1) memcpy(buf, js.c_str(), js.size() + 1);
+  return QB_OK;
+}
+
+int qb_shard_event_dest(int nlocal, int nranks, int rank, const int *rank_bits, const int *victims, int npairs,
+                        const uint64_t *local, uint64_t *dest, int64_t count) {
+  if (!rank_bits || !victims || (!local && count) || (!dest && count)) return fail(QB_ERR_ARG, "null pointer");
+  if (nranks < 1 || (nranks & (nranks - 1)) || rank < 0 || rank >= nranks) return fail(QB_ERR_ARG, "bad rank/nranks");
+  int pbits = 0;
+  while ((1 << pbits) < nranks) ++pbits;
+  qb::PushMap m;
+  QB(event_map(nlocal, pbits, rank, rank_bits, victims, size_t(npairs), &m));
+  for (int64_t k = 0; k < count; ++k) dest[k] = qb::push_apply(m, local[k]);
   return QB_OK;
 }
 

@@ -3,9 +3,9 @@
 // One CTA of 256 threads = one TILE of 2^K amplitudes (K <= 13, default 12 = 64 KiB; see qb_types.h).
 // Up to three CTAs are resident per SM (80 registers, 64 KiB tile + <= 9 KiB of ladder tables each), and
 // because they start and finish at different times one streams its tile while the others compute.
-// (A persistent CTA per SM with a ring of tile buffers -- k_fused_pipe below, kept as a measured
-// experiment -- loses: warps that move through the rounds in lockstep cover the fp64 and
-// shared-memory latencies worse than warps of different CTAs in different phases.)
+// (A persistent CTA per SM with a ring of tile buffers was measured in round 1 and lost by 29 %: warps
+// that move through the rounds in lockstep cover the fp64 and shared-memory latencies worse than warps
+// of different CTAs in different phases -- DESIGN.md, experiment log.)
 //
 //   1. LOAD   the tile is gathered from HBM straight into (swizzled) shared memory with cp.async
 //             (LDGSTS, 16 B per request, L2-only): 8 consecutive lanes fetch one 128-byte run, and the
@@ -24,6 +24,10 @@
 //             and the supremacy circuits need), and the generic interpreter.
 //   3. STORE  the last round writes its groups straight to HBM with streaming stores when it can
 //             (st_direct); otherwise each warp stores the sub-cube of the last run from shared memory.
+//             On a sharded state the store stage can carry an EXCHANGE EVENT (PushMap, kernels.h): every
+//             amplitude is written to where the event's bit permutation of the distributed index puts
+//             it -- this rank's alternate buffer or, through CUDA IPC peer mappings, another rank's, as
+//             posted writes over NVLink -- so the all-to-all costs no sweep of its own.
 //
 // Shared-memory layout: the tile is stored XOR-swizzled, slot(j) = j ^ (fold(j >> 3) & 7)
 // with fold(x) = x ^ x>>3 ^ x>>6 ^ x>>9, in 16-byte units.  The 16-byte bank group of j is
@@ -90,6 +94,8 @@ struct FusedParams {
   const double2 *outph;
   const int32_t *outbits;
   const uint32_t *jbtab;
+  int push_on;   // 1: the store stage writes through `push` (exchange event fused into this pass)
+  PushMap push;
   int debug;  // timing experiments only -- 1: skip the op loop, 2: skip the rounds, 4: skip the store, 8: skip the load, 16: no round programs, 32: (unused), 64: CTA barrier after every round
   // per copy iteration i (thread t moves copy index t + 256 i, see QbPassDesc::ld_map / st_map): global
   // offset of copy index 256 i in units of 8 amplitudes, and the XOR that takes the byte slot of copy
@@ -699,6 +705,8 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
   double2 *s_tab = tile + tileN;                                        // ntable
   uint32_t *s_active = reinterpret_cast<uint32_t *>(s_tab + P.desc.ntable);  // 4 words: ops whose
                                                                         // outside-tile predicate holds for this tile
+  double2 **s_out = reinterpret_cast<double2 **>(s_active + 4);         // push: destination buffer of every rank
+  if (P.push_on && threadIdx.x < kPushMaxRanks) s_out[threadIdx.x] = P.push.out[threadIdx.x];
   const QbOp *s_ops = P.ops;        // constant bank
   const QbRound *s_rounds = P.rounds;
   const uint32_t tid = threadIdx.x;
@@ -956,7 +964,21 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
     }
 
     // ---- STORE ---------------------------------------------------------------------------
-    if (!(P.debug & 4) && io_on && !st_direct) {
+    if (P.push_on && io_on) {
+      // the tile goes to where the exchange event puts it: distributed index = sigma(rank, base) | sigma(thread
+      // term) | sigma(iteration term); its top bits name the destination rank, the rest the slot in that
+      // rank's alternate buffer (posted writes over NVLink for the other ranks)
+      uint64_t sb = (base & ~P.push.moved_mask) | P.push.rank_term | g_st;
+#pragma unroll
+      for (int k = 0; k < kPushMaxMoved; ++k)
+        if (k < P.push.nmoved) sb |= ((base >> P.push.src[k]) & 1) << P.push.dst[k];
+      const uint64_t lmask = (uint64_t(1) << P.push.nl) - 1;
+#pragma unroll 4
+      for (uint32_t i = 0; i < io_iters; ++i) {
+        const uint64_t a = sb + (uint64_t(P.st_goff[i]) << 3);
+        __stcs(s_out[a >> P.push.nl] + (a & lmask), lds128(tile_sa + (s_st ^ P.st_sxor[i])));
+      }
+    } else if (!(P.debug & 4) && io_on && !st_direct) {
       double2 *dst = psi + (base | g_st);
       if (io_iters == 16) {
 #pragma unroll
@@ -974,145 +996,13 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
   }
 }
 
-// ---- k_fused_pipe: persistent, software-pipelined form of the pass for program-only passes --------
-// (kept as a measured experiment, see launch_fused_pass: it loses to the one-shot kernel)
-// One CTA of 512 threads per SM walks over its tiles with a ring of kPipeBufs 64 KiB tile buffers.
-// While all 16 warps run the rounds of tile k, the cp.async copies of tiles k+1 and k+2 are in
-// flight, so nobody ever sits waiting for HBM with nothing else resident to run: with one-shot CTAs
-// (k_fused_pass) a warp spends more than half of its life waiting for its tile to arrive and only
-// ~7 of the 24 resident warps are in their compute phase at any time, too few to cover the fp64 and
-// shared-memory latencies of the rounds.  One group per thread per round (512 groups at K = 12);
-// warps w and w + 8 share a per-warp sub-cube, so the barrier-free runs of rounds use a 64-thread
-// named barrier per pair instead of a warp sync.
-constexpr int kPipeThreads = 512;
-constexpr int kPipeBufs = 3;
-
-__global__ void __launch_bounds__(kPipeThreads, 1) k_fused_pipe(const __grid_constant__ FusedParams P) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  constexpr int K = 12;
-  constexpr uint32_t tileN = 1u << K;
-  constexpr uint32_t kTileBytes = tileN * sizeof(double2);
-  double2 *s_tab = reinterpret_cast<double2 *>(smem_raw + size_t(kPipeBufs) * kTileBytes);
-  const uint32_t tid = threadIdx.x;
-  double2 *__restrict__ psi = P.psi;
-  const uint32_t buf0_sa = uint32_t(__cvta_generic_to_shared(smem_raw));
-  const uint32_t tab_sa = uint32_t(__cvta_generic_to_shared(s_tab));
-
-  // copy index c = tid + 512 i: bits 0..8 from the thread, bits 9..11 from the iteration
-  uint64_t g_ld = tid & 7u, g_st = tid & 7u;
-  uint32_t j_ld = tid & 7u, j_st = tid & 7u;
-#pragma unroll
-  for (int k = 3; k < 9; ++k) {
-    const uint32_t bit = (tid >> k) & 1u;
-    j_ld |= bit << P.desc.ld_map[k];
-    j_st |= bit << P.desc.st_map[k];
-    g_ld |= uint64_t(bit) << P.desc.tile_bits[P.desc.ld_map[k]];
-    g_st |= uint64_t(bit) << P.desc.tile_bits[P.desc.st_map[k]];
-  }
-  const uint32_t s_ld = swz(j_ld) << 4, s_st = swz(j_st) << 4;
-
-  const uint32_t ntiles = 1u << (P.nbits - K);
-  auto tile_base = [&](uint32_t t) {
-    uint64_t b = 0, tt = t;
-    if (P.desc.nseg >= 0) {
-#pragma unroll
-      for (int r = 0; r < QB_MAX_SEGS; ++r) {
-        if (r < P.desc.nseg) {
-          const int len = P.desc.seg_len[r];
-          b |= (tt & ((uint64_t(1) << len) - 1)) << P.desc.seg_pos[r];
-          tt >>= len;
-        }
-      }
-      return b;
-    }
-    for (int bit = 0; bit < P.nbits; ++bit) {
-      if (!((P.desc.tile_mask >> bit) & 1)) {
-        b |= (tt & 1) << bit;
-        tt >>= 1;
-      }
-    }
-    return b;
-  };
-  auto issue_load = [&](uint32_t t, uint32_t slot) {
-    if (t < ntiles) {
-      const double2 *src = psi + (tile_base(t) | g_ld);
-      const uint32_t sa = buf0_sa + slot * kTileBytes;
-#pragma unroll
-      for (uint32_t i = 0; i < tileN / kPipeThreads; ++i)
-        cp_async16(sa + (s_ld ^ P.ld_sxor[2 * i]), src + (uint64_t(P.ld_goff[2 * i]) << 3));
-    }
-    cp_async_commit();  // always: keeps the group count in step with the tile count
-  };
-
-  const uint32_t ngroups = tileN >> 3;
-  const int nb_tab = 1 << (K - QB_ROUND_BITS - QB_LADDER_LANE_BITS);
-  const uint32_t stride = gridDim.x;
-  issue_load(blockIdx.x, 0);
-  issue_load(blockIdx.x + stride, 1);
-  for (int i = tid; i < P.desc.ntable; i += kPipeThreads) s_tab[i] = __ldg(P.tables + i);
-  __syncthreads();
-  uint32_t slot = 0;
-  for (uint32_t t = blockIdx.x; t < ntiles; t += stride) {
-    const uint64_t base = tile_base(t);
-    // per-tile constants of the phase ladders, folded into this tile's copy of T_b (every round of
-    // the previous tile is finished: its store phase does not read the tables)
-    for (int oi = int(tid >> 5); oi < P.desc.nops; oi += kPipeThreads / 32) {
-      const QbOp *op = P.ops + oi;
-      const int k8 = op->kind & 0xff;
-      if (k8 == QB_K_LADDER || k8 == QB_K_ULADDER) {
-        const int lane = int(tid & 31u);
-        const double2 *ph = P.outph + op->outph_off;
-        double2 c = make_double2(1.0, 0.0);
-        if (lane < op->nout && ((base >> __ldg(P.outbits + op->out_off + lane)) & 1)) c = __ldg(ph + 1 + lane);
-        if (lane == 0) c = cmul(c, __ldg(ph));
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          double2 d;
-          d.x = __shfl_xor_sync(0xffffffffu, c.x, o);
-          d.y = __shfl_xor_sync(0xffffffffu, c.y, o);
-          c = cmul(c, d);
-        }
-        if (lane < nb_tab) {
-          const int e = op->table_off + (1 << QB_LADDER_LANE_BITS) + lane;
-          s_tab[e] = cmul(__ldg(P.tables + e), c);
-        }
-      }
-    }
-    cp_async_wait<kPipeBufs - 2>();  // this tile has landed; the next one may still be in flight
-    __syncthreads();                 // ... for every thread; the store of the previous tile is done too
-    // refill the buffer the previous tile just left (two tiles ahead)
-    issue_load(t + (kPipeBufs - 1) * stride, (slot + kPipeBufs - 1) % kPipeBufs);
-    const uint32_t tile_sa = buf0_sa + slot * kTileBytes;
-    for (int r = 0; r < ((P.debug & 2) ? 0 : P.desc.nrounds); ++r) {
-      const QbRound *R = P.rounds + r;
-      program_round<true, kPipeThreads>(P, r, R->op_begin, R->op_end, tile_sa, tab_sa, ngroups, tid, base, false);
-      if (R->nobar) asm volatile("bar.sync %0, 64;" ::"r"(1u + ((tid >> 5) & 7u)) : "memory");
-      else __syncthreads();
-    }
-    if (!(P.debug & 4)) {
-      double2 *dst = psi + (base | g_st);
-#pragma unroll
-      for (uint32_t i = 0; i < tileN / kPipeThreads; ++i)
-        __stcs(dst + (uint64_t(P.st_goff[2 * i]) << 3), lds128(tile_sa + (s_st ^ P.st_sxor[2 * i])));
-    }
-    slot = (slot + 1) % kPipeBufs;
-  }
-  cp_async_wait<0>();
-}
-
 size_t fused_smem_bytes(int K, int ntable) {
-  return (size_t(1) << K) * sizeof(double2) + size_t(ntable) * sizeof(double2) + 4 * sizeof(uint32_t);
+  return (size_t(1) << K) * sizeof(double2) + size_t(ntable) * sizeof(double2) + 4 * sizeof(uint32_t) +
+         kPushMaxRanks * sizeof(double2 *);
 }
 
 constexpr size_t kSmemLimit = 227 * 1024;
 int g_sms = 0;
-
-// QCC_B200_FUSED_PIPE (experiment, see launch_fused_pass), read per launch
-int pipe_mode() {
-  const char *e = getenv("QCC_B200_FUSED_PIPE");
-  return e ? atoi(e) : 0;
-}
-bool pipe_forced() { return pipe_mode() != 0; }
 
 template <bool FULL, bool FAST>
 cudaError_t configure_one() {
@@ -1132,9 +1022,6 @@ cudaError_t fused_configure(int device) {
   static_assert(sizeof(FusedParams) <= 32764, "kernel parameter space");
   cudaError_t err = cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, device);
   if (err != cudaSuccess) return err;
-  if ((err = cudaFuncSetAttribute(k_fused_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kSmemLimit))) !=
-      cudaSuccess)
-    return err;
   if ((err = configure_one<true, true>()) != cudaSuccess) return err;
   if ((err = configure_one<true, false>()) != cudaSuccess) return err;
   if ((err = configure_one<false, true>()) != cudaSuccess) return err;
@@ -1262,7 +1149,22 @@ cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cuda
         }
   }
   if (dbg & (1 | 2 | 4 | 8 | 16)) P.desc.ld_direct = P.desc.st_direct = 0;  // timing experiments use the copy path
-  if (pipe_forced()) P.desc.ld_direct = P.desc.st_direct = 0;
+  P.push_on = 0;
+  if (p.push) {
+    // exchange event fused into the store stage: every store address term goes through the event's bit
+    // permutation (linear over OR on disjoint bit sets, so thread / iteration / tile terms stay separate)
+    P.push_on = 1;
+    P.push = *p.push;
+    P.desc.st_direct = 0;
+    auto sig = [&](uint64_t local) { return push_apply(*p.push, local) & ~p.push->rank_term; };
+    for (int k = 3; k < 8 && k < K; ++k)
+      P.st_gbit[k] = uint32_t(sig(uint64_t(1) << p.desc.tile_bits[p.desc.st_map[k]]) >> 3);
+    for (uint32_t i = 0; i < (1u << K) / kFThreads; ++i) {
+      uint64_t gs = 0;
+      for (int k = 8; k < K; ++k) gs |= uint64_t((i >> (k - 8)) & 1u) << p.desc.tile_bits[p.desc.st_map[k]];
+      P.st_goff[i] = uint32_t(sig(gs) >> 3);
+    }
+  }
   // FAST: no round needs the op interpreter (and the debug switches that fall back to it are off)
   bool fast = !(dbg & (1 | 16));
   for (int r = 0; r < p.desc.nrounds; ++r)
@@ -1276,17 +1178,6 @@ cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cuda
   unsigned blocks = ntiles;
   if (persist > 0 && ntiles > unsigned(persist * g_sms)) blocks = unsigned(persist * g_sms);
   const bool full = ((1u << (K - 3)) % kFThreads) == 0;
-  // EXPERIMENT, off by default: QCC_B200_FUSED_PIPE=1 sends program-only passes over K = 12 tiles (with
-  // enough tiles to fill the ring on every SM; =2: any tile count, what the tests use) through the
-  // persistent pipelined kernel.  Measured on a B200 it is SLOWER than one-shot CTAs (QFT-30 32.8 vs 25.5 ms,
-  // larose-28 195 vs 163 ms): 16 warps that move through the rounds in lockstep cover the fp64 and
-  // shared-memory latencies worse than 24 warps of three CTAs in different phases.  Read per launch.
-  const int pipe = pipe_mode();
-  const size_t pipe_smem = size_t(kPipeBufs) * (size_t(1) << 12) * sizeof(double2) + size_t(p.desc.ntable) * sizeof(double2);
-  if (pipe && fast && K == 12 && !(dbg & 8) && (pipe == 2 || ntiles >= unsigned(4 * g_sms)) && pipe_smem <= kSmemLimit) {
-    k_fused_pipe<<<std::min(unsigned(g_sms), ntiles), kPipeThreads, pipe_smem, st>>>(P);
-    return cudaGetLastError();
-  }
   if (full && fast) k_fused_pass<true, true><<<blocks, kFThreads, smem, st>>>(P);
   else if (full) k_fused_pass<true, false><<<blocks, kFThreads, smem, st>>>(P);
   else if (fast) k_fused_pass<false, true><<<blocks, kFThreads, smem, st>>>(P);

@@ -388,6 +388,52 @@ cudaError_t launch_pair_swap(double2 *local, double2 *peer, int nbits, int victi
   return cudaGetLastError();
 }
 
+// ---- push exchange without a pass to ride on ------------------------------------------------------
+// Plain out-of-place remap: amplitude e of this shard goes to out[a >> nl][a & (2^nl - 1)], a = sigma(rank, e).
+// Moved bits are >= 3 (engine.cu), so 8 consecutive lanes still write one 128-byte run; 4 independent
+// 16-byte copies per thread, the remote ones posted writes over NVLink.
+namespace {
+__global__ void __launch_bounds__(256) k_push_remap(const double2 *__restrict__ psi, const __grid_constant__ PushMap m) {
+  __shared__ double2 *s_out[kPushMaxRanks];
+  if (threadIdx.x < kPushMaxRanks) s_out[threadIdx.x] = m.out[threadIdx.x];
+  __syncthreads();
+  const uint64_t n = uint64_t(1) << m.nl;
+  const uint64_t lmask = n - 1;
+  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+  for (uint64_t e0 = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; e0 < n; e0 += 4 * stride) {
+    double2 v[4];
+    uint64_t a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint64_t e = e0 + uint64_t(u) * stride;
+      if (e < n) {
+        v[u] = __ldcs(psi + e);
+        uint64_t x = (e & ~m.moved_mask) | m.rank_term;
+#pragma unroll
+        for (int k = 0; k < kPushMaxMoved; ++k)
+          if (k < m.nmoved) x |= ((e >> m.src[k]) & 1) << m.dst[k];
+        a[u] = x;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint64_t e = e0 + uint64_t(u) * stride;
+      if (e < n) __stcs(s_out[a[u] >> m.nl] + (a[u] & lmask), v[u]);
+    }
+  }
+}
+}  // namespace
+
+cudaError_t launch_push_remap(const double2 *psi, const PushMap &m, cudaStream_t st) {
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const uint64_t n = uint64_t(1) << m.nl;
+  const uint64_t want = (n + 1023) / 1024;
+  const unsigned blocks = unsigned(std::min<uint64_t>(std::max<uint64_t>(want, 1), uint64_t(sms) * 8));
+  k_push_remap<<<blocks, 256, 0, st>>>(psi, m);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_cvt_f2d(const float2 *in, double2 *out, uint64_t n, cudaStream_t st) {
   k_cvt_f2d<<<stride_blocks(n), kThreads, 0, st>>>(in, out, n);
   return cudaGetLastError();

@@ -39,6 +39,28 @@ cudaError_t launch_list_above(const double2 *psi, uint64_t n, double thr, uint64
 // so every element pair is swapped exactly once and nothing is staged.
 cudaError_t launch_pair_swap(double2 *local, double2 *peer, int nbits, int victim, int sel_local, int upper,
                              cudaStream_t st);
+// Push exchange (engine.cu do_push_event): one exchange event is a permutation sigma of the bits of the
+// DISTRIBUTED index (rank << nl | local index).  Every rank writes each of its amplitudes to where it belongs
+// afterwards -- out[destination rank] + destination local index, the other ranks' buffers reached through
+// CUDA IPC peer mappings over NVLink -- out of place, into the alternate buffer of the double-buffered
+// state.  The fused pass does this in its store stage (fused.cu), k_push_remap as a plain copy.
+constexpr int kPushMaxRanks = 16;
+constexpr int kPushMaxMoved = 8;
+struct PushMap {
+  int nl = 0;                       // local index bits
+  int nmoved = 0;                   // local source bits that move
+  int src[kPushMaxMoved] = {};      // local source bit ...
+  int dst[kPushMaxMoved] = {};      // ... -> bit of the distributed index it lands on (>= nl: a rank bit)
+  uint64_t moved_mask = 0;          // OR of 1 << src[k]
+  uint64_t rank_term = 0;           // sigma(rank << nl): where this rank's own rank bits land
+  double2 *out[kPushMaxRanks] = {}; // per destination rank: base of the buffer the event fills
+};
+inline uint64_t push_apply(const PushMap &m, uint64_t local) {   // distributed destination index of a local index
+  uint64_t a = (local & ~m.moved_mask) | m.rank_term;
+  for (int k = 0; k < m.nmoved; ++k) a |= ((local >> m.src[k]) & 1) << m.dst[k];
+  return a;
+}
+cudaError_t launch_push_remap(const double2 *psi, const PushMap &m, cudaStream_t st);
 cudaError_t launch_cvt_f2d(const float2 *in, double2 *out, uint64_t n, cudaStream_t st);
 
 // ---- fused tile-resident pass (fused.cu) ---------------------------------------
@@ -51,6 +73,7 @@ struct DevicePass {
   const int32_t *outbits; // device (ladder outside-bit lists) or nullptr
   const uint32_t *jbtab;  // device (per round, per group: base index | swizzled slot << 16)
   int noutbits = 0;       // entries in outbits
+  const PushMap *push = nullptr;  // HOST: the pass stores through this exchange event's bit permutation
 };
 cudaError_t fused_configure(int device);  // opt in to large dynamic shared memory, query SM count
 cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cudaStream_t st);

@@ -24,18 +24,6 @@ void close_step(ShardStep *cur, std::vector<ShardStep> *steps) {
   *cur = ShardStep();
 }
 
-void push_exchange(ShardLayout *L, int global_pos, int victim, std::vector<ShardStep> *steps) {
-  ShardStep ex;
-  ex.kind = 1;
-  ex.rank_bit = global_pos - L->nl;
-  ex.victim = victim;
-  steps->push_back(ex);
-  std::vector<int> inv = inverse_of(L->perm);
-  const int la = inv[size_t(global_pos)], lb = inv[size_t(victim)];
-  L->perm[size_t(la)] = victim;
-  L->perm[size_t(lb)] = global_pos;
-}
-
 bool nondiagonal(int kind) { return kind == QB_K_U || kind == QB_K_PERM || kind == QB_K_SWAP; }
 
 bool is_plain_x(const QbGate &g) {
@@ -43,57 +31,60 @@ bool is_plain_x(const QbGate &g) {
          g.m[4] == 1.0 && g.m[5] == 0.0;
 }
 
+bool relabel_enabled() {
+  static const bool no_relabel = getenv("QCC_B200_NO_RELABEL") != nullptr;
+  return !no_relabel;
+}
+
+// does gate g need its target qubit to be LOCAL?  (a plain x on a sharded qubit is a rank relabel)
+bool needs_local(const QbGate &g) { return nondiagonal(g.kind) && !(relabel_enabled() && is_plain_x(g)); }
+
+// first gate index >= from that needs logical qubit lq local; ngates if none
+int64_t next_need(const QbGate *gates, int64_t ngates, int64_t from, int lq) {
+  for (int64_t j = from; j < ngates; ++j)
+    if (gates[j].target == lq && needs_local(gates[j])) return j;
+  return ngates;
+}
+
 // value of the LOGICAL qubit that lives at global physical position pb, on this rank
 int global_bit(const ShardLayout &L, int pb) { return int(((uint32_t(L.rank) ^ L.flip) >> (pb - L.nl)) & 1u); }
 
-// exchange global position <-> local victim; a relabelled (flipped) rank bit arrives in the victim bit
-// as the negation of its qubit: one local x puts it right, and the new occupant of the rank bit is plain
-void exchange_bits(ShardLayout *L, int global_pos, int victim, ShardStep *cur, std::vector<ShardStep> *steps) {
+// One exchange event: every (global position, victim) pair is swapped; a relabelled (flipped) rank bit
+// arrives in its victim bit as the negation of its qubit: one local x puts it right, and the new
+// occupant of the rank bit is plain.
+void exchange_event(ShardLayout *L, const std::vector<std::pair<int, int>> &pairs, ShardStep *cur,
+                    std::vector<ShardStep> *steps) {
   close_step(cur, steps);
-  push_exchange(L, global_pos, victim, steps);
-  const uint32_t fb = 1u << (global_pos - L->nl);
-  if (L->flip & fb) {
-    L->flip &= ~fb;
-    QbGate x{};
-    x.ctl_mask = 0;
-    x.target = victim;
-    x.kind = QB_K_PERM;
-    memcpy(x.m, kX, sizeof kX);
-    cur->gates.push_back(x);
-  }
-}
-
-int64_t hoist_point(const ShardLayout &L, const QbGate *gates, int64_t seg_start, int64_t i, int victim);
-
-// Belady: among the top local bits, evict the qubit whose next use as a mixing target is farthest.
-// With hoisting, among the equally far ones the victim that lets the exchange move back to a pass
-// boundary wins (a qubit whose own last mixing gate lies before that boundary), higher bits first.
-int choose_victim(const ShardLayout &L, const QbGate *gates, int64_t ngates, int64_t from, int64_t seg_start) {
-  std::vector<int> inv = inverse_of(L.perm);
-  int best = L.nl - 1;
-  int64_t best_dist = -1;
-  bool best_hoists = false;
-  for (int v = L.nl - 1; v >= std::max(0, L.nl - L.window); --v) {
-    const int lv = inv[size_t(v)];
-    int64_t dist = ngates + 1;
-    for (int64_t j = from + 1; j < ngates; ++j)
-      if (nondiagonal(gates[j].kind) && gates[j].target == lv) {
-        dist = j - from;
-        break;
-      }
-    if (dist < best_dist) continue;
-    const bool hoists = L.hoist && hoist_point(L, gates, seg_start, from, v) < from;
-    if (dist > best_dist || (hoists && !best_hoists)) {
-      best_dist = dist;
-      best = v;
-      best_hoists = hoists;
+  ShardStep ex;
+  ex.kind = 1;
+  for (const auto &pr : pairs) {
+    const int global_pos = pr.first, victim = pr.second;
+    ex.rank_bits.push_back(global_pos - L->nl);
+    ex.victims.push_back(victim);
+    std::vector<int> inv = inverse_of(L->perm);
+    const int la = inv[size_t(global_pos)], lb = inv[size_t(victim)];
+    L->perm[size_t(la)] = victim;
+    L->perm[size_t(lb)] = global_pos;
+    const uint32_t fb = 1u << (global_pos - L->nl);
+    if (L->flip & fb) {
+      L->flip &= ~fb;
+      QbGate x{};
+      x.ctl_mask = 0;
+      x.target = victim;
+      x.kind = QB_K_PERM;
+      memcpy(x.m, kX, sizeof kX);
+      cur->gates.push_back(x);
     }
   }
-  return best;
+  steps->push_back(ex);
+}
+
+void exchange_bits(ShardLayout *L, int global_pos, int victim, ShardStep *cur, std::vector<ShardStep> *steps) {
+  exchange_event(L, {{global_pos, victim}}, cur, steps);
 }
 
 // Where to put the exchange that gate i needs: the latest pass boundary of the local stream in
-// [seg_start, i] from which on the victim's qubit is not a mixing target any more (it becomes sharded
+// [seg_start, i] from which on the victim's qubit is not needed local any more (it becomes sharded
 // at that point).  Pass boundaries are estimated the way the fusion planner cuts: a new pass when one
 // more distinct target bit above QB_TILE_LOW would not fit.  Depends on the stream, the permutation
 // and the victim only, so every rank finds the same point.
@@ -102,12 +93,16 @@ int64_t hoist_point(const ShardLayout &L, const QbGate *gates, int64_t seg_start
   const int lv = inv[size_t(victim)];
   int64_t j0 = seg_start;
   for (int64_t k = i - 1; k >= seg_start; --k)
-    if (nondiagonal(gates[k].kind) && gates[k].target == lv) {
+    if (gates[k].target == lv && needs_local(gates[k])) {
       j0 = k + 1;
       break;
     }
   int64_t best = i;
   bool found = false;
+  if (j0 == seg_start && L.hoist > 1) {   // the very start of the segment is a boundary too (previous event / flush)
+    best = seg_start;
+    found = true;
+  }
   std::vector<int> targets;
   for (int64_t k = seg_start; k < i; ++k) {
     if (!nondiagonal(gates[k].kind)) continue;
@@ -124,6 +119,70 @@ int64_t hoist_point(const ShardLayout &L, const QbGate *gates, int64_t seg_start
     targets.push_back(pt);
   }
   return found ? best : i;
+}
+
+// Victim for the qubit gate i needs: among the local bits of the window, prefer one that lets the
+// exchange sit on a pass boundary (hoisting; its qubit is not needed again before that boundary),
+// then Belady -- the qubit whose next use as a mixing target is farthest -- then the higher bit.
+// A hoistable victim that is needed again almost at once is not preferred (it would come straight back).
+void choose_victim(const ShardLayout &L, const QbGate *gates, int64_t ngates, int64_t i, int64_t seg_start,
+                   int *victim, int64_t *point) {
+  std::vector<int> inv = inverse_of(L.perm);
+  int best = L.nl - 1;
+  int64_t best_dist = -1, best_point = i;
+  bool best_hoists = false;
+  const int64_t soon = 4 * int64_t(L.pass_targets);
+  for (int v = L.nl - 1; v >= std::max(0, L.nl - L.window); --v) {
+    const int lv = inv[size_t(v)];
+    const int64_t dist = next_need(gates, ngates, i + 1, lv) - i;
+    const int64_t hp = L.hoist ? hoist_point(L, gates, seg_start, i, v) : i;
+    const bool hoists = hp < i && (dist > soon || dist >= ngates - i);
+    bool better;
+    if (best_dist < 0) better = true;
+    else if (hoists != best_hoists) better = hoists;
+    else better = dist > best_dist;
+    if (better) {
+      best = v;
+      best_dist = dist;
+      best_hoists = hoists;
+      best_point = hoists ? hp : i;
+    }
+  }
+  *victim = best;
+  *point = best_point;
+}
+
+// Prefetch: the event at point j (needed by gate i) also swaps in every other sharded qubit that is
+// needed before the best remaining victim is, soonest first.
+void add_prefetch_pairs(const ShardLayout &L, const QbGate *gates, int64_t ngates, int64_t j,
+                        std::vector<std::pair<int, int>> *pairs) {
+  std::vector<int> inv = inverse_of(L.perm);
+  struct Cand {
+    int pos;
+    int64_t need;
+  };
+  std::vector<Cand> globals, locals;
+  auto used = [&](int pos) {
+    for (const auto &pr : *pairs)
+      if (pr.first == pos || pr.second == pos) return true;
+    return false;
+  };
+  for (int G = L.nl; G < L.n; ++G) {
+    if (used(G)) continue;
+    const int64_t u = next_need(gates, ngates, j, inv[size_t(G)]);
+    if (u < ngates) globals.push_back(Cand{G, u});
+  }
+  if (globals.empty()) return;
+  for (int v = L.nl - 1; v >= std::max(0, L.nl - L.window); --v)
+    if (!used(v)) locals.push_back(Cand{v, next_need(gates, ngates, j, inv[size_t(v)])});
+  std::stable_sort(globals.begin(), globals.end(), [](const Cand &a, const Cand &b) { return a.need < b.need; });
+  std::stable_sort(locals.begin(), locals.end(), [](const Cand &a, const Cand &b) { return a.need > b.need; });
+  size_t li = 0;
+  for (const Cand &g : globals) {
+    if (li >= locals.size() || locals[li].need <= g.need) break;
+    pairs->push_back({g.pos, locals[li].pos});
+    ++li;
+  }
 }
 
 }  // namespace
@@ -147,21 +206,23 @@ void lower_for_rank(ShardLayout *L, const QbGate *gates, int64_t ngates, std::ve
       continue;
     }
     if (nondiagonal(g.kind) && L->perm[size_t(g.target)] >= nl) {
-      static const bool no_relabel = getenv("QCC_B200_NO_RELABEL") != nullptr;
-      if (is_plain_x(g) && !no_relabel) {   // x on a sharded qubit: relabel the rank bit, move nothing
+      if (is_plain_x(g) && relabel_enabled()) {   // x on a sharded qubit: relabel the rank bit, move nothing
         L->flip ^= 1u << (L->perm[size_t(g.target)] - nl);
         cur.retired += 1;
         continue;
       }
-      const int victim = choose_victim(*L, gates, ngates, i, seg_start);
-      const int64_t j = L->hoist ? hoist_point(*L, gates, seg_start, i, victim) : i;
+      int victim = 0;
+      int64_t j = i;
+      choose_victim(*L, gates, ngates, i, seg_start, &victim, &j);
+      std::vector<std::pair<int, int>> pairs{{L->perm[size_t(g.target)], victim}};
+      if (L->prefetch) add_prefetch_pairs(*L, gates, ngates, j, &pairs);
       if (j < i) {   // undo what the open step holds of gates j .. i-1; they are lowered again below
         const Mark &mk = marks[size_t(j - seg_start)];
         cur.gates.resize(mk.ngates);
         cur.retired = mk.retired;
         L->flip = mk.flip;
       }
-      exchange_bits(L, L->perm[size_t(g.target)], victim, &cur, steps);
+      exchange_event(L, pairs, &cur, steps);
       seg_start = j;
       marks.clear();
       i = j - 1;     // resume at gate j under the new layout (gate i itself now finds its target local)
@@ -265,8 +326,12 @@ std::string steps_to_json(const ShardLayout &L, const std::vector<ShardStep> &st
     const ShardStep &st = steps[k];
     if (k) s += ",";
     if (st.kind == 1) {
-      snprintf(buf, sizeof buf, "{\"kind\":1,\"rank_bit\":%d,\"victim\":%d}", st.rank_bit, st.victim);
-      s += buf;
+      s += "{\"kind\":1,\"pairs\":[";
+      for (size_t j = 0; j < st.rank_bits.size(); ++j) {
+        snprintf(buf, sizeof buf, "%s[%d,%d]", j ? "," : "", st.rank_bits[j], st.victims[j]);
+        s += buf;
+      }
+      s += "]}";
       continue;
     }
     snprintf(buf, sizeof buf, "{\"kind\":0,\"retired\":%lld,\"gates\":[", (long long)st.retired);

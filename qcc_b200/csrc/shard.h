@@ -33,12 +33,16 @@ namespace qb {
 
 struct ShardStep {
   // kind 0: run `gates` (physical LOCAL bits, ready for plan_gates / launch_gate) on the shard
-  // kind 1: exchange -- swap physical global bit nl + rank_bit with local bit `victim`
+  // kind 1: exchange EVENT -- for every k, swap physical global bit nl + rank_bits[k] with local bit
+  //         victims[k].  The pairs of one event are disjoint, so the event is one bit permutation of the
+  //         distributed index: executed as ONE all-to-all (each rank keeps 2^-k of its shard and sends
+  //         2^-k to each of the 2^k - 1 ranks that differ from it in those rank bits) by the push
+  //         exchange of engine.cu, or pair after pair by the in-place / NCCL exchanges.
   int kind = 0;
   std::vector<QbGate> gates;
   int64_t retired = 0;   // logical gate records this step accounts for (incl. skipped ones)
-  int rank_bit = 0;
-  int victim = 0;
+  std::vector<int> rank_bits;
+  std::vector<int> victims;
 };
 
 struct ShardLayout {
@@ -57,6 +61,11 @@ struct ShardLayout {
   // is long done); off with NCCL's narrow one.
   int hoist = 0;
   int pass_targets = 9;
+  // prefetch = 1: an event also brings in every other sharded qubit that is needed (as a mixing target)
+  // before the local qubit it would evict -- the all-to-all moves 1 - 2^-k of a shard for k bits, so the
+  // extra bits are nearly free, whereas a separate event later costs another half shard.  Only with the
+  // push exchange; the pairwise exchanges pay half a shard per bit either way.
+  int prefetch = 0;
 };
 
 // Victims are taken from the top `kVictimWindow` local bits so that the exchanged half

@@ -76,8 +76,10 @@ def _worker(rank, world, port, n, out_dir):
       dist.broadcast_object_list(ids, src=0)
       s = _cabi.DeviceState(n, 0, rank, rank=rank, nranks=world, comm_id=ids[0])
       s.set_fusion(fusion)
+      mode = s.exchange_mode()
       for name, stream in _streams(n).items():
         psi0 = random_state(n, 21)
+        ex_before = s.counters()["exchanges"]
         s.set_basis(0)                       # resets the bit permutation
         s.copy_in(psi0[rank << nl:(rank + 1) << nl])
         s.xg_apply_gates(_cabi.pack_xg_gates(stream))
@@ -89,9 +91,8 @@ def _worker(rank, world, port, n, out_dir):
         pb = [s.prob_bit(b) for b in (0, nl - 1, n - 1)]
         lay = s.layout()
         ex = s.counters()["exchanges"]
-        s.canonicalize()
+        shard = s.copy_out()                 # undoes the bit remap (collective) before copying
         assert s.layout()["perm"] == list(range(n))
-        shard = s.copy_out()
         err = float(np.abs(shard - want[rank << nl:(rank + 1) << nl]).max())
         wi = int(np.argmax(np.abs(want) ** 2))
         ii = np.arange(1 << n)
@@ -99,8 +100,18 @@ def _worker(rank, world, port, n, out_dir):
               abs(amp - want[12345 % (1 << n)]) < 1e-12 and
               all(abs(v - float(np.sum(np.abs(want[(ii >> b) & 1 == 1]) ** 2))) < 1e-12
                   for v, b in zip(pb, (0, nl - 1, n - 1))))
+        ex0 = s.counters()["exchanges"]
+        if name == "qft":
+          # three more QFTs queued into ONE flush: events hoisted to pass boundaries across the repetitions
+          s.copy_in(psi0[rank << nl:(rank + 1) << nl])
+          for _ in range(3):
+            s.xg_apply_gates(_cabi.pack_xg_gates(stream))
+          w3 = psi0.copy()
+          for _ in range(3):
+            w3 = oracle.c_run(w3, n, stream)
+          err = max(err, float(np.abs(s.copy_out() - w3[rank << nl:(rank + 1) << nl]).max()))
         with open(os.path.join(out_dir, f"{name}_{int(fusion)}_{rank}.txt"), "w") as f:
-          f.write(f"{err} {int(ok)} {ex} {lay['perm']}")
+          f.write(f"{err} {int(ok)} {ex - ex_before} {mode} {lay['perm']}")
       s.close()
     dist.barrier()
   finally:
@@ -108,21 +119,25 @@ def _worker(rank, world, port, n, out_dir):
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("exchange", ["nccl", "peer"])
+@pytest.mark.parametrize("exchange", ["push", "swap", "nccl"])
 def test_sharded_state_matches_oracle(world, exchange, tmp_path, monkeypatch):
-  """exchange = "peer": QCC_B200_PEER_SWAP=1 -- the pair exchange as ONE kernel swapping the two half
-  shards in place through CUDA IPC peer mappings (falls back to NCCL send/recv, on every rank alike,
-  where the mapping is unavailable)."""
+  """QCC_B200_EXCHANGE: "push" (default) -- double-buffered state, an exchange event of any number of
+  (sharded bit, local bit) pairs is ONE all-to-all written through CUDA IPC peer mappings by the store
+  stage of the fused pass before it; "swap" -- one in-place kernel per pair over the same mappings;
+  "nccl" -- ncclSend/ncclRecv per pair (also what the other two fall back to, on every rank alike, where
+  the mappings are unavailable)."""
   if _ngpus() < world:
     pytest.skip(f"needs {world} GPUs")
   import torch.multiprocessing as mp
-  monkeypatch.setenv("QCC_B200_PEER_SWAP", "1" if exchange == "peer" else "0")   # inherited by the workers
+  monkeypatch.setenv("QCC_B200_EXCHANGE", exchange)   # inherited by the workers
   n = 18
   mp.spawn(_worker, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
   for name in ("qft", "random", "larose"):
     for fusion in (1, 0):
       for r in range(world):
-        err, ok, ex, perm = open(tmp_path / f"{name}_{fusion}_{r}.txt").read().split(" ", 3)
+        err, ok, ex, mode, perm = open(tmp_path / f"{name}_{fusion}_{r}.txt").read().split(" ", 4)
         assert float(err) <= 1e-12 and ok == "1", (name, fusion, r, err, ok, perm)
-      if name == "qft":
-        assert int(ex) == int(math.log2(world))
+        assert mode == exchange, f"asked for the {exchange} exchange, the ranks agreed on {mode}"
+      if name == "qft":   # every sharded qubit comes in exactly once: ONE event when the push exchange sees the
+        # whole stream, else one exchange per sharded qubit
+        assert int(ex) == (1 if exchange == "push" and fusion else int(math.log2(world)))

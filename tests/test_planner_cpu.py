@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
   for name in declared:
     assert hasattr(L, name), f"{name} declared in qcc_b200.h but not exported"
   assert declared == set(_cabi.PROTOTYPES), "ctypes prototypes out of sync with the header"
-  assert L.qb_abi_version() == 1
+  assert L.qb_abi_version() == 2
 
 
 def test_no_gpu_means_loud_failure(has_gpu):

@@ -102,18 +102,19 @@ def _worker(rank, world, port, n, out_dir):
               assert g["ctl_mask"] < (1 << nl) and g["target"] < nl
               apply_masked(shard, nl, g["ctl_mask"], g["target"], m)
             continue
-          k, v = st["rank_bit"], st["victim"]
-          b = (rank >> k) & 1
-          partner = rank ^ (1 << k)
-          sel = 0 if b else 1
-          run, nruns = 1 << v, 1 << (nl - 1 - v)
-          view = shard.reshape(nruns, 2, run)
-          send = torch.from_numpy(np.ascontiguousarray(view[:, sel, :]).view(np.float64))
-          recv = torch.empty_like(send)
-          reqs = [dist.isend(send, partner), dist.irecv(recv, partner)]
-          for r in reqs:
-            r.wait()
-          view[:, sel, :] = recv.numpy().view(np.complex128).reshape(nruns, run)
+          assert len({k for k, _ in st["pairs"]}) == len(st["pairs"]) == len({v for _, v in st["pairs"]})
+          for k, v in st["pairs"]:   # the pairs of an event are disjoint: one after the other == all at once
+            b = (rank >> k) & 1
+            partner = rank ^ (1 << k)
+            sel = 0 if b else 1
+            run, nruns = 1 << v, 1 << (nl - 1 - v)
+            view = shard.reshape(nruns, 2, run)
+            send = torch.from_numpy(np.ascontiguousarray(view[:, sel, :]).view(np.float64))
+            recv = torch.empty_like(send)
+            reqs = [dist.isend(send, partner), dist.irecv(recv, partner)]
+            for r in reqs:
+              r.wait()
+            view[:, sel, :] = recv.numpy().view(np.complex128).reshape(nruns, run)
         if not canon:
           assert retired == len(gates)
         # gather shards on rank 0 and undo the bit permutation
@@ -135,33 +136,41 @@ def _worker(rank, world, port, n, out_dir):
           want = run_bits(psi0.copy(), n, gates)
           err = float(np.abs(got - want).max())
           with open(os.path.join(out_dir, f"{name}_{int(canon)}.txt"), "w") as f:
-            f.write(f"{err} {sum(1 for s in plan['steps'] if s['kind'] == 1)} {flip}")
+            f.write(f"{err} {sum(len(s['pairs']) for s in plan['steps'] if s['kind'] == 1)} {flip} "
+                    f"{sum(1 for s in plan['steps'] if s['kind'] == 1)}")
     dist.barrier()
   finally:
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n,window,hoist", [(2, 9, None, 0), (4, 10, None, 0), (4, 10, 30, 0), (4, 10, 30, 1),
-                                                  (2, 12, 30, 1)])
-def test_sharded_lowering_over_gloo(world, n, window, hoist, tmp_path, monkeypatch):
-  """window = 30: the victim window of the peer-swap exchange (any local bit), QCC_B200_VICTIM_WINDOW;
-  hoist = 1: exchanges moved back to pass boundaries (QCC_B200_HOIST), gates in between lowered again."""
+@pytest.mark.parametrize("world,n,window,hoist,prefetch",
+                         [(2, 9, None, 0, 0), (4, 10, None, 0, 0), (4, 10, 30, 0, 0), (4, 10, 30, 1, 0), (2, 12, 30, 1, 0),
+                          (4, 10, 7, 1, 1), (8, 12, 9, 1, 1), (4, 13, 10, 0, 1)])
+def test_sharded_lowering_over_gloo(world, n, window, hoist, prefetch, tmp_path, monkeypatch):
+  """window: the victim window of the peer-memory exchanges (any local bit above the lowest few),
+  QCC_B200_VICTIM_WINDOW; hoist = 1: exchanges moved back to pass boundaries (QCC_B200_HOIST), gates in
+  between lowered again; prefetch = 1: multi-bit events (QCC_B200_PREFETCH), the push exchange's setting."""
   import torch.multiprocessing as mp
   if window:
     monkeypatch.setenv("QCC_B200_VICTIM_WINDOW", str(window))
   if hoist:
     monkeypatch.setenv("QCC_B200_HOIST", "1")
+  if prefetch:
+    monkeypatch.setenv("QCC_B200_PREFETCH", "1")
   port = _free_port()
   mp.spawn(_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
   flips_seen = 0
   for name in ("qft", "random", "larose", "xlayers"):
     for canon in (1, 0):
-      err, nex, flip = open(tmp_path / f"{name}_{canon}.txt").read().split()
+      err, nex, flip, nev = open(tmp_path / f"{name}_{canon}.txt").read().split()
       assert float(err) <= 1e-12, (name, canon, err)
       flips_seen += int(flip) != 0
   assert flips_seen > 0   # the x layers leave relabelled rank bits behind (uncanonicalised run)
-  # QFT touches each sharded bit as a non-diagonal target exactly once: one exchange per global bit
+  # QFT touches each sharded bit as a non-diagonal target exactly once: one exchanged pair per global bit,
+  # and with prefetch all of them travel in ONE event
   assert int(open(tmp_path / "qft_0.txt").read().split()[1]) == int(math.log2(world))
+  if prefetch:
+    assert int(open(tmp_path / "qft_0.txt").read().split()[3]) == 1
 
 
 def test_lowering_is_identical_in_structure_on_every_rank():
@@ -169,7 +178,7 @@ def test_lowering_is_identical_in_structure_on_every_rank():
   n, world = 10, 4
   gates = _circuits(n)["random"]
   plans = [json.loads(_cabi.shard_lower_json(n, world, r, gates, canonicalize=True)) for r in range(world)]
-  shape = lambda p: [(s["kind"], s.get("rank_bit"), s.get("victim")) for s in p["steps"]]
+  shape = lambda p: [(s["kind"], s.get("pairs")) for s in p["steps"]]
   assert all(shape(p) == shape(plans[0]) for p in plans)
   assert all(p["perm"] == plans[0]["perm"] and p["flip"] == plans[0]["flip"] for p in plans)
 
@@ -200,6 +209,32 @@ def test_hoisted_exchange_keeps_sharded_qft_at_three_passes(monkeypatch):
 
   assert passes({}) == (4, 1)
   assert passes({"QCC_B200_VICTIM_WINDOW": "30", "QCC_B200_HOIST": "1"}) == (3, 1)
+
+
+def test_push_event_destinations_equal_pairwise_exchanges():
+  """The push exchange (engine.cu event_map / kernels.h push_apply, through qb_shard_event_dest) writes every
+  amplitude of every rank straight to its place after the event.  That must be the permutation the pairs
+  of the event produce when exchanged one after the other the send/recv way, and a bijection."""
+  from qcc_b200 import _cabi
+  rng = np.random.default_rng(7)
+  for world, nl, pairs in [(2, 6, [(0, 4)]), (4, 7, [(1, 5)]), (4, 7, [(0, 3), (1, 6)]), (8, 8, [(2, 7), (0, 4)]),
+                           (8, 9, [(1, 3), (2, 8), (0, 5)])]:
+    full = rng.normal(size=world << nl) + 1j * rng.normal(size=world << nl)
+    shards = [full[r << nl:(r + 1) << nl].copy() for r in range(world)]
+    want = [x.copy() for x in shards]
+    for k, v in pairs:
+      nxt = [x.copy() for x in want]
+      run, nruns = 1 << v, 1 << (nl - 1 - v)
+      for r in range(world):
+        sel = 0 if (r >> k) & 1 else 1
+        nxt[r].reshape(nruns, 2, run)[:, sel, :] = want[r ^ (1 << k)].reshape(nruns, 2, run)[:, 1 - sel, :]
+      want = nxt
+    got = np.full(world << nl, np.nan + 0j)
+    for r in range(world):
+      dest = _cabi.shard_event_dest(nl, world, r, pairs, np.arange(1 << nl))
+      assert np.isnan(got[dest]).all()
+      got[dest] = shards[r]
+    assert np.array_equal(got, np.concatenate(want)), (world, nl, pairs)
 
 
 def test_pair_swap_index_math_equals_send_recv_layout():
