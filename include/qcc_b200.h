@@ -176,6 +176,9 @@ int qb_get_amplitude(qb_state *s, uint64_t index, double out[2]);
 int qb_norm2(qb_state *s, double *out);                       /* sum |psi_i|^2 */
 int qb_argmax(qb_state *s, uint64_t *index, double *prob);    /* state.py:60-78 */
 int qb_prob_bit(qb_state *s, int bit, double *p_one);         /* P(bit == 1) */
+/* sum of |psi_i|^2 over the indices whose `bit` equals `value`: trace(P rho) of ops.py:426-460 for the
+ * projector onto that value, computed directly (no 1 - p cancellation; states need not be normalised) */
+int qb_prob_bit_value(qb_state *s, int bit, int value, double *p);
 /* Sparse listing for print_qureg: every index with |psi|^2 >= threshold, ascending
  * index order.  *count receives the total number found; if it exceeds cap, an unspecified
  * subset of `cap` entries is stored (retry with a larger cap).  labels/amps may be NULL

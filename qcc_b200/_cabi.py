@@ -85,6 +85,7 @@ PROTOTYPES = {
     "qb_norm2": [_P, _DP],
     "qb_argmax": [_P, ctypes.POINTER(_U64), _DP],
     "qb_prob_bit": [_P, _I, _DP],
+    "qb_prob_bit_value": [_P, _I, _I, _DP],
     "qb_list_above": [_P, ctypes.c_double, _U64, _P, _P, ctypes.POINTER(_U64)],
     "qb_host_apply1": [_P, _P, _I, _I, _I, _I],
     "qb_host_applyc": [_P, _P, _I, _I, _I, _I, _I],
@@ -145,6 +146,34 @@ def pack_xg_gates(gates) -> ctypes.Array:
     for j in range(8):
       arr[k].m[j] = flat[j]
   return arr
+
+
+# qb_xg_gate as a numpy record: 4 x int32 + 4 x complex128 = 80 bytes, no padding
+XG_DTYPE = np.dtype([("kind", np.int32), ("ctl", np.int32), ("tgt", np.int32), ("pad", np.int32),
+                     ("m", np.complex128, (4,))])
+assert XG_DTYPE.itemsize == ctypes.sizeof(qb_xg_gate) == 80
+
+
+class GateBuffer:
+  """Host-side batch of gate records in the ABI's layout: the python face appends here (a few numpy
+  stores per gate) and hands the whole batch to qb_xg_apply_gates in ONE foreign call, instead of one
+  ctypes call + matrix conversion per gate."""
+
+  def __init__(self, cap: int = 8192):
+    self.cap = cap
+    self.arr = np.zeros(cap, dtype=XG_DTYPE)
+    self.kind, self.ctl, self.tgt, self.m = self.arr["kind"], self.arr["ctl"], self.arr["tgt"], self.arr["m"]
+    self.n = 0
+
+  def append(self, kind: int, ctl: int, tgt: int, gate) -> bool:
+    """Returns True when the buffer is full and must be handed over."""
+    k = self.n
+    self.kind[k] = kind
+    self.ctl[k] = ctl
+    self.tgt[k] = tgt
+    self.m[k] = np.asarray(gate, dtype=np.complex128).reshape(4)
+    self.n = k + 1
+    return self.n == self.cap
 
 
 def pack_gates(gates) -> ctypes.Array:
@@ -297,6 +326,12 @@ class DeviceState:
   def xg_apply_gates(self, packed):
     check(lib().qb_xg_apply_gates(self._h, packed, len(packed)))
 
+  def xg_apply_buffer(self, buf: "GateBuffer"):
+    """Hand over (and empty) a GateBuffer."""
+    if buf.n:
+      n, buf.n = buf.n, 0
+      check(lib().qb_xg_apply_gates(self._h, ctypes.cast(buf.arr.ctypes.data, ctypes.POINTER(qb_xg_gate)), n))
+
   # -- sharding
   def layout(self) -> dict:
     nl, r, nr = _I(), _I(), _I()
@@ -345,6 +380,11 @@ class DeviceState:
   def prob_bit(self, bit: int) -> float:
     out = ctypes.c_double()
     check(lib().qb_prob_bit(self._h, bit, ctypes.byref(out)))
+    return out.value
+
+  def prob_bit_value(self, bit: int, value: int) -> float:
+    out = ctypes.c_double()
+    check(lib().qb_prob_bit_value(self._h, bit, value, ctypes.byref(out)))
     return out.value
 
   def list_above(self, threshold: float, cap: int = 1 << 16):

@@ -53,6 +53,7 @@ class qc:
     self._tile_bits = tile_bits
     self._shard = dict(rank=rank, nranks=nranks, comm_id=comm_id)
     self._dev: Optional[_cabi.DeviceState] = None
+    self._gbuf = _cabi.GateBuffer()      # gate records not yet handed to the engine (see _queue)
     self._pending: List[Tuple[str, object, int]] = []   # ('basis', bits, n) | ('dense', vec, n)
 
     self.simple_gates = [
@@ -84,6 +85,7 @@ class qc:
       if self._dev is None:
         raise AssertionError("circuit has no qubits yet")
       return
+    self._flush_gates()      # queued gates act on the state as it is now, before it grows
     total = self.nbits
     if self._shard["nranks"] > 1 and not (self._dev is None and all(f[0] == "basis" for f in self._pending)):
       raise NotImplementedError("sharded circuits must be built from basis registers before the first gate")
@@ -117,8 +119,23 @@ class qc:
 
   @property
   def dev(self) -> _cabi.DeviceState:
+    """The engine handle, with every gate issued so far handed over (readouts, copies and direct
+    engine calls all come through here, so they observe all prior gates -- gates_jit.cc's protocol)."""
     self._materialize()
+    self._flush_gates()
     return self._dev
+
+  def _flush_gates(self) -> None:
+    if self._gbuf.n and self._dev is not None:
+      self._dev.xg_apply_buffer(self._gbuf)
+
+  def _queue(self, kind: int, ctl: int, tgt: int, gate) -> None:
+    """One gate record for the engine.  Records are batched on the host and cross the C ABI thousands at
+    a time (qb_xg_apply_gates); the engine queues and fuses them as before."""
+    if self._pending or self._dev is None:
+      self._materialize()
+    if self._gbuf.append(kind, ctl, tgt, gate):
+      self._flush_gates()
 
   @property
   def psi(self) -> state.DevicePsi:
@@ -132,6 +149,7 @@ class qc:
     if self._dev is not None:
       self._dev.close()
     self._pending = []
+    self._gbuf.n = 0          # gates queued for the state that is being replaced
     self._dev = self._new_device_state(n, 0)
     self._dev.copy_in(vec)
 
@@ -211,7 +229,7 @@ class qc:
         self.ir.single(name, idx, gate, val)
       if self.eager:
         assert idx < self.nbits, "Invalid qubit index"
-        self.dev.xg_apply1(idx, gate)
+        self._queue(1, 0, idx, gate)
 
   def applyc(self, gate, ctl, idx, name: str = None, *, val: float = None) -> None:  # circuit.py:199-215
     if isinstance(idx, state.Reg):
@@ -223,7 +241,7 @@ class qc:
       self.ir.controlled(name, ctl_qubit, idx, gate, val)
     if self.eager:
       assert idx < self.nbits, "Invalid qubit index"
-      self.dev.xg_applyc(ctl_qubit, idx, gate)
+      self._queue(2, ctl_qubit, idx, gate)
     self.x(ctl_qubit, by_0)
 
   def cx0(self, idx0: int, idx1: int) -> None:
@@ -298,8 +316,7 @@ class qc:
     """Probability of qubit `idx` being `tostate`; optionally project + renormalise.  The
     reference goes through a 4^n density matrix (ops.py:426-460); here it is one device
     reduction and, for the collapse, one diagonal gate diag(1/sqrt p, 0) on that qubit."""
-    p1 = self.psi.prob_of_qubit(idx)
-    prob = p1 if tostate == 1 else 1.0 - p1
+    prob = self.psi.weight_of_qubit(idx, 1 if tostate == 1 else 0)   # trace(P rho), computed directly
     if collapse:
       assert math.sqrt(max(prob, 0.0)) > 1e-10, "Measurement collapses to 0.0."
       s = 1.0 / math.sqrt(prob)
@@ -473,8 +490,8 @@ class qc:
       self.psi.dump("Current state")
 
   def sync(self) -> None:
-    if self._dev is not None:
-      self._dev.sync()
+    if self._dev is not None or self._pending:
+      self.dev.sync()
 
   def close(self) -> None:
     if self._dev is not None:

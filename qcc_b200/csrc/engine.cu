@@ -1011,27 +1011,30 @@ int qb_norm2(qb_state *s, double *out) {
   return QB_OK;
 }
 
-int qb_prob_bit(qb_state *s, int bit, double *p_one) {
-  if (!s || !p_one) return fail(QB_ERR_ARG, "null pointer");
+int qb_prob_bit_value(qb_state *s, int bit, int value, double *p) {
+  if (!s || !p) return fail(QB_ERR_ARG, "null pointer");
   if (bit < 0 || bit >= s->nq) return fail(QB_ERR_ARG, "bit out of range");
+  if (value != 0 && value != 1) return fail(QB_ERR_ARG, "bit value must be 0 or 1");
   QB(flush(s));
   {
     ProfScope ps(s, QB_KCLASS_AUX, double(s->len) * 8.0);
     const int pb = s->perm[size_t(bit)];
     if (pb < s->n) {
-      CU(qb::launch_prob_mask(s->psi, s->len, uint64_t(1) << pb, s->d_scalar, s->stream));
-    } else if (((uint32_t(s->rank) ^ s->flip) >> (pb - s->n)) & 1u) {
-      CU(qb::launch_norm2(s->psi, s->len, s->d_scalar, s->stream));  // the bit is 1 on this whole shard
+      CU(qb::launch_prob_mask(s->psi, s->len, uint64_t(1) << pb, uint64_t(value) << pb, s->d_scalar, s->stream));
+    } else if (int(((uint32_t(s->rank) ^ s->flip) >> (pb - s->n)) & 1u) == value) {
+      CU(qb::launch_norm2(s->psi, s->len, s->d_scalar, s->stream));  // the bit has this value on the whole shard
     } else {
       CU(cudaMemsetAsync(s->d_scalar, 0, sizeof(double), s->stream));
     }
   }
   s->cnt.kernel_launches += 1;
   QB(allreduce_scalar(s, s->d_scalar));
-  CU(cudaMemcpyAsync(p_one, s->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaMemcpyAsync(p, s->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
   CU(cudaStreamSynchronize(s->stream));
   return QB_OK;
 }
+
+int qb_prob_bit(qb_state *s, int bit, double *p_one) { return qb_prob_bit_value(s, bit, 1, p_one); }
 
 int qb_argmax(qb_state *s, uint64_t *index, double *prob) {
   if (!s || !index || !prob) return fail(QB_ERR_ARG, "null pointer");

@@ -201,12 +201,12 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_prob_mask(const double2 *__restrict__ psi, uint64_t n, uint64_t mask, double *out) {
+k_prob_mask(const double2 *__restrict__ psi, uint64_t n, uint64_t mask, uint64_t want, double *out) {
   __shared__ double part[kThreads / 32];
   double acc = 0.0;
   uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
   for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
-    if ((i & mask) == mask) {
+    if ((i & mask) == want) {
       double2 v = psi[i];
       acc += v.x * v.x + v.y * v.y;
     }
@@ -307,14 +307,14 @@ cudaError_t launch_scale(double2 *psi, uint64_t n, double f, cudaStream_t st) {
 }
 
 cudaError_t launch_norm2(const double2 *psi, uint64_t n, double *out, cudaStream_t st) {
-  return launch_prob_mask(psi, n, 0, out, st);
+  return launch_prob_mask(psi, n, 0, 0, out, st);
 }
 
-cudaError_t launch_prob_mask(const double2 *psi, uint64_t n, uint64_t mask, double *out,
+cudaError_t launch_prob_mask(const double2 *psi, uint64_t n, uint64_t mask, uint64_t want, double *out,
                              cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(out, 0, sizeof(double), st);
   if (e != cudaSuccess) return e;
-  k_prob_mask<<<stride_blocks(n), kThreads, 0, st>>>(psi, n, mask, out);
+  k_prob_mask<<<stride_blocks(n), kThreads, 0, st>>>(psi, n, mask, want, out);
   return cudaGetLastError();
 }
 

@@ -20,8 +20,8 @@ cudaError_t launch_fill_random(double2 *psi, uint64_t n, uint64_t index_offset, 
 cudaError_t launch_scale(double2 *psi, uint64_t n, double f, cudaStream_t st);
 // out: 1 double (sum |psi|^2), zeroed by the launcher
 cudaError_t launch_norm2(const double2 *psi, uint64_t n, double *out, cudaStream_t st);
-// out: 1 double = sum of |psi_i|^2 over i with (i & mask) == mask
-cudaError_t launch_prob_mask(const double2 *psi, uint64_t n, uint64_t mask, double *out,
+// out: 1 double = sum of |psi_i|^2 over i with (i & mask) == want
+cudaError_t launch_prob_mask(const double2 *psi, uint64_t n, uint64_t mask, uint64_t want, double *out,
                              cudaStream_t st);
 // Per-block partial argmax: blk_prob[b], blk_idx[b] for b < *nblocks_out; host finishes.
 int argmax_blocks();

@@ -103,6 +103,10 @@ class DevicePsi:
     """P(python qubit `qubit` == 1)."""
     return self._dev.prob_bit(self.nbits - 1 - qubit)
 
+  def weight_of_qubit(self, qubit: int, value: int) -> float:
+    """Sum of |amp|^2 over the basis states whose python qubit `qubit` equals `value` (not normalised)."""
+    return self._dev.prob_bit_value(self.nbits - 1 - qubit, value)
+
   def nonzero(self, threshold: float = 1e-12, cap: int = 1 << 16):
     """(index, amplitude) of every basis state with |amp|^2 >= threshold, ascending index."""
     labels, amps, total = self._dev.list_above(threshold, cap)

@@ -49,63 +49,73 @@ def hsweep(n: int):
   return [(1, 0, q, h) for q in range(n)]
 
 
-# supremacy.py:19-97 CZ patterns are data in the reference; the generator below follows the
-# same construction rule (supremacy.py:123-158, 208-240) on a caller-supplied pattern set.
-def supremacy(n: int, depth: int, seed: int = 0, patterns=None):
-  """Random circuit in the style of supremacy.py: layer 0 is h on every qubit; each later
-  layer places cz pairs from a random pattern and fills the rest by the rules of
-  supremacy.py:147-154 (after cz -> v or yroot at random, after that or h -> t); a final h
-  layer closes it (supremacy.py:156-158).  `patterns` is a list of per-qubit offsets like the
-  reference's; by default nearest-neighbour / +6 offsets (the two distances sim_circuit
-  handles, supremacy.py:234-239) are generated from the seed."""
-  rng = random.Random(seed)
-  if patterns is None:
-    patterns = []
-    for p in range(8):
-      pat = [0] * n
-      step = 1 if p % 2 == 0 else 6
-      i = (p // 2) % (2 * step)
-      while i + step < n:
-        pat[i] = step
-        i += 2 * step if step == 1 else (1 if (i + 1) % step else step + 1)
-      patterns.append(pat)
-  H, T, U, CZ, UNK = "h", "t", "u", "cz", None
-  state0 = [H] * n
-  states = [state0]
+# The eight CZ layouts of supremacy.py:53-97 on its 6 x 6 grid, one digit per qubit: 0 = no gate starts
+# here, d = a cz from this qubit to qubit + d (1: right neighbour, 6: the qubit below).  Constant data of the
+# reference's workload (configs[4]); the stream is only the reference's stream with this exact table.
+_ROW = "000000"
+SUPREMACY_PATTERNS = tuple([int(ch) for ch in txt] for txt in (
+    ("001000" "100010") * 3,
+    ("100010" "001000") * 3,
+    _ROW + "060606" + _ROW + "060606" + _ROW + _ROW,
+    _ROW + "606060" + _ROW + "606060" + _ROW + _ROW,
+    ("000100" "010000") * 3,
+    ("010000" "000100") * 3,
+    "606060" + _ROW + "060606" + _ROW + "606060" + _ROW,
+    "060606" + _ROW + "060606" + _ROW + "060606" + _ROW,
+))
+
+
+def supremacy_layers(n: int, depth: int, rng):
+  """The gate grid of supremacy.py:123-158 (build_circuit): depth + 1 layers of n marks ('h', 't', 'u',
+  'cz' or None).  One rng.randint(0, 7) per middle layer picks the pattern, exactly as the reference draws."""
+  layer = ["h"] * n
+  layers = [layer]
   for _ in range(depth - 1):
-    state1 = [UNK] * n
-    pat = patterns[rng.randint(0, len(patterns) - 1)]
+    nxt = [None] * n
+    pat = SUPREMACY_PATTERNS[rng.randint(0, 7)]
     for i in range(min(n, len(pat))):
-      if pat[i] != 0 and i + pat[i] < n and state1[i] is UNK and state1[i + pat[i]] is UNK:
-        state1[i] = (CZ, i + pat[i])
-        state1[i + pat[i]] = (CZ, -1)
+      if pat[i] and i + pat[i] < n:
+        nxt[i] = nxt[i + pat[i]] = "cz"
     for i in range(n):
-      is_cz = isinstance(state1[i], tuple)
-      was_cz = isinstance(state0[i], tuple)
-      if was_cz and not is_cz:
-        state1[i] = U
-      elif state0[i] == U and not is_cz:
-        state1[i] = T
-      elif state0[i] == H and not is_cz:
-        state1[i] = T
-    state0 = state1
-    states.append(state0)
-  states.append([H] * n)
+      if nxt[i] == "cz":
+        continue
+      if layer[i] == "cz":
+        nxt[i] = "u"
+      elif layer[i] in ("u", "h"):
+        nxt[i] = "t"
+    layer = nxt
+    layers.append(layer)
+  layers.append(["h"] * n)
+  return layers
+
+
+def supremacy(n: int, depth: int, seed: int = 0):
+  """The gate stream supremacy.py runs for --nbits n --depth depth after random.seed(seed): build_circuit
+  (supremacy.py:123-158) then the gate calls of sim_circuit (:208-240) -- layers 0 .. depth-1 (the closing h
+  layer is built but not simulated, :218), 'u' drawn as v or yroot by one more randint each, and cz marks
+  paired with the right neighbour and / or the qubit six further on, whichever also carries a mark (:234-239).
+  random.Random(seed) is the generator random.seed(seed) installs, so the draws are the reference's."""
+  rng = random.Random(seed)
+  layers = supremacy_layers(n, depth, rng)
   g = {k: np.asarray(v) for k, v in (("h", ops.Hadamard()), ("t", ops.Tgate()), ("v", ops.Vgate()),
                                      ("yroot", ops.Yroot()), ("z", ops.PauliZ()))}
   out = []
-  for s in states:
+  for d in range(depth):
+    s = list(layers[d])
     for i in range(n):
-      if s[i] is UNK:
+      if s[i] is None:
         continue
-      if s[i] == H:
-        out.append((1, 0, i, g["h"]))
-      elif s[i] == T:
-        out.append((1, 0, i, g["t"]))
-      elif s[i] == U:
+      if s[i] in ("h", "t"):
+        out.append((1, 0, i, g[s[i]]))
+      elif s[i] == "u":
         out.append((1, 0, i, g["v"] if rng.randint(0, 1) == 0 else g["yroot"]))
-      elif isinstance(s[i], tuple) and s[i][1] >= 0:
-        out.append((2, i, s[i][1], g["z"]))
+      else:
+        if i < n - 1 and s[i + 1] == "cz":
+          out.append((2, i, i + 1, g["z"]))
+          s[i + 1] = None
+        if i < n - 6 and s[i + 6] == "cz":
+          out.append((2, i, i + 6, g["z"]))
+          s[i + 6] = None
   return out
 
 

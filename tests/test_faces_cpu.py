@@ -80,6 +80,23 @@ def test_larose_and_composite_streams_match_the_reference():
     assert np.abs(np.asarray(m) - rm).max() < 1e-12
 
 
+@pytest.mark.parametrize("n,depth", [(10, 8), (12, 10)])
+def test_supremacy_stream_is_the_reference_stream(n, depth):
+  """workloads.supremacy(n, depth, seed) must emit, gate for gate, what supremacy.py's build_circuit +
+  sim_circuit (supremacy.py:123-158, 208-240) issue after random.seed(seed): the golden files hold the IR
+  the reference recorded for seed 0 (tests/golden/make_golden.py)."""
+  from qcc_b200 import workloads
+  z = load_golden(f"circ_supremacy_n{n}_d{depth}.npz")
+  got = workloads.supremacy(n, depth, seed=0)
+  assert len(got) == len(z["kind"])
+  for (kind, ctl, tgt, m), k, c, t, gm, name in zip(got, z["kind"], z["ctl"], z["tgt"], z["mats"], z["names"]):
+    assert kind == int(k) and tgt == int(t) and (kind == 1 or ctl == int(c)), name
+    assert np.array_equal(np.asarray(m).reshape(4), gm), name
+  # the pattern table: 8 layouts of the 6 x 6 grid, offsets 1 (right) and 6 (down) only
+  assert len(workloads.SUPREMACY_PATTERNS) == 8
+  assert all(len(p) == 36 and set(p) <= {0, 1, 6} for p in workloads.SUPREMACY_PATTERNS)
+
+
 def test_qft_swaps_inverse_qft_stream():
   qc = circuit.qc("qft9", eager=False)
   r = qc.reg(9, 0)
