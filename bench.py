@@ -171,7 +171,8 @@ def cpu_reference_sample(n, stream, budget_s=20.0, max_gates=8):
   psi[1] = 1.0
   psi[:] += 1.0 / (1 << (nn // 2 + 1))  # dense, so every pair does real arithmetic; also first-touches the pages
   t_total, done = 0.0, 0
-  for kind, c, t, m in stream[:max_gates]:
+  picks = [stream[(k * len(stream)) // max_gates] for k in range(max_gates)]   # spread over the whole stream
+  for kind, c, t, m in picks:
     if nn != n:  # remap qubit numbers into the smaller register
       t = min(t, nn - 1)
       c = min(c, nn - 1)
@@ -187,8 +188,8 @@ def cpu_reference_sample(n, stream, budget_s=20.0, max_gates=8):
     if t_total > budget_s:
       break
   gps = done / t_total * scale
-  desc = (f"first {done} gates of the stream with reference xgates (bit_width=128) on a dense "
-          f"{nn}-qubit numpy state, {t_total:.1f} s of CPU work, 1 thread")
+  desc = (f"{done} gates spread evenly over the {len(stream)}-gate stream with reference xgates (bit_width=128) on a "
+          f"dense {nn}-qubit numpy state, {t_total:.1f} s of CPU work, 1 thread")
   if nn != n:
     desc += f"; host RAM could not hold {n} qubits: scaled by 4^-{(n - nn) // 2} (time ~ 2^n)"
   return gps, desc
@@ -223,6 +224,58 @@ def cpu_reference_libq_sample(width=24, ngates=26):
                      f"of {t1 - t0:.2f} s; libq stops at 28 qubits and its time grows with 2^n")}
 
 
+def cpu_sweep(args):
+  """BASELINE.md section 4, steps 2-3, on this box's host cores (1 thread: the reference has no threading):
+  reference xgates (bit_width=128) per gate at n = 26 / 28 / 30 -- h on EVERY target position, cx with a near and
+  a far control -- and stock libq on the QFT IR at n <= 28 after a walsh.  One JSON line."""
+  from oracle import oracle
+  out = {"impl": "reference", "kind": "cpu_sweep", "host_cores": os.cpu_count(), "threads": 1, "xgates": [], "libq": []}
+  if not oracle.have_ref("libxgates.so"):
+    print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libxgates.so not built"}))
+    return
+  xg = oracle.RefXgates()
+  H = oracle.GATES["h"]
+  X = oracle.GATES["x"]
+  for n in args.sweep_qubits:
+    try:
+      psi = np.full(1 << n, 1.0 / np.sqrt(float(1 << n)), dtype=np.complex128)
+    except MemoryError:
+      out["xgates"].append({"qubits": n, "error": "host RAM"})
+      continue
+    xg.apply1(psi, H, n, 0)    # first touch
+    per_target = []
+    for t in range(n):
+      t0 = time.perf_counter()
+      xg.apply1(psi, H, n, t)
+      per_target.append(time.perf_counter() - t0)
+    cx = {}
+    for name, c, t in (("near control (ctl 1, tgt 0)", 1, 0), ("far control (ctl n-1, tgt 0)", n - 1, 0),
+                       ("far target (ctl 0, tgt n-1)", 0, n - 1)):
+      t0 = time.perf_counter()
+      xg.applyc(psi, X, n, c, t)
+      cx[name] = time.perf_counter() - t0
+    byts = 32.0 * (1 << n)
+    out["xgates"].append({
+        "qubits": n, "h_seconds_per_python_target": per_target,
+        "h_gates_per_s": n / sum(per_target), "h_gbs_algorithmic": byts * n / sum(per_target) / 1e9,
+        "h_slowest_s": max(per_target), "h_fastest_s": min(per_target),
+        "cx_seconds": cx, "cx_gbs_algorithmic": {k: byts / 2 / v / 1e9 for k, v in cx.items()}})
+    del psi
+  for width in args.sweep_libq:
+    r = cpu_reference_libq_sample(width=width, ngates=2 * width)
+    if r:
+      out["libq"].append(r)
+  # n = 32 / 34: no reference runs (xgates is int-indexed, libq stops at 28); the reference's own rule
+  # (supremacy.py:283-297): time ~ gates x bytes
+  base = next((x for x in out["xgates"] if x.get("qubits") == max(args.sweep_qubits) and "h_gates_per_s" in x), None)
+  if base:
+    out["extrapolated"] = {f"{m} qubits": {"h_gates_per_s": base["h_gates_per_s"] / 2 ** (m - base["qubits"]),
+                                          "rule": "time proportional to gates x bytes (supremacy.py:283-297), from "
+                                                  f"the {base['qubits']}-qubit measurement; NOT measured"}
+                           for m in (32, 34)}
+  print(json.dumps(out))
+
+
 def run_reference_arm(args, wl, stream):
   """--impl reference: the reference's own CPU implementation of the path, bounded sample per step."""
   rank = int(os.environ.get("RANK", "0"))
@@ -242,13 +295,19 @@ def run_reference_arm(args, wl, stream):
   xg.apply1(psi, stream[0][3], n, stream[0][2])
   probe = time.perf_counter() - t0
   per_step = max(1, min(len(stream), int(150.0 / max(probe, 1e-3) / max(total, 1))))
+  # The sample is STRIDED over the whole stream (stride coprime with its length), so that over the run the
+  # sampled gates have the stream's own mix of gate kinds and target positions -- xgates' cost per gate does not
+  # depend on the state, so the sampled rate is an unbiased estimate of the whole-stream rate.
+  stride = max(1, len(stream) // max(1, per_step * total))
+  while stride > 1 and np.gcd(stride, len(stream)) != 1:
+    stride -= 1
   pos = 0
 
   def step():
     nonlocal pos
     for _ in range(per_step):
       kind, c, t, m = stream[pos % len(stream)]
-      pos += 1
+      pos += stride
       if kind == 1:
         xg.apply1(psi, m, n, t)
       else:
@@ -261,8 +320,10 @@ def run_reference_arm(args, wl, stream):
     step()
   dt = time.perf_counter() - t0
   value = per_step * args.steps / dt
-  sample = (f"{per_step} consecutive gates of the {args.workload} stream per step on a dense {n}-qubit "
-            f"complex128 numpy state, reference xgates (src/lib/xgates.cc built -O3 -ffast-math), 1 thread")
+  sample = (f"{per_step} gates of the {args.workload} stream per step, taken every {stride}-th gate over the whole "
+            f"{len(stream)}-gate stream ({per_step * total} gates in the run, same kind / target mix as the stream), on "
+            f"a dense {n}-qubit complex128 numpy state, reference xgates (src/lib/xgates.cc built -O3 -ffast-math), "
+            f"1 thread; a full step of {len(stream)} gates would take ~{len(stream) / max(value, 1e-9) / 60:.0f} min here")
   print(json.dumps({
       "impl": "reference", "metric": "gate-applies/sec", "value": value, "unit": "gates/s",
       "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -275,55 +336,153 @@ def run_reference_arm(args, wl, stream):
   }))
 
 
+def _roofline_of(prof, shard_len, peak, peak_src):
+  """roofline block of the dominant compute kernel class of a profile (qb_profile_read)."""
+  names = {"apply1": "k_apply_u", "phase": "k_apply_phase", "fused": "k_fused_pass", "fused_push": "k_fused_pass (push store)"}
+  cand = [k for k in names if prof[k]["launches"]]
+  if not cand:
+    return None
+  dom = max(cand, key=lambda k: prof[k]["ms"])
+  d = prof[dom]
+  ach = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+  return {"bound": "hbm", "kernel": names[dom], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+          "traffic": None, "peak_source": peak_src, "launches": d["launches"], "avg_launch_ms": d["ms"] / d["launches"],
+          "algorithmic_bytes_per_launch": d["bytes"] / d["launches"],
+          "note": "per GPU: algorithmic bytes (32 B x shard amplitudes per sweep) / summed CUDA-event time of that "
+                  "kernel class on rank 0"}
+
+
 def run_algorithm(args):
-  """Whole-algorithm runs for the multi-GPU configs: wall + CUDA-event time of ONE execution."""
+  """Whole-algorithm runs of the multi-GPU configs (configs[3] grover-32 x 4, configs[4] supremacy-34 x 8):
+  ONE execution through the python circuit.qc surface (grover) / the packed stream (supremacy), timed by
+  wall clock (what the user waits for: gate dispatch, lowering, planning, kernels, readout) and by the
+  engine's CUDA events per kernel class (device time, roofline of the dominant kernel)."""
   rank = int(os.environ.get("RANK", "0"))
   world = int(os.environ.get("WORLD_SIZE", "1"))
   local_rank = int(os.environ.get("LOCAL_RANK", "0"))
   dist = None
-  comm_id = None
   from qcc_b200 import _cabi, circuit, workloads
+
+  def new_comm():
+    if world == 1:
+      return None
+    ids = [_cabi.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    return ids[0]
+
   if world > 1:
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    ids = [_cabi.comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(ids, src=0)
-    comm_id = ids[0]
   n = args.qubits or (32 if args.workload == "grover" else 34)
-  factory = lambda name: circuit.qc(name, device=local_rank, rank=rank, nranks=world, comm_id=comm_id)
+  peak, peak_src = hbm_peak()
+  factory = lambda name: circuit.qc(name, device=local_rank, rank=rank, nranks=world, comm_id=new_comm())
+  extra = {}
+  sampler = ClockSampler(local_rank)
+  sampler.start()
   t0 = time.perf_counter()
   if args.workload == "grover":
     nb = n // 2
     np.random.seed(0)
-    qc, bits = workloads.grover_circuit(nb, qc_factory=factory)
+    qc = factory("Grover")
+    prof_on = []
+
+    def fac(_name):
+      return qc
+
+    # the state exists after the first register + gate; profiling is switched on by a hook on materialisation
+    orig = qc._new_device_state
+
+    def hooked(*a, **k):
+      dev = orig(*a, **k)
+      dev.profile_enable(True)
+      prof_on.append(dev)
+      return dev
+
+    qc._new_device_state = hooked
+    qc, bits = workloads.grover_circuit(nb, qc_factory=fac, iterations=args.iterations or None)
     maxbits, maxprob = qc.psi.maxprob()
     check = {"marked": bits, "found": maxbits[:nb], "ok": maxbits[:nb] == bits, "maxprob": maxprob}
-    desc = f"grover.py circuit version, {nb} search bits, {n} qubits"
+    desc = (f"grover.py:124-168 (circuit version), {nb} search bits + 1 ancilla + {nb - 1} multi_control helpers = "
+            f"{n} qubits, np.random.seed(0)" + (f", {args.iterations} iterations" if args.iterations else ""))
   else:
     stream = workloads.supremacy(n, args.depth, seed=0)
+    packed = _cabi.pack_xg_gates(stream)
     qc = factory("supremacy")
     qc.reg(n, 0)
-    qc.dev.xg_apply_gates(_cabi.pack_xg_gates(stream))
+    qc.dev.profile_enable(True)
+    t0 = time.perf_counter()
+    qc.dev.timer_start()
+    qc.dev.xg_apply_gates(packed)
+    extra["device_ms_circuit"] = qc.dev.timer_stop()
+    wall_circuit = time.perf_counter() - t0
     norm = qc.psi.norm2()
-    check = {"norm2": norm, "ok": abs(norm - 1.0) < 1e-9}
-    desc = f"supremacy.py-style random circuit, {n} qubits, depth {args.depth}, seed 0"
+    amp0 = qc.psi[0]
+    # full-size property: the circuit followed by its inverse (reversed stream, adjoint matrices) is the
+    # identity -- every pass, exchange event and relabel of the forward run has to be undone exactly
+    inv = [(k, c, t, np.conj(np.asarray(m).reshape(2, 2)).T) for k, c, t, m in reversed(stream)]
+    qc.dev.xg_apply_gates(_cabi.pack_xg_gates(inv))
+    back = qc.psi[0]
+    norm_back = qc.psi.norm2()
+    check = {"norm2": norm, "amp0_after_circuit": [amp0.real, amp0.imag],
+             "amp0_after_circuit_then_inverse": [back.real, back.imag], "norm2_after_inverse": norm_back,
+             "ok": abs(norm - 1.0) < 1e-9 and abs(back - 1.0) < 1e-9 and abs(norm_back - 1.0) < 1e-9}
+    extra["wall_s_circuit"] = wall_circuit
+    desc = (f"supremacy.py build_circuit + sim_circuit gate stream (supremacy.py:123-158, 208-240), {n} qubits, "
+            f"depth {args.depth}, random.seed(0): {len(stream)} gates; then the inverse stream as a check")
   qc.sync()
   wall = time.perf_counter() - t0
+  clocks = sampler.summary()
   c = qc.dev.counters()
+  prof = qc.dev.profile_read(reset=True)
+  mode = qc.dev.exchange_mode()
+  nl = n - int(np.log2(world))
+  device_ms = sum(v["ms"] for v in prof.values())
+  # parity of the sharded engine against a single GPU on the same seeded generator at a size one GPU holds
+  parity = None
+  if args.workload == "supremacy" and args.check_qubits and world > 1:
+    m = min(args.check_qubits, n)
+    st = workloads.supremacy(m, args.depth, seed=0)
+    pk = _cabi.pack_xg_gates(st)
+    qs = circuit.qc("check", device=local_rank, rank=rank, nranks=world, comm_id=new_comm())
+    qs.reg(m, 0)
+    qs.dev.xg_apply_gates(pk)
+    rng = np.random.default_rng(5)
+    idx = [int(x) for x in rng.integers(0, 1 << m, size=48)] + [0, (1 << m) - 1]
+    got = np.array([qs.psi[i] for i in idx])
+    ex_events = qs.dev.counters()["exchanges"]
+    qs.close()
+    if rank == 0:
+      with _cabi.DeviceState(m, 0, local_rank) as one:
+        one.xg_apply_gates(pk)
+        want = np.array([one.amplitude(i) for i in idx])
+      err = float(np.abs(got - want).max())
+      parity = {"qubits": m, "sampled_amplitudes": len(idx), "max_abs_err_vs_single_gpu": err, "ok": err <= 1e-10,
+                "exchange_events": ex_events, "gates": len(st)}
   if dist is not None:
     dist.barrier()
   if rank == 0:
+    gates = c["gates_applied"]
     print(json.dumps({
-        "metric": "gate-applies/sec", "value": c["gates_applied"] / wall, "unit": "gates/s", "n_gpus": world,
+        "metric": "gate-applies/sec", "value": gates / wall, "unit": "gates/s", "n_gpus": world,
         "steps": 1, "warmup": 0, "ms_per_step": wall * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "desc": desc, "qubits": n,
-                   "parallelism": f"state sharded over {world} GPUs" if world > 1 else "1 GPU",
-                   "timing": "wall clock of one full run incl. python gate dispatch, planning and readout"},
-        "gates": c["gates_applied"], "passes": c["passes"], "gpu_launches": c["kernel_launches"],
-        "exchanges": c["exchanges"], "bytes_exchanged_per_rank": c["bytes_exchanged"], "check": check}))
+        "config": {"workload": args.workload, "desc": desc, "qubits": n, "shard_qubits": nl,
+                   "parallelism": f"state sharded over {world} GPUs, exchange mode {mode}" if world > 1 else "1 GPU",
+                   "timing": "value = gates / wall clock of the one full run incl. python gate dispatch, lowering, "
+                             "planning and readouts; device_ms = summed CUDA-event time of every kernel class on rank 0"},
+        "gates": gates, "passes": c["passes"], "gpu_launches": c["kernel_launches"],
+        "wall_s": wall, "device_ms": device_ms, "host_overhead_frac": 1.0 - device_ms * 1e-3 / wall if wall else None,
+        "kernel_ms": {k: v["ms"] for k, v in prof.items() if v["launches"]},
+        "kernel_launches": {k: v["launches"] for k, v in prof.items() if v["launches"]},
+        "roofline": _roofline_of(prof, 1 << nl, peak, peak_src),
+        "exchange": {"mode": mode, "events": c["exchanges"], "bytes_sent_per_rank": c["bytes_exchanged"],
+                     "fused_push_passes": prof["fused_push"]["launches"],
+                     "nvlink_gbs_per_direction_rank0":
+                         c["bytes_exchanged"] / ((prof["fused_push"]["ms"] + prof["exchange"]["ms"]) * 1e-3) / 1e9
+                         if (prof["fused_push"]["ms"] + prof["exchange"]["ms"]) > 0 else None} if world > 1 else None,
+        "check": check, "parity_vs_single_gpu": parity, "clocks": clocks, **extra}))
   qc.close()
   if dist is not None:
     dist.destroy_process_group()
@@ -336,6 +495,10 @@ def main():
   ap.add_argument("--warmup", type=int, default=3)
   ap.add_argument("--workload", default="qft30", choices=sorted(WORKLOADS) + list(ALGOS))
   ap.add_argument("--depth", type=int, default=20)
+  ap.add_argument("--iterations", type=int, default=0, help="grover: override the iteration count (debug)")
+  ap.add_argument("--check-qubits", type=int, default=28,
+                  help="supremacy on N > 1 GPUs: also run the generator at this size sharded AND on one GPU and "
+                       "compare sampled amplitudes (0 = skip)")
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   ap.add_argument("--qubits", type=int, default=0, help="override the workload's qubit count (debug)")
   ap.add_argument("--tile-bits", type=int, default=12)
@@ -343,12 +506,19 @@ def main():
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-e2e", action="store_true")
   ap.add_argument("--no-secondary", action="store_true")
+  ap.add_argument("--cpu-sweep", action="store_true",
+                  help="reference CPU baselines of BASELINE.md section 4 (xgates per target at 26/28/30 qubits, libq "
+                       "on the QFT IR): host only, one JSON line")
+  ap.add_argument("--sweep-qubits", type=int, nargs="*", default=[26, 28, 30])
+  ap.add_argument("--sweep-libq", type=int, nargs="*", default=[22, 24, 26])
   ap.add_argument("--weak", action="store_true", help="N > 1: grow the state to n + log2(N) qubits")
   ap.add_argument("--flush-per-step", action="store_true",
                   help="flush the gate queue after every step instead of once at the end of the timed region "
                        "(sharded states: the lowering then cannot place exchange events across step boundaries)")
   args = ap.parse_args()
   args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+  if args.cpu_sweep:
+    return cpu_sweep(args)
   if args.workload in ALGOS:
     return run_algorithm(args)
   wl = dict(WORKLOADS[args.workload])

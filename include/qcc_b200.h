@@ -221,6 +221,13 @@ int qb_plan_json(int nqubits, const qb_gate *gates, int64_t ngates, int tile_bit
  * identity layout.  Host only: the CPU tests execute it with numpy shards + gloo send/recv. */
 int qb_shard_lower_json(int nqubits, int nranks, int rank, const qb_gate *gates, int64_t ngates,
                         int canonicalize, char *buf, size_t cap, size_t *needed);
+/* Counts only, same lowering + planning as a flush of these gates on rank `rank` (identity layout to start
+ * with): stats[0] exchange events, [1] exchanged (sharded bit, local bit) pairs, [2] passes, [3] of them fused
+ * passes, [4] events that ride on the store stage of a fused pass, [5] rounds, [6] ops.  window / hoist /
+ * prefetch are the lowering parameters (push exchange: nlocal - 5 capped at nlocal - 3, 1, 1; NCCL: 6, 0, 0).
+ * Host only. */
+int qb_shard_plan_stats(int nqubits, int nranks, int rank, const qb_gate *gates, int64_t ngates, int tile_bits,
+                        int window, int hoist, int prefetch, int64_t stats[8]);
 /* Where the push exchange of engine.cu writes: for one exchange event (npairs pairs: rank bit k <-> local
  * victim bit) and each local index of `rank`'s shard, the index in the DISTRIBUTED vector
  * (destination rank << nlocal | destination local index).  Host only; the CPU tests check it against the

@@ -64,6 +64,8 @@ PROTOTYPES = {
     "qb_state_exchange_mode": [_P, ctypes.POINTER(_I)],
     "qb_shard_lower_json": [_I, _I, _I, ctypes.POINTER(qb_gate), ctypes.c_int64, _I, ctypes.c_char_p,
                             ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)],
+    "qb_shard_plan_stats": [_I, _I, _I, ctypes.POINTER(qb_gate), ctypes.c_int64, _I, _I, _I, _I,
+                            ctypes.POINTER(ctypes.c_int64)],
     "qb_shard_event_dest": [_I, _I, _I, ctypes.POINTER(_I), ctypes.POINTER(_I), _I, _P, _P, ctypes.c_int64],
     "qb_state_destroy": [_P],
     "qb_state_nqubits": [_P, ctypes.POINTER(_I)],
@@ -209,6 +211,17 @@ def shard_lower_json(nqubits: int, nranks: int, rank: int, gates, canonicalize: 
   check(lib().qb_shard_lower_json(nqubits, nranks, rank, arr, len(arr), int(canonicalize), buf, need.value,
                                   ctypes.byref(need)))
   return buf.value.decode()
+
+
+def shard_plan_stats(nqubits: int, nranks: int, rank: int, gates, tile_bits: int = 12, mode: str = "push") -> dict:
+  """Events / pairs / passes a flush of `gates` (index-bit numbering) costs on one rank (host only)."""
+  arr = gates if isinstance(gates, ctypes.Array) else pack_gates(gates)
+  nl = nqubits - int(np.log2(nranks))
+  window, hoist, prefetch = {"push": (min(max(6, nl - 5), nl - 3), 1, 1), "swap": (max(6, nl - 5), 1, 0),
+                             "nccl": (6, 0, 0)}[mode]
+  st = (ctypes.c_int64 * 8)()
+  check(lib().qb_shard_plan_stats(nqubits, nranks, rank, arr, len(arr), tile_bits, window, hoist, prefetch, st))
+  return dict(zip(("events", "pairs", "passes", "fused_passes", "events_on_a_pass", "rounds", "ops"), st))
 
 
 def shard_event_dest(nlocal: int, nranks: int, rank: int, pairs, local: np.ndarray) -> np.ndarray:

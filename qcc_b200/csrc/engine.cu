@@ -1360,6 +1360,72 @@ int qb_shard_lower_json(int nqubits, int nranks, int rank, const qb_gate *gates,
   return QB_OK;
 }
 
+int qb_shard_plan_stats(int nqubits, int nranks, int rank, const qb_gate *gates, int64_t ngates, int tile_bits,
+                        int window, int hoist, int prefetch, int64_t stats[8]) {
+  if ((!gates && ngates) || !stats) return fail(QB_ERR_ARG, "null pointer");
+  if (nranks < 1 || (nranks & (nranks - 1)) || rank < 0 || rank >= nranks) return fail(QB_ERR_ARG, "bad rank/nranks");
+  int pbits = 0;
+  while ((1 << pbits) < nranks) ++pbits;
+  if (nqubits - pbits < 4 || nqubits > 40) return fail(QB_ERR_ARG, "nqubits out of range");
+  std::vector<QbGate> q;
+  q.reserve(size_t(ngates));
+  for (int64_t k = 0; k < ngates; ++k) {
+    const qb_gate &g = gates[k];
+    if (g.target < 0 || g.target >= nqubits || (g.ctl_mask >> g.target & 1) || (g.ctl_mask >> nqubits))
+      return fail(QB_ERR_ARG, "gate %lld: bad bits", (long long)k);
+    QbGate x;
+    x.ctl_mask = g.ctl_mask;
+    x.target = g.target;
+    x.kind = classify(g.m);
+    memcpy(x.m, g.m, sizeof x.m);
+    q.push_back(x);
+  }
+  for (int k = 0; k < 8; ++k) stats[k] = 0;
+  std::vector<qb::ShardStep> steps;
+  if (nranks > 1) {
+    qb::ShardLayout L;
+    L.n = nqubits;
+    L.nl = nqubits - pbits;
+    L.p = pbits;
+    L.rank = rank;
+    L.perm.resize(size_t(nqubits));
+    for (int b = 0; b < nqubits; ++b) L.perm[size_t(b)] = b;
+    L.window = std::max(1, std::min(window, L.nl));
+    L.hoist = hoist;
+    L.prefetch = prefetch;
+    L.pass_targets = std::max(1, tile_bits - QB_TILE_LOW);
+    qb::lower_for_rank(&L, q.data(), ngates, &steps);
+  } else {
+    qb::ShardStep st;
+    st.gates = q;
+    steps.push_back(st);
+  }
+  bool tail_fused = false;
+  for (const qb::ShardStep &st : steps) {
+    if (st.kind == 1) {
+      stats[0] += 1;
+      stats[1] += int64_t(st.rank_bits.size());
+      stats[4] += tail_fused ? 1 : 0;
+      tail_fused = false;
+      continue;
+    }
+    tail_fused = false;
+    if (st.gates.empty()) continue;
+    qb::Plan plan;
+    qb::plan_gates(nqubits - pbits, st.gates.data(), int64_t(st.gates.size()), tile_bits, &plan);
+    for (const qb::PlannedPass &pp : plan.passes) {
+      stats[2] += 1;
+      if (pp.single_gate < 0) {
+        stats[3] += 1;
+        stats[5] += int64_t(pp.rounds.size());
+        stats[6] += int64_t(pp.ops.size());
+      }
+    }
+    tail_fused = !plan.passes.empty() && plan.passes.back().single_gate < 0;
+  }
+  return QB_OK;
+}
+
 int qb_shard_event_dest(int nlocal, int nranks, int rank, const int *rank_bits, const int *victims, int npairs,
                         const uint64_t *local, uint64_t *dest, int64_t count) {
   if (!rank_bits || !victims || (!local && count) || (!dest && count)) return fail(QB_ERR_ARG, "null pointer");

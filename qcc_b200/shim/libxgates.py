@@ -33,6 +33,16 @@ from qcc_b200 import _cabi  # noqa: E402
 
 _lib = _cabi.lib()  # raises if the library has not been built
 _DEVICE = int(os.environ.get("QCC_B200_DEVICE", "-1"))
+_calls = {"apply1": 0, "applyc": 0}
+if os.environ.get("QCC_B200_SHIM_LOG"):   # tests: proof that the reference's gates came through here
+  import atexit
+  import json
+
+  def _write_log():
+    with open(os.environ["QCC_B200_SHIM_LOG"], "w") as f:
+      json.dump(_calls, f)
+
+  atexit.register(_write_log)
 
 
 def _check(psi, gate, nbits, bit_width):
@@ -48,6 +58,7 @@ def _check(psi, gate, nbits, bit_width):
 def apply1(psi, gate, nbits, tgt, bit_width):
   """Apply a single-qubit gate in place (xgates.cc:89-107)."""
   g = _check(psi, gate, nbits, bit_width)
+  _calls["apply1"] += 1
   rc = _lib.qb_host_apply1(psi.ctypes.data, g.ctypes.data, int(nbits), int(tgt), int(bit_width), _DEVICE)
   if rc == -1:
     raise ValueError(_lib.qb_last_error().decode())
@@ -58,6 +69,7 @@ def apply1(psi, gate, nbits, tgt, bit_width):
 def applyc(psi, gate, nbits, ctl, tgt, bit_width):
   """Apply a controlled single-qubit gate in place (xgates.cc:126-145)."""
   g = _check(psi, gate, nbits, bit_width)
+  _calls["applyc"] += 1
   rc = _lib.qb_host_applyc(psi.ctypes.data, g.ctypes.data, int(nbits), int(ctl), int(tgt), int(bit_width),
                            _DEVICE)
   if rc == -1:

@@ -3,6 +3,7 @@
   * libq C++ face (programs compiled against qcc_b200/libq/libq.h)
   * libxgates shim (the two callables the reference's circuit.py binds)
 Everything is compared to golden vectors recorded from the reference or to the oracle."""
+import json
 import math
 import os
 import re
@@ -378,3 +379,55 @@ def test_order_finding_python_face(number, a, order):
   assert all(order % r == 0 for r in rs) and math.lcm(*rs) == order
   assert pow(a, order, number) == 1
   qc.close()
+
+
+# ---------------------------------------------------------------------------------------
+# The UNMODIFIED reference over the libxgates shim: its own test file
+# and its supremacy.py, with PYTHONPATH = <reference tree>:<qcc_b200/shim>, so that circuit.py:36-41
+# binds OUR apply1 / applyc.  The tree is staged by __graft_entry__.build() under the git-ignored
+# baseline/_ref/qcc (it travels to the GPU box); /root/reference is used where it exists.
+# ---------------------------------------------------------------------------------------
+def _reference_tree():
+  for cand in ("/root/reference", os.path.join(ROOT, "baseline", "_ref", "qcc")):
+    if os.path.exists(os.path.join(cand, "src", "lib", "circuit_test.py")):
+      return cand
+  return None
+
+
+def _run_reference(script, args, tmp_path):
+  ref = _reference_tree()
+  log = str(tmp_path / "shim_calls.json")
+  env = dict(os.environ, PYTHONPATH=ref + os.pathsep + os.path.join(ROOT, "qcc_b200", "shim"),
+             QCC_B200_SHIM_LOG=log)
+  r = subprocess.run([sys.executable, os.path.join(ref, "src", script)] + args, cwd=ref, env=env,
+                     capture_output=True, text=True, timeout=900)
+  calls = json.load(open(log)) if os.path.exists(log) else None
+  return r, calls
+
+
+@pytest.mark.parametrize("width", [64, 128])
+def test_reference_circuit_test_passes_over_the_shim(width, tmp_path):
+  """src/lib/circuit_test.py (21 tests; :69-107 is the one that pins xgates against the Python definition,
+  negative controls included) run unchanged, every gate executed by the B200 through libxgates.py."""
+  if _reference_tree() is None:
+    pytest.skip("no reference tree staged (baseline/_ref/qcc)")
+  r, calls = _run_reference(os.path.join("lib", "circuit_test.py"), [f"--tensor_width={width}"], tmp_path)
+  out = r.stdout + r.stderr
+  assert r.returncode == 0, out[-3000:]
+  assert "Could not find 'libxgates.so'" not in out      # the reference did not fall back to Python
+  m = re.search(r"Ran (\d+) tests", out)
+  assert m and int(m.group(1)) >= 20 and "OK" in out, out[-2000:]
+  assert calls and calls["apply1"] > 100 and calls["applyc"] > 100, calls
+
+
+@pytest.mark.parametrize("width", [64, 128])
+def test_reference_supremacy_runs_over_the_shim(width, tmp_path):
+  """src/supremacy.py --nbits 20 (its default size) unchanged: build_circuit + sim_circuit, one shim call per gate."""
+  if _reference_tree() is None:
+    pytest.skip("no reference tree staged (baseline/_ref/qcc)")
+  r, calls = _run_reference("supremacy.py", ["--nbits=20", "--depth=12", f"--tensor_width={width}"], tmp_path)
+  out = r.stdout + r.stderr
+  assert r.returncode == 0, out[-3000:]
+  assert "Could not find 'libxgates.so'" not in out
+  assert "Estimated sim for FULL experiment" in out
+  assert calls and calls["apply1"] + calls["applyc"] > 100, calls

@@ -134,3 +134,87 @@ def test_larose_28_fused_equals_single_gate_path():
       y = b.copy_out(first, 1 << 16)
       assert np.abs(x - y).max() < 1e-12
     assert a.counters()["passes"] == 6 and b.counters()["passes"] == len(stream)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Whole-vector parity against the REFERENCE at 26 and 28 qubits: the unmodified src/lib/xgates.cc build
+# (oracle/_ref/libxgates.so, shipped to the GPU box) handles these sizes in a fraction of a second per gate;
+# the C restatement of the same loops (oracle.c_run) stands in where that build is absent.  At >= 2^14
+# tiles these are the sizes where 64-bit index arithmetic, the tile-number -> base scatter over several
+# runs of non-tile bits and the per-tile constants of ladders with many partners outside the tile can go
+# wrong without any small test noticing.
+# ---------------------------------------------------------------------------------------------------
+def _reference_run(psi, n, stream):
+  if oracle.have_ref("libxgates.so"):
+    return oracle.RefXgates().run(psi, n, stream), "reference xgates"
+  return oracle.c_run(psi, n, stream), "oracle restatement"
+
+
+def _interesting_qubits(n):
+  """python qubits whose index bits are 0-2 (inside every 128-byte run), 12-14 (around the tile edge at
+  K = 12), the middle and n-1 (the longest stride)."""
+  bits = [0, 1, 2, 12, 13, 14, n // 2 + 3, n - 2, n - 1]
+  return [n - 1 - b for b in bits]
+
+
+def _big_streams(n):
+  H, V, X = oracle.GATES["h"], oracle.GATES["v"], oracle.GATES["x"]
+  out = {}
+  # QFT blocks (circuit.py:320-326) on chosen pivots: h + the cu1 ladder to EVERY lower qubit, so the pivot on
+  # index bit 0 drags a ladder with n - 1 partners, most of them outside any tile
+  qft = []
+  for k, p in enumerate(sorted({n - 1, n - 3, n - 14, n // 2, 1}, reverse=True)):
+    qft.append((1, 0, p, H))
+    lower = list(reversed(range(p)))
+    if k:                                  # later pivots: nearest two partners, every third one, and the far end
+      lower = [j for i, j in enumerate(lower) if i < 2 or i % 3 == 0 or j < 2][:12]
+    for j in lower:
+      qft.append((2, p, j, oracle.u1(math.pi / 2 ** (p - j))))
+  out["qft_blocks"] = qft
+  # larose_benchmark.py:47-54 on a subset of the qubits (cx onto python qubit 0 = index bit n-1, controls anywhere)
+  lar = []
+  for bit in _interesting_qubits(n) + [5, 9]:
+    lar += [(1, 0, bit, H), (1, 0, bit, V)]
+    if bit:
+      lar.append((2, bit, 0, X))
+  out["larose_subset"] = lar
+  # random gates: targets from the interesting set, controls anywhere (mostly outside the tile)
+  rng = np.random.default_rng(n)
+  names = ["h", "v", "yroot", "t", "x", "y", "z", "s"]
+  rnd = []
+  tq = _interesting_qubits(n)
+  while len(rnd) < 36:
+    r = rng.random()
+    m = oracle.u1(float(rng.uniform(-3, 3))) if r < 0.25 else (
+        oracle.rotation([1.0, 0, 0], float(rng.uniform(-3, 3))) if r < 0.35 else oracle.GATES[names[rng.integers(len(names))]])
+    t = tq[int(rng.integers(len(tq)))]
+    if rng.random() < 0.4:
+      rnd.append((1, 0, t, m))
+    else:
+      c = int(rng.integers(n))
+      if c != t:
+        rnd.append((2, c, t, m))
+  out["random"] = rnd
+  return out
+
+
+@pytest.mark.parametrize("n,name,tile_bits", [(26, "qft_blocks", 12), (26, "qft_blocks", 7), (26, "larose_subset", 12),
+                                              (26, "random", 12), (26, "random", 10), (28, "qft_blocks", 12),
+                                              (28, "random", 12)])
+def test_whole_vector_matches_the_reference_at_26_and_28_qubits(n, name, tile_bits):
+  """tile_bits = 7 at 26 qubits gives the ladders 19 partner bits outside the tile (more than the 18 a
+  30-qubit QFT pass has at K = 12)."""
+  stream = _big_streams(n)[name]
+  rng = np.random.default_rng(100 + n)
+  psi0 = rng.standard_normal(1 << n) + 1j * rng.standard_normal(1 << n)
+  psi0 /= np.linalg.norm(psi0)
+  with _cabi.DeviceState(n) as s:
+    s.set_tile_bits(tile_bits)
+    s.copy_in(psi0)
+    s.xg_apply_gates(_cabi.pack_xg_gates(stream))
+    got = s.copy_out()
+    cnt = s.counters()
+  want, who = _reference_run(psi0, n, stream)      # in place: psi0 is the reference result now
+  err = float(np.abs(got - want).max())
+  assert err <= 1e-10, (n, name, tile_bits, who, err)
+  assert cnt["passes"] < len(stream)               # it did go through fused passes
