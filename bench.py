@@ -56,6 +56,8 @@ WORKLOADS = {
 
 def build_stream(name, n):
   from qcc_b200 import workloads
+  if name.startswith("supremacy"):
+    return workloads.supremacy(n, 20, seed=0)
   if name.startswith("qft"):
     return workloads.qft(n)
   if name.startswith("larose"):
@@ -488,6 +490,84 @@ def run_algorithm(args):
     dist.destroy_process_group()
 
 
+def run_matrix(args):
+  """--matrix qft:28,qft:30,supremacy:34,...: the north-star table (QFT and the supremacy.py random circuit at
+  28-34 qubits on N GPUs) in ONE process per rank -- one line of JSON per entry, same timing rules as the default
+  line (CUDA events on the engine's stream, max over ranks, K steps queued and flushed inside the timed region)."""
+  rank = int(os.environ.get("RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  dist = None
+  if world > 1:
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+  from qcc_b200 import _cabi
+  peak, peak_src = hbm_peak()
+  for entry in args.matrix.split(","):
+    name, n = entry.split(":")
+    n = int(n)
+    line = {"workload": name, "qubits": n, "n_gpus": world}
+    s = None
+    try:
+      stream = build_stream(name, n)
+      packed = _cabi.pack_xg_gates(stream)
+      comm_id = None
+      if world > 1:
+        ids = [_cabi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        comm_id = ids[0]
+      s = _cabi.DeviceState(n, 0, local_rank, rank=rank, nranks=world, comm_id=comm_id)
+      s.set_tile_bits(args.tile_bits)
+      s.fill_random(1234)
+      for _ in range(args.warmup):
+        s.xg_apply_gates(packed)
+      s.sync()
+      if dist is not None:
+        dist.barrier()
+      c0 = s.counters()
+      s.profile_enable(True)
+      s.profile_read(reset=True)
+      s.timer_start()
+      for _ in range(args.steps):
+        s.xg_apply_gates(packed)
+      ms = s.timer_stop()
+      prof = s.profile_read(reset=True)
+      s.profile_enable(False)
+      c1 = s.counters()
+      if dist is not None:
+        import torch
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+      norm = s.norm2()
+      sent = c1["bytes_exchanged"] - c0["bytes_exchanged"]
+      carrier = prof["fused_push"]["ms"] + prof["exchange"]["ms"]
+      nl = n - int(np.log2(world))
+      line.update({
+          "gates_per_step": len(stream), "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+          "value": len(stream) * args.steps / (ms * 1e-3), "unit": "gates/s", "shard_qubits": nl,
+          "passes_per_step": (c1["passes"] - c0["passes"]) / args.steps,
+          "achieved_gbs_swept_per_gpu": (c1["bytes_swept"] - c0["bytes_swept"]) / (ms * 1e-3) / 1e9,
+          "frac_of_hbm_roofline_per_gpu": (c1["bytes_swept"] - c0["bytes_swept"]) / (ms * 1e-3) / 1e9 / peak,
+          "roofline": _roofline_of(prof, 1 << nl, peak, peak_src),
+          "kernel_ms": {k: v["ms"] for k, v in prof.items() if v["launches"]},
+          "exchange": None if world == 1 else {
+              "mode": s.exchange_mode(), "events_per_step": (c1["exchanges"] - c0["exchanges"]) / args.steps,
+              "bytes_sent_per_rank_per_step": sent / args.steps,
+              "nvlink_gbs_per_direction_rank0": sent / (carrier * 1e-3) / 1e9 if carrier else None},
+          "norm2_after": norm})
+    except Exception as ex:  # pylint: disable=broad-except
+      line["error"] = str(ex)[:300]
+    if s is not None:
+      s.close()
+    if rank == 0:
+      print(json.dumps(line), flush=True)
+  if dist is not None:
+    dist.destroy_process_group()
+
+
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
@@ -506,6 +586,8 @@ def main():
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-e2e", action="store_true")
   ap.add_argument("--no-secondary", action="store_true")
+  ap.add_argument("--matrix", default="", help="comma list of workload:qubits entries, e.g. qft:28,supremacy:30 "
+                                               "(one JSON line each; see run_matrix)")
   ap.add_argument("--cpu-sweep", action="store_true",
                   help="reference CPU baselines of BASELINE.md section 4 (xgates per target at 26/28/30 qubits, libq "
                        "on the QFT IR): host only, one JSON line")
@@ -519,6 +601,8 @@ def main():
   args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
   if args.cpu_sweep:
     return cpu_sweep(args)
+  if args.matrix:
+    return run_matrix(args)
   if args.workload in ALGOS:
     return run_algorithm(args)
   wl = dict(WORKLOADS[args.workload])

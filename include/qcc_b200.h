@@ -131,8 +131,8 @@ int qb_state_create(int nqubits, uint64_t init_label, int device, qb_state **out
  * swapped with local ones: one all-to-all over NVLink peer memory written by the store stage of the
  * preceding fused pass; ncclSend/ncclRecv pair exchanges where peer mappings are unavailable) and a
  * logical->physical bit remap; diagonal gates and controls on sharded bits need no communication.  qb_copy_in/out address this rank's
- * slice of the canonical vector (they undo the bit remap first, collectively); qb_list_above lists
- * this rank's entries under their logical labels. */
+ * slice of the canonical vector (they undo the bit remap first, collectively); qb_list_above returns the
+ * same merged listing of the whole state on every rank. */
 int qb_comm_get_unique_id(void *id128);
 int qb_state_create_sharded(int nqubits, uint64_t init_label, int device, int rank, int nranks,
                             const void *id128, qb_state **out);
@@ -221,9 +221,15 @@ int qb_plan_json(int nqubits, const qb_gate *gates, int64_t ngates, int tile_bit
  * identity layout.  Host only: the CPU tests execute it with numpy shards + gloo send/recv. */
 int qb_shard_lower_json(int nqubits, int nranks, int rank, const qb_gate *gates, int64_t ngates,
                         int canonicalize, char *buf, size_t cap, size_t *needed);
+/* The queue's peephole, applied in place to a gate list (host only): every adjacent five-gate
+ * Sleator-Weinfurter run cu(a,t,V) cx(a,b) cu(b,t,V^dagger) cx(a,b) cu(b,t,V) -- how circuit.py:227-246 spells
+ * ccx / ccu / ccu1 -- becomes ONE doubly-controlled V^2 on t followed by four identity gates (so the gate count is
+ * kept).  *fused receives the number of runs replaced.  qb_flush does this before planning unless
+ * QCC_B200_NO_CCU_FUSE is set. */
+int qb_fuse_gates(qb_gate *gates, int64_t ngates, int64_t *fused);
 /* Counts only, same lowering + planning as a flush of these gates on rank `rank` (identity layout to start
  * with): stats[0] exchange events, [1] exchanged (sharded bit, local bit) pairs, [2] passes, [3] of them fused
- * passes, [4] events that ride on the store stage of a fused pass, [5] rounds, [6] ops.  window / hoist /
+ * passes, [4] events that ride on the store stage of a fused pass, [5] rounds, [6] ops, [7] Sleator-Weinfurter runs fused.  window / hoist /
  * prefetch are the lowering parameters (push exchange: nlocal - 5 capped at nlocal - 3, 1, 1; NCCL: 6, 0, 0).
  * Host only. */
 int qb_shard_plan_stats(int nqubits, int nranks, int rank, const qb_gate *gates, int64_t ngates, int tile_bits,

@@ -64,6 +64,7 @@ PROTOTYPES = {
     "qb_state_exchange_mode": [_P, ctypes.POINTER(_I)],
     "qb_shard_lower_json": [_I, _I, _I, ctypes.POINTER(qb_gate), ctypes.c_int64, _I, ctypes.c_char_p,
                             ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)],
+    "qb_fuse_gates": [ctypes.POINTER(qb_gate), ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)],
     "qb_shard_plan_stats": [_I, _I, _I, ctypes.POINTER(qb_gate), ctypes.c_int64, _I, _I, _I, _I,
                             ctypes.POINTER(ctypes.c_int64)],
     "qb_shard_event_dest": [_I, _I, _I, ctypes.POINTER(_I), ctypes.POINTER(_I), _I, _P, _P, ctypes.c_int64],
@@ -213,6 +214,15 @@ def shard_lower_json(nqubits: int, nranks: int, rank: int, gates, canonicalize: 
   return buf.value.decode()
 
 
+def fuse_gates(gates):
+  """The flush peephole on a list of (ctl_mask, target_bit, 2x2): returns (fused list, runs replaced)."""
+  arr = pack_gates(gates)
+  n = ctypes.c_int64(0)
+  check(lib().qb_fuse_gates(arr, len(arr), ctypes.byref(n)))
+  out = [(int(g.ctl_mask), int(g.target), np.array(list(g.m)).view(np.complex128).reshape(2, 2)) for g in arr]
+  return out, n.value
+
+
 def shard_plan_stats(nqubits: int, nranks: int, rank: int, gates, tile_bits: int = 12, mode: str = "push") -> dict:
   """Events / pairs / passes a flush of `gates` (index-bit numbering) costs on one rank (host only)."""
   arr = gates if isinstance(gates, ctypes.Array) else pack_gates(gates)
@@ -221,7 +231,7 @@ def shard_plan_stats(nqubits: int, nranks: int, rank: int, gates, tile_bits: int
                              "nccl": (6, 0, 0)}[mode]
   st = (ctypes.c_int64 * 8)()
   check(lib().qb_shard_plan_stats(nqubits, nranks, rank, arr, len(arr), tile_bits, window, hoist, prefetch, st))
-  return dict(zip(("events", "pairs", "passes", "fused_passes", "events_on_a_pass", "rounds", "ops"), st))
+  return dict(zip(("events", "pairs", "passes", "fused_passes", "events_on_a_pass", "rounds", "ops", "ccu_fused"), st))
 
 
 def shard_event_dest(nlocal: int, nranks: int, rank: int, pairs, local: np.ndarray) -> np.ndarray:

@@ -14,6 +14,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <cmath>
@@ -106,6 +107,9 @@ struct qb_state {
   unsigned long long *d_counter = nullptr;
   double *d_blk_prob = nullptr;
   uint64_t *d_blk_idx = nullptr;
+  uint64_t *d_list_labels = nullptr;     // qb_list_above output buffers, kept between calls
+  double2 *d_list_amps = nullptr;
+  uint64_t list_cap = 0;
   // fused-pass staging (device copies of the current plan)
   void *d_plan = nullptr;
   size_t d_plan_cap = 0;
@@ -516,11 +520,35 @@ void make_layout(const qb_state *s, qb::ShardLayout *L) {
   L->pass_targets = std::max(1, s->tile_bits - QB_TILE_LOW);
 }
 
+double host_now_ms() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return double(ts.tv_sec) * 1e3 + double(ts.tv_nsec) * 1e-6;
+}
+
+int flush_impl(qb_state *s);
+
+// QCC_B200_TRACE_FLUSH=1: one line per flush on stderr (gates, host milliseconds spent lowering + planning +
+// launching) -- where the host time of a long gate stream goes.
 int flush(qb_state *s) {
+  static const bool trace = getenv("QCC_B200_TRACE_FLUSH") != nullptr;
+  if (!trace || s->queue.empty()) return flush_impl(s);
+  const size_t ng = s->queue.size();
+  const uint64_t p0 = s->cnt.passes;
+  const double t0 = host_now_ms();
+  const int rc = flush_impl(s);
+  fprintf(stderr, "qcc_b200 flush: %zu gates -> %llu passes, host %.2f ms\n", ng,
+          (unsigned long long)(s->cnt.passes - p0), host_now_ms() - t0);
+  return rc;
+}
+
+int flush_impl(qb_state *s) {
   if (s->queue.empty()) return QB_OK;
   CU(cudaSetDevice(s->device));
   std::vector<QbGate> q;
   q.swap(s->queue);
+  static const bool no_ccu = getenv("QCC_B200_NO_CCU_FUSE") != nullptr;
+  if (!no_ccu && s->fusion) qb::fuse_ccu_runs(q.data(), int64_t(q.size()));
   if (s->nranks == 1) return run_local(s, q);
   qb::ShardLayout L;
   make_layout(s, &L);
@@ -817,6 +845,8 @@ int qb_state_destroy(qb_state *s) {
   if (s->d_counter) cudaFree(s->d_counter);
   if (s->d_blk_prob) cudaFree(s->d_blk_prob);
   if (s->d_blk_idx) cudaFree(s->d_blk_idx);
+  if (s->d_list_labels) cudaFree(s->d_list_labels);
+  if (s->d_list_amps) cudaFree(s->d_list_amps);
   if (s->d_plan) cudaFree(s->d_plan);
   if (s->h_plan) cudaFreeHost(s->h_plan);
   if (s->plan_free) cudaEventDestroy(s->plan_free);
@@ -1042,7 +1072,15 @@ int qb_argmax(qb_state *s, uint64_t *index, double *prob) {
   int nb = qb::argmax_blocks();
   {
     ProfScope ps(s, QB_KCLASS_AUX, double(s->len) * 16.0);
-    CU(qb::launch_argmax(s->psi, s->len, s->d_blk_prob, s->d_blk_idx, s->stream));
+    qb::LogicalMap lm;
+    if (s->nranks > 1) {
+      lm.identity = 0;
+      lm.n = s->n;
+      lm.hi = logical_of(s, s->rank, 0);
+      for (int b = 0; b < s->nq; ++b)
+        if (s->perm[size_t(b)] < s->n) lm.lpos[s->perm[size_t(b)]] = b;
+    }
+    CU(qb::launch_argmax(s->psi, s->len, s->d_blk_prob, s->d_blk_idx, lm, s->stream));
   }
   s->cnt.kernel_launches += 1;
   std::vector<double> hp(nb);
@@ -1058,8 +1096,7 @@ int qb_argmax(qb_state *s, uint64_t *index, double *prob) {
       bi = hi[b];
     }
   if (s->nranks > 1) {
-    // translate to the logical index, then pick the global winner (ties: lowest logical index)
-    bi = logical_of(s, s->rank, bi);
+    // the kernel already reports logical indices: pick the global winner (ties: lowest logical index)
     std::string why;
     const qb::NcclApi *nc = qb::nccl_api(&why);
     if (!nc) return fail(QB_ERR_COMM, "%s", why.c_str());
@@ -1093,48 +1130,83 @@ int qb_list_above(qb_state *s, double threshold, uint64_t cap, uint64_t *labels,
   if (!s || !count) return fail(QB_ERR_ARG, "null pointer");
   if (cap && (!labels || !amps)) return fail(QB_ERR_ARG, "null output buffers with cap > 0");
   QB(flush(s));
-  uint64_t *d_labels = nullptr;
-  double2 *d_amps = nullptr;
-  if (cap) {
-    CU(cudaMalloc(&d_labels, cap * sizeof(uint64_t)));
-    cudaError_t e = cudaMalloc(&d_amps, cap * sizeof(double2));
-    if (e != cudaSuccess) {
-      cudaFree(d_labels);
-      return fail(QB_ERR_NOMEM, "list buffers: %s", cudaGetErrorString(e));
-    }
+  // sharded: every rank lists its shard, then the lists are all-gathered -- the buffers hold one slot of
+  // `cap` entries per rank
+  const uint64_t slots = s->nranks > 1 ? uint64_t(s->nranks) + 1 : 1;
+  if (cap * slots > s->list_cap) {
+    if (s->d_list_labels) cudaFree(s->d_list_labels);
+    if (s->d_list_amps) cudaFree(s->d_list_amps);
+    s->d_list_labels = nullptr;
+    s->d_list_amps = nullptr;
+    s->list_cap = 0;
+    cudaError_t e = cudaMalloc(&s->d_list_labels, cap * slots * sizeof(uint64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&s->d_list_amps, cap * slots * sizeof(double2));
+    if (e != cudaSuccess) return fail(QB_ERR_NOMEM, "list buffers: %s", cudaGetErrorString(e));
+    s->list_cap = cap * slots;
   }
-  cudaError_t e;
+  uint64_t *d_labels = s->d_list_labels;
+  double2 *d_amps = s->d_list_amps;
   {
     ProfScope ps(s, QB_KCLASS_AUX, double(s->len) * 16.0);
-    e = qb::launch_list_above(s->psi, s->len, threshold, cap, s->d_counter, d_labels, d_amps, s->stream);
+    CU(qb::launch_list_above(s->psi, s->len, threshold, cap, s->d_counter, d_labels, d_amps, s->stream));
   }
   s->cnt.kernel_launches += 1;
   unsigned long long found = 0;
-  if (e == cudaSuccess) e = cudaMemcpyAsync(&found, s->d_counter, sizeof found, cudaMemcpyDeviceToHost, s->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+  CU(cudaMemcpyAsync(&found, s->d_counter, sizeof found, cudaMemcpyDeviceToHost, s->stream));
+  CU(cudaStreamSynchronize(s->stream));
   uint64_t got = std::min<uint64_t>(found, cap);
   std::vector<uint64_t> hl(got);
   std::vector<double2> ha(got);
-  if (e == cudaSuccess && got) {
-    e = cudaMemcpy(hl.data(), d_labels, got * sizeof(uint64_t), cudaMemcpyDeviceToHost);
-    if (e == cudaSuccess) e = cudaMemcpy(ha.data(), d_amps, got * sizeof(double2), cudaMemcpyDeviceToHost);
+  if (got) {
+    CU(cudaMemcpyAsync(hl.data(), d_labels, got * sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaMemcpyAsync(ha.data(), d_amps, got * sizeof(double2), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
   }
-  if (d_labels) cudaFree(d_labels);
-  if (d_amps) cudaFree(d_amps);
-  if (e != cudaSuccess) return fail(QB_ERR_CUDA, "list_above: %s", cudaGetErrorString(e));
+  uint64_t total = found;
+  if (s->nranks > 1) {
+    // labels under their LOGICAL names, then everybody's list to everybody (collective, like every readout)
+    for (uint64_t i = 0; i < got; ++i) hl[i] = logical_of(s, s->rank, hl[i]);
+    std::string why;
+    const qb::NcclApi *nc = qb::nccl_api(&why);
+    if (!nc) return fail(QB_ERR_COMM, "%s", why.c_str());
+    const int R = s->nranks;
+    uint64_t *d_cnt = s->d_blk_idx;   // scratch: 1 + R counters
+    CU(cudaMemcpyAsync(d_cnt, &found, sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
+    NC(nc, nc->AllGather(d_cnt, d_cnt + 1, 1, ncclUint64, s->comm, s->stream));
+    std::vector<uint64_t> cnts(static_cast<size_t>(R));
+    CU(cudaMemcpyAsync(cnts.data(), d_cnt + 1, sizeof(uint64_t) * size_t(R), cudaMemcpyDeviceToHost, s->stream));
+    if (cap) {
+      if (got) CU(cudaMemcpyAsync(d_labels, hl.data(), got * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
+      NC(nc, nc->AllGather(d_labels, d_labels + cap, size_t(cap), ncclUint64, s->comm, s->stream));
+      NC(nc, nc->AllGather(d_amps, d_amps + cap, size_t(cap) * 2, ncclDouble, s->comm, s->stream));
+    }
+    CU(cudaStreamSynchronize(s->stream));
+    total = 0;
+    for (int r = 0; r < R; ++r) total += cnts[size_t(r)];
+    hl.clear();
+    ha.clear();
+    for (int r = 0; r < R && cap; ++r) {
+      const uint64_t g = std::min<uint64_t>(cnts[size_t(r)], cap);
+      if (!g) continue;
+      const size_t at = hl.size();
+      hl.resize(at + g);
+      ha.resize(at + g);
+      CU(cudaMemcpy(hl.data() + at, d_labels + cap * uint64_t(r + 1), g * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+      CU(cudaMemcpy(ha.data() + at, d_amps + cap * uint64_t(r + 1), g * sizeof(double2), cudaMemcpyDeviceToHost));
+    }
+    got = hl.size();
+  }
   // the kernel's slots are in arrival order; present them by ascending label
   std::vector<uint64_t> order(got);
   for (uint64_t i = 0; i < got; ++i) order[i] = i;
   std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return hl[a] < hl[b]; });
-  if (s->nranks > 1)
-    for (uint64_t i = 0; i < got; ++i) hl[i] = logical_of(s, s->rank, hl[i]);
-  std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return hl[a] < hl[b]; });
-  for (uint64_t i = 0; i < got; ++i) {
+  const uint64_t nout = std::min<uint64_t>(got, cap);
+  for (uint64_t i = 0; i < nout; ++i) {
     labels[i] = hl[order[i]];
     amps[2 * i] = ha[order[i]].x;
     amps[2 * i + 1] = ha[order[i]].y;
   }
-  *count = found;
+  *count = total;
   return QB_OK;
 }
 
@@ -1381,6 +1453,7 @@ int qb_shard_plan_stats(int nqubits, int nranks, int rank, const qb_gate *gates,
     q.push_back(x);
   }
   for (int k = 0; k < 8; ++k) stats[k] = 0;
+  if (!getenv("QCC_B200_NO_CCU_FUSE")) stats[7] = qb::fuse_ccu_runs(q.data(), ngates);
   std::vector<qb::ShardStep> steps;
   if (nranks > 1) {
     qb::ShardLayout L;
@@ -1422,6 +1495,24 @@ int qb_shard_plan_stats(int nqubits, int nranks, int rank, const qb_gate *gates,
       }
     }
     tail_fused = !plan.passes.empty() && plan.passes.back().single_gate < 0;
+  }
+  return QB_OK;
+}
+
+int qb_fuse_gates(qb_gate *gates, int64_t ngates, int64_t *fused) {
+  if ((!gates && ngates) || !fused) return fail(QB_ERR_ARG, "null pointer");
+  std::vector<QbGate> q(static_cast<size_t>(ngates));
+  for (int64_t k = 0; k < ngates; ++k) {
+    q[size_t(k)].ctl_mask = gates[k].ctl_mask;
+    q[size_t(k)].target = gates[k].target;
+    q[size_t(k)].kind = classify(gates[k].m);
+    memcpy(q[size_t(k)].m, gates[k].m, sizeof gates[k].m);
+  }
+  *fused = qb::fuse_ccu_runs(q.data(), ngates);
+  for (int64_t k = 0; k < ngates; ++k) {
+    gates[k].ctl_mask = q[size_t(k)].ctl_mask;
+    gates[k].target = q[size_t(k)].target;
+    memcpy(gates[k].m, q[size_t(k)].m, sizeof gates[k].m);
   }
   return QB_OK;
 }

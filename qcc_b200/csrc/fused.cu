@@ -61,13 +61,6 @@ namespace qb {
 namespace {
 
 constexpr int kFThreads = 256;
-// Direct loads of the first round (QbPassDesc::ld_direct) are compiled out: measured slower than the
-// cp.async copy (see planner.cc); build with -DQB_DIRECT_LD=1 and run with QCC_B200_DIRECT_LD=1 to repeat
-// the experiment.  Direct stores of the last round stay.
-#ifndef QB_DIRECT_LD
-#define QB_DIRECT_LD 0
-#endif
-
 // Host-precomputed per-round constants of the round programs (all derivable from QbRound / QbOp;
 // kept out of the hot loop's uniform-datapath instruction stream).
 struct RoundAux {
@@ -300,11 +293,12 @@ __device__ __forceinline__ void hladder(double2 (&a)[8], double r, double2 cf, c
   }
 }
 
-// Direct rounds (QbPassDesc::ld_direct / st_direct): the first round of a pass takes its groups straight
-// from HBM, the last one writes them straight back -- the tile then passes through shared memory only
-// between rounds.  gp = psi + tile base; the thread's part of the index (its group-number bits scattered
-// to the tile bits) is built once per round, the iteration part and the round bits come from RoundAux.
-// IO (template parameter of the round programs): bit 0 = load directly, bit 1 = store directly.
+// Direct store (QbPassDesc::st_direct): the last round of a pass writes its groups straight back to HBM, so
+// the tile skips one shared-memory write + read and the barrier before the store.  gp = psi + tile base; the
+// thread's part of the index (its group-number bits scattered to the tile bits) is built once per round, the
+// iteration part and the round bits come from RoundAux.  (Direct LOADS of the first round were measured in
+// round 1 and lost 7-17 %: only 8 loads per thread in flight instead of the cp.async copy's 16.)
+// IO (template parameter of the round programs): 2 = store directly, 0 = through shared memory.
 
 // ---- round program HL3: three Hadamard+ladder stages on round positions 0, 1, 2 ---------------
 // The shape of every round of a QFT (circuit.py:320-328): h(b0) + ladder(b0), h(b1) + ladder(b1),
@@ -354,15 +348,9 @@ __device__ __forceinline__ void round_hl3(const uint32_t tile_sa, const uint32_t
     double2 a[8];
     double2 *gq = nullptr;
     if (IO != 0) gq = gp + (g_t + (uint64_t(X->gji[sub]) << 3));
-    if (IO & 1) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e)
-        a[e] = __ldcs(gq + (uint64_t(((e & 1) ? X->gb[0] : 0u) + ((e & 2) ? X->gb[1] : 0u) + ((e & 4) ? X->gb[2] : 0u)) << 3));
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e)
-        a[e] = lds128(tile_sa + (pb ^ ((e & 1) ? b0 : 0u) ^ ((e & 2) ? b1 : 0u) ^ ((e & 4) ? b2 : 0u)));
-    }
+    for (int e = 0; e < 8; ++e)
+      a[e] = lds128(tile_sa + (pb ^ ((e & 1) ? b0 : 0u) ^ ((e & 2) ? b1 : 0u) ^ ((e & 4) ? b2 : 0u)));
     const uint32_t tboff = (32u + (q >> 5)) << 4;
     // stage 0: pairs (e, e|1)
     {
@@ -495,15 +483,9 @@ __device__ __forceinline__ void round_ux(const uint32_t tile_sa, const uint32_t 
     double2 a[8];
     double2 *gq = nullptr;
     if (IO != 0) gq = gp + (g_t + (uint64_t(X->gji[sub]) << 3));
-    if (IO & 1) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e)
-        a[e] = __ldcs(gq + (uint64_t(((e & 1) ? X->gb[0] : 0u) + ((e & 2) ? X->gb[1] : 0u) + ((e & 4) ? X->gb[2] : 0u)) << 3));
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e)
-        a[e] = lds128(tile_sa + (pb ^ ((e & 1) ? b0 : 0u) ^ ((e & 2) ? b1 : 0u) ^ ((e & 4) ? b2 : 0u)));
-    }
+    for (int e = 0; e < 8; ++e)
+      a[e] = lds128(tile_sa + (pb ^ ((e & 1) ? b0 : 0u) ^ ((e & 2) ? b1 : 0u) ^ ((e & 4) ? b2 : 0u)));
     if (uni == 3) {
       // all three positions carry a column-imaginary U (every round of larose): one straight-line block,
       // no control-flow joins between the stages, so no register moves to line results up
@@ -652,11 +634,10 @@ __device__ __forceinline__ void program_round(const FusedParams &P, const int r,
   const QbOp *o = P.ops + ob;
   const uint32_t *jbt = P.jbtab + (size_t(r) << P.desc.ngroups_log2);
   const bool upper = R->prog == QB_PROG_HL3U;
-  const bool ld = QB_DIRECT_LD && FULL && direct && r == 0 && P.desc.ld_direct;
   const bool st = FULL && direct && r + 1 == P.desc.nrounds && P.desc.st_direct;
   double2 *const gp = P.psi + base;
   uint64_t g_t = 0;
-  if (ld || st) {
+  if (st) {
     // the thread's group-number bits (0..7) scattered to the index bits they drive (lanes 0..7 sit on
     // tile positions 0..2 = index bits 0..2; the other terms are multiples of 8 amplitudes)
     uint32_t g8 = 0;
@@ -670,10 +651,8 @@ __device__ __forceinline__ void program_round(const FusedParams &P, const int r,
   }
 #define QB_ROUND_IO(CALL)                                    \
   do {                                                       \
-    if (!FULL || THREADS != kFThreads || (!ld && !st)) { constexpr int IO = 0; CALL; } \
-    else if (QB_DIRECT_LD && ld && !st) { constexpr int IO = FULL && THREADS == kFThreads ? 1 : 0; CALL; } \
-    else if (!QB_DIRECT_LD || !ld) { constexpr int IO = FULL && THREADS == kFThreads ? 2 : 0; CALL; }       \
-    else { constexpr int IO = FULL && THREADS == kFThreads ? 3 : 0; CALL; }                \
+    if (!FULL || THREADS != kFThreads || !st) { constexpr int IO = 0; CALL; } \
+    else { constexpr int IO = FULL && THREADS == kFThreads ? 2 : 0; CALL; }   \
   } while (0)
   if (R->prog == QB_PROG_UX) {
     QB_ROUND_IO((round_ux<FULL, IO, THREADS>(tile_sa, jbt, o, oe - ob, R, X, ngroups, tid, base, gp, g_t, tab_sa)));
@@ -696,7 +675,8 @@ __device__ __forceinline__ void program_round(const FusedParams &P, const int r,
 // FAST: every round of the pass has a round program, so the op interpreter is not compiled in; the
 // kernel then fits 80 registers and a third CTA per SM (24 instead of 16 warps to hide the
 // shared-memory and fp64 latencies of the rounds).
-template <bool FULL, bool FAST>
+// PUSH: the store stage carries an exchange event (its own instantiation, so the plain pass pays nothing for it).
+template <bool FULL, bool FAST, bool PUSH>
 __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __grid_constant__ FusedParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int K = P.desc.K;
@@ -706,7 +686,7 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
   uint32_t *s_active = reinterpret_cast<uint32_t *>(s_tab + P.desc.ntable);  // 4 words: ops whose
                                                                         // outside-tile predicate holds for this tile
   double2 **s_out = reinterpret_cast<double2 **>(s_active + 4);         // push: destination buffer of every rank
-  if (P.push_on && threadIdx.x < kPushMaxRanks) s_out[threadIdx.x] = P.push.out[threadIdx.x];
+  if (PUSH && threadIdx.x < kPushMaxRanks) s_out[threadIdx.x] = P.push.out[threadIdx.x];
   const QbOp *s_ops = P.ops;        // constant bank
   const QbRound *s_rounds = P.rounds;
   const uint32_t tid = threadIdx.x;
@@ -764,9 +744,9 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
   };
   // direct first / last round: no copy-in / copy-out of the tile (FAST or not, the first / last round
   // then has a round program; the debug switches that bypass the programs turn it off on the host)
-  const bool ld_direct = QB_DIRECT_LD && FULL && P.desc.ld_direct, st_direct = FULL && P.desc.st_direct;
+  const bool st_direct = !PUSH && FULL && P.desc.st_direct;
   auto issue_load = [&](uint64_t b) {
-    if (!(P.debug & 8) && io_on && !ld_direct) {
+    if (!(P.debug & 8) && io_on) {
       const double2 *src = psi + (b | g_ld);
       if (io_iters == 16) {  // K = 12: constant-bank operands with immediate addresses
 #pragma unroll
@@ -964,7 +944,7 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
     }
 
     // ---- STORE ---------------------------------------------------------------------------
-    if (P.push_on && io_on) {
+    if (PUSH && io_on) {
       // the tile goes to where the exchange event puts it: distributed index = sigma(rank, base) | sigma(thread
       // term) | sigma(iteration term); its top bits name the destination rank, the rest the slot in that
       // rank's alternate buffer (posted writes over NVLink for the other ranks)
@@ -1004,12 +984,12 @@ size_t fused_smem_bytes(int K, int ntable) {
 constexpr size_t kSmemLimit = 227 * 1024;
 int g_sms = 0;
 
-template <bool FULL, bool FAST>
+template <bool FULL, bool FAST, bool PUSH>
 cudaError_t configure_one() {
-  cudaError_t err = cudaFuncSetAttribute(k_fused_pass<FULL, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaError_t err = cudaFuncSetAttribute(k_fused_pass<FULL, FAST, PUSH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          int(kSmemLimit));
   if (err != cudaSuccess) return err;
-  return cudaFuncSetAttribute(k_fused_pass<FULL, FAST>, cudaFuncAttributePreferredSharedMemoryCarveout,
+  return cudaFuncSetAttribute(k_fused_pass<FULL, FAST, PUSH>, cudaFuncAttributePreferredSharedMemoryCarveout,
                               cudaSharedmemCarveoutMaxShared);
 }
 
@@ -1022,10 +1002,14 @@ cudaError_t fused_configure(int device) {
   static_assert(sizeof(FusedParams) <= 32764, "kernel parameter space");
   cudaError_t err = cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, device);
   if (err != cudaSuccess) return err;
-  if ((err = configure_one<true, true>()) != cudaSuccess) return err;
-  if ((err = configure_one<true, false>()) != cudaSuccess) return err;
-  if ((err = configure_one<false, true>()) != cudaSuccess) return err;
-  return configure_one<false, false>();
+  if ((err = configure_one<true, true, false>()) != cudaSuccess) return err;
+  if ((err = configure_one<true, false, false>()) != cudaSuccess) return err;
+  if ((err = configure_one<false, true, false>()) != cudaSuccess) return err;
+  if ((err = configure_one<false, false, false>()) != cudaSuccess) return err;
+  if ((err = configure_one<true, true, true>()) != cudaSuccess) return err;
+  if ((err = configure_one<true, false, true>()) != cudaSuccess) return err;
+  if ((err = configure_one<false, true, true>()) != cudaSuccess) return err;
+  return configure_one<false, false, true>();
 }
 
 cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cudaStream_t st) {
@@ -1148,7 +1132,7 @@ cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cuda
           for (int k = 0; k < 3; ++k) P.aux[r].s *= p.ops[p.rounds[r].op_begin + k].m[0];
         }
   }
-  if (dbg & (1 | 2 | 4 | 8 | 16)) P.desc.ld_direct = P.desc.st_direct = 0;  // timing experiments use the copy path
+  if (dbg & (1 | 2 | 4 | 8 | 16)) P.desc.st_direct = 0;  // timing experiments use the copy path
   P.push_on = 0;
   if (p.push) {
     // exchange event fused into the store stage: every store address term goes through the event's bit
@@ -1178,10 +1162,15 @@ cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cuda
   unsigned blocks = ntiles;
   if (persist > 0 && ntiles > unsigned(persist * g_sms)) blocks = unsigned(persist * g_sms);
   const bool full = ((1u << (K - 3)) % kFThreads) == 0;
-  if (full && fast) k_fused_pass<true, true><<<blocks, kFThreads, smem, st>>>(P);
-  else if (full) k_fused_pass<true, false><<<blocks, kFThreads, smem, st>>>(P);
-  else if (fast) k_fused_pass<false, true><<<blocks, kFThreads, smem, st>>>(P);
-  else k_fused_pass<false, false><<<blocks, kFThreads, smem, st>>>(P);
+  if (P.push_on) {
+    if (full && fast) k_fused_pass<true, true, true><<<blocks, kFThreads, smem, st>>>(P);
+    else if (full) k_fused_pass<true, false, true><<<blocks, kFThreads, smem, st>>>(P);
+    else if (fast) k_fused_pass<false, true, true><<<blocks, kFThreads, smem, st>>>(P);
+    else k_fused_pass<false, false, true><<<blocks, kFThreads, smem, st>>>(P);
+  } else if (full && fast) k_fused_pass<true, true, false><<<blocks, kFThreads, smem, st>>>(P);
+  else if (full) k_fused_pass<true, false, false><<<blocks, kFThreads, smem, st>>>(P);
+  else if (fast) k_fused_pass<false, true, false><<<blocks, kFThreads, smem, st>>>(P);
+  else k_fused_pass<false, false, false><<<blocks, kFThreads, smem, st>>>(P);
   return cudaGetLastError();
 }
 

@@ -221,19 +221,33 @@ k_prob_mask(const double2 *__restrict__ psi, uint64_t n, uint64_t mask, uint64_t
   }
 }
 
+// Index space in which "lowest index wins a tie" is decided (state.py:75 np.abs(psi).argmax() on the LOGICAL
+// vector): identity for an unsharded state; for a shard, local bit b is logical bit lpos[b] and the rank bits
+// contribute `hi`.
+__device__ __forceinline__ uint64_t logical_index(const LogicalMap &m, uint64_t i) {
+  if (m.identity) return i;
+  uint64_t l = m.hi;
+#pragma unroll 1
+  for (int b = 0; b < m.n; ++b) l |= ((i >> b) & 1) << m.lpos[b];
+  return l;
+}
+
 __global__ void __launch_bounds__(kThreads)
-k_argmax(const double2 *__restrict__ psi, uint64_t n, double *blk_prob, uint64_t *blk_idx) {
+k_argmax(const double2 *__restrict__ psi, uint64_t n, double *blk_prob, uint64_t *blk_idx, const LogicalMap lm) {
   __shared__ double sp[kThreads / 32];
   __shared__ uint64_t si[kThreads / 32];
   double best = -1.0;
-  uint64_t bidx = 0;
+  uint64_t bidx = ~uint64_t(0);   // LOGICAL index of the best so far
   uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
   for (uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
     double2 v = psi[i];
     double p = v.x * v.x + v.y * v.y;
-    if (p > best) {  // ascending i per thread: strict > keeps the lowest index
+    if (p > best) {
       best = p;
-      bidx = i;
+      bidx = logical_index(lm, i);
+    } else if (p == best && !lm.identity) {   // identity: ascending i per thread, strict > keeps the lowest index
+      const uint64_t l = logical_index(lm, i);
+      if (l < bidx) bidx = l;
     }
   }
 #pragma unroll
@@ -320,10 +334,10 @@ cudaError_t launch_prob_mask(const double2 *psi, uint64_t n, uint64_t mask, uint
 
 int argmax_blocks() { return kReduceBlocks; }
 
-cudaError_t launch_argmax(const double2 *psi, uint64_t n, double *blk_prob, uint64_t *blk_idx,
+cudaError_t launch_argmax(const double2 *psi, uint64_t n, double *blk_prob, uint64_t *blk_idx, const LogicalMap &lm,
                           cudaStream_t st) {
   // always kReduceBlocks entries: blocks beyond the data report prob = -1
-  k_argmax<<<kReduceBlocks, kThreads, 0, st>>>(psi, n, blk_prob, blk_idx);
+  k_argmax<<<kReduceBlocks, kThreads, 0, st>>>(psi, n, blk_prob, blk_idx, lm);
   return cudaGetLastError();
 }
 

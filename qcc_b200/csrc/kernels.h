@@ -23,9 +23,17 @@ cudaError_t launch_norm2(const double2 *psi, uint64_t n, double *out, cudaStream
 // out: 1 double = sum of |psi_i|^2 over i with (i & mask) == want
 cudaError_t launch_prob_mask(const double2 *psi, uint64_t n, uint64_t mask, uint64_t want, double *out,
                              cudaStream_t st);
-// Per-block partial argmax: blk_prob[b], blk_idx[b] for b < *nblocks_out; host finishes.
+// Per-block partial argmax: blk_prob[b], blk_idx[b] for b < argmax_blocks(); host finishes.  blk_idx holds
+// LOGICAL indices (LogicalMap: where each local bit and the rank bits sit in the logical index), and ties go to
+// the lowest logical index -- np.abs(psi).argmax() of state.py:75 whatever the exchange history of a shard.
+struct LogicalMap {
+  int identity = 1;
+  int n = 0;          // local bits
+  int lpos[40] = {};  // local physical bit -> logical bit
+  uint64_t hi = 0;    // contribution of this rank's rank bits
+};
 int argmax_blocks();
-cudaError_t launch_argmax(const double2 *psi, uint64_t n, double *blk_prob, uint64_t *blk_idx,
+cudaError_t launch_argmax(const double2 *psi, uint64_t n, double *blk_prob, uint64_t *blk_idx, const LogicalMap &lm,
                           cudaStream_t st);
 // Compaction of indices with |psi|^2 >= thr: counter (1 x u64, zeroed by launcher), and up to
 // cap (label, amp) pairs in arbitrary order.

@@ -975,11 +975,6 @@ void emit_pass(int nbits, int K, const std::vector<const Item *> &items, const s
       }
       return low == 7;
     };
-    // Direct LOADS are a measured loss (QFT-30 27.4 vs 26.5 ms, larose-28 203 vs 174 ms on the same box): a
-    // thread can only have the 8 loads of one group in flight (registers), half the bytes in flight of
-    // the cp.async copy, and pays the HBM latency once per group instead of once per tile.  Opt-in only.
-    static const bool direct_ld = getenv("QCC_B200_DIRECT_LD") != nullptr;
-    pp.desc.ld_direct = direct_ld && !pp.rounds.empty() && direct_ok(pp.rounds.front()) ? 1 : 0;
     pp.desc.st_direct = !pp.rounds.empty() && direct_ok(pp.rounds.back()) ? 1 : 0;
   }
   pp.desc.ntable = int32_t(pp.tables.size());
@@ -1032,6 +1027,85 @@ double gate_bytes_per_amp(const QbGate &g) {
   int nb = __builtin_popcountll(g.ctl_mask);
   if (g.kind == QB_K_PHASE || g.kind == QB_K_DIAG) nb += 1;  // diagonal = half
   return 32.0 / double(uint64_t(1) << nb);
+}
+
+// ---- peephole: Sleator-Weinfurter recognition -------------------------------------------------------
+// circuit.py:227-246 (ccu) spells every doubly-controlled gate -- each Toffoli of multi_control's ladder
+// (circuit.py:341-392), ccu1, cswap -- as five gates:
+//     cu(a, t, V)  cx(a, b)  cu(b, t, V^dagger)  cx(a, b)  cu(b, t, V)        with V^2 = U
+// which is exactly  U on t where a AND b are set.  Found in the queued stream (the five gates adjacent, the
+// matrices matching to 1e-13), the run is replaced by ONE doubly-controlled gate U = V V plus four no-ops that
+// keep the gate count: a quarter of the amplitudes touched once instead of three half-vector butterflies and
+// two swaps, and b stops being a mixing target (fewer tile bits per pass, fewer exchanges on a sharded state).
+// Entries of U within 1e-14 of 0 / +-1 are snapped so that X^(1/2) squared is again the pure swap.
+int64_t fuse_ccu_runs(QbGate *g, int64_t n) {
+  auto one_ctl = [](const QbGate &x) { return x.ctl_mask != 0 && (x.ctl_mask & (x.ctl_mask - 1)) == 0; };
+  auto is_cx = [&](const QbGate &x) {
+    return one_ctl(x) && (x.kind == QB_K_PERM || x.kind == QB_K_SWAP) && x.m[0] == 0.0 && x.m[1] == 0.0 && x.m[2] == 1.0 &&
+           x.m[3] == 0.0 && x.m[4] == 1.0 && x.m[5] == 0.0 && x.m[6] == 0.0 && x.m[7] == 0.0;
+  };
+  const double tol = 1e-13;
+  int64_t fused = 0;
+  for (int64_t i = 0; i + 4 < n; ++i) {
+    const QbGate &g1 = g[i], &g2 = g[i + 1], &g3 = g[i + 2], &g4 = g[i + 3], &g5 = g[i + 4];
+    if (g1.kind == QB_K_NOP || !one_ctl(g1) || !is_cx(g2) || !is_cx(g4)) continue;
+    const uint64_t a = g1.ctl_mask, bmask = uint64_t(1) << g2.target;
+    const int t = g1.target;
+    if (g2.ctl_mask != a || g4.ctl_mask != a || g4.target != g2.target || g2.target == t || (a >> t & 1)) continue;
+    if (g3.ctl_mask != bmask || g5.ctl_mask != bmask || g3.target != t || g5.target != t) continue;
+    if (g3.kind == QB_K_NOP || g5.kind == QB_K_NOP) continue;
+    bool ok = true;
+    // g5 == g1 and g3 == g1^dagger
+    const int tr[4] = {0, 2, 1, 3};
+    for (int k = 0; k < 4 && ok; ++k) {
+      if (fabs(g5.m[2 * k] - g1.m[2 * k]) > tol || fabs(g5.m[2 * k + 1] - g1.m[2 * k + 1]) > tol) ok = false;
+      if (fabs(g3.m[2 * k] - g1.m[2 * tr[k]]) > tol || fabs(g3.m[2 * k + 1] + g1.m[2 * tr[k] + 1]) > tol) ok = false;
+    }
+    if (!ok) continue;
+    // V must be unitary for g3 to undo it where only one control is set
+    Cplx v[4], vd[4], u[4], id[4];
+    for (int k = 0; k < 4; ++k) {
+      v[k] = Cplx{g1.m[2 * k], g1.m[2 * k + 1]};
+      vd[k] = Cplx{g3.m[2 * k], g3.m[2 * k + 1]};
+    }
+    for (int r = 0; r < 2; ++r)
+      for (int c = 0; c < 2; ++c) {
+        Cplx p = cmulh(v[r * 2], v[c]), q = cmulh(v[r * 2 + 1], v[2 + c]);
+        u[r * 2 + c] = Cplx{p.x + q.x, p.y + q.y};
+        Cplx p2 = cmulh(vd[r * 2], v[c]), q2 = cmulh(vd[r * 2 + 1], v[2 + c]);
+        id[r * 2 + c] = Cplx{p2.x + q2.x, p2.y + q2.y};
+      }
+    if (fabs(id[0].x - 1) > tol || fabs(id[0].y) > tol || fabs(id[3].x - 1) > tol || fabs(id[3].y) > tol ||
+        fabs(id[1].x) > tol || fabs(id[1].y) > tol || fabs(id[2].x) > tol || fabs(id[2].y) > tol)
+      continue;
+    QbGate f{};
+    f.ctl_mask = a | bmask;
+    f.target = t;
+    auto snap = [](double x) {
+      if (fabs(x) < 1e-14) return 0.0;
+      if (fabs(x - 1.0) < 1e-14) return 1.0;
+      if (fabs(x + 1.0) < 1e-14) return -1.0;
+      return x;
+    };
+    for (int k = 0; k < 4; ++k) {
+      f.m[2 * k] = snap(u[k].x);
+      f.m[2 * k + 1] = snap(u[k].y);
+    }
+    f.kind = classify_matrix(f.m);
+    g[i] = f;
+    for (int k = 1; k < 5; ++k) {
+      QbGate nop{};
+      nop.ctl_mask = 0;
+      nop.target = t;
+      nop.kind = QB_K_NOP;
+      nop.m[0] = 1.0;
+      nop.m[6] = 1.0;
+      g[i + k] = nop;
+    }
+    fused += 1;
+    i += 4;
+  }
+  return fused;
 }
 
 void plan_gates(int nbits, const QbGate *gates, int64_t ngates, int tile_bits, Plan *out) {
@@ -1139,8 +1213,8 @@ std::string Plan::to_json() const {
       s += "]}";
       continue;
     }
-    snprintf(buf, sizeof buf, "{\"single_gate\":-1,\"ngates\":%lld,\"K\":%d,\"warp_io\":%d,\"ld_direct\":%d,\"st_direct\":%d,\"ld_map\":[",
-             (long long)p.ngates, p.desc.K, p.desc.warp_io, p.desc.ld_direct, p.desc.st_direct);
+    snprintf(buf, sizeof buf, "{\"single_gate\":-1,\"ngates\":%lld,\"K\":%d,\"warp_io\":%d,\"st_direct\":%d,\"ld_map\":[",
+             (long long)p.ngates, p.desc.K, p.desc.warp_io, p.desc.st_direct);
     s += buf;
     for (int k = 0; k < p.desc.K; ++k) {
       snprintf(buf, sizeof buf, "%s%d", k ? "," : "", p.desc.ld_map[k]);

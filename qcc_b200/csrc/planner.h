@@ -53,6 +53,10 @@ int classify_matrix(const double m[8]);
 // SURVEY.md 8(d) algorithmic bytes per amplitude of the full vector for one gate.
 double gate_bytes_per_amp(const QbGate &g);
 
+// Peephole over a queued stream, in place: every five-gate Sleator-Weinfurter run (circuit.py:227-246) becomes
+// one doubly-controlled gate + four no-ops.  Returns the number of runs replaced.  See planner.cc.
+int64_t fuse_ccu_runs(QbGate *gates, int64_t ngates);
+
 void plan_gates(int nbits, const QbGate *gates, int64_t ngates, int tile_bits, Plan *out);
 
 }  // namespace qb

@@ -134,11 +134,10 @@ struct QbPassDesc {
   int32_t warp_io;
   int32_t ld_map[QB_MAX_TILE_BITS];
   int32_t st_map[QB_MAX_TILE_BITS];
-  // ld_direct = 1: the first round reads its groups straight from HBM into registers (no copy into shared
-  // memory first); st_direct = 1: the last round writes its groups straight back.  Needs warp_io, a round
+  // st_direct = 1: the last round writes its groups straight back to HBM.  Needs warp_io, a round
   // program, round bits outside tile positions 0..2 and lanes 0..7 of a warp on positions 0..2 (so 8 lanes
-  // still move one 128-byte run).  Saves one shared-memory write and one read of the whole tile each.
-  int32_t ld_direct, st_direct;
+  // still move one 128-byte run).  Saves one shared-memory write and one read of the whole tile.
+  int32_t st_direct, pad2_;
 };
 
 #endif  // QCC_B200_CSRC_QB_TYPES_H_

@@ -161,8 +161,8 @@ def interpret_plan(plan_json: str, n: int, gates, psi: np.ndarray) -> np.ndarray
             assert np.array_equal(copied, np.sort(je[mine].ravel())), f"{name}: warp {w} copies what it does not own"
       elif not p.get("warp_io"):
         assert p.get("ld_map", list(range(K))) == list(range(K)) and p.get("st_map", list(range(K))) == list(range(K))
-      # direct rounds: groups straight from / to HBM -- 8 lanes must still cover one 128-byte run
-      for flag, at in (("ld_direct", 0), ("st_direct", len(p["rounds"]) - 1)):
+      # direct-store round: groups straight to HBM -- 8 lanes must still cover one 128-byte run
+      for flag, at in (("st_direct", len(p["rounds"]) - 1),):
         if p.get(flag) and ri == at:
           assert p["warp_io"] and R["prog"] != 0
           assert min(rbit) >= 3 and sorted(qmap[:3]) == [0, 1, 2]

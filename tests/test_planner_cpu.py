@@ -216,3 +216,45 @@ def test_round_bank_classes():
       assert sorted(q % 3 for q in R["qmap"][:3]) == [0, 1, 2]
       seen += 1
   assert seen > 5
+
+
+def test_sleator_weinfurter_runs_become_one_doubly_controlled_gate():
+  """qb_flush's peephole (planner.cc fuse_ccu_runs, through qb_fuse_gates): the five gates circuit.py:227-246
+  emits for ccu(a, b, t, U) -- cu(a,t,V) cx(a,b) cu(b,t,V^dagger) cx(a,b) cu(b,t,V), V = sqrt(U) -- are replaced
+  by ONE gate on t controlled by a AND b (+ four identities); anything that merely looks similar is left alone.
+  Checked by running both gate lists on a random state with the index-bit reference."""
+  from scipy.linalg import sqrtm
+  from helpers import oracle, random_state, run_bits
+  n = 7
+  X, H = oracle.GATES["x"], oracle.GATES["h"]
+
+  def ccu(a, b, t, u):
+    v = np.asarray(sqrtm(np.asarray(u, dtype=np.complex128)))
+    return [(1 << a, t, v), (1 << a, b, X), (1 << b, t, v.conj().T), (1 << a, b, X), (1 << b, t, v)]
+
+  gates = [(0, q, H) for q in range(n)]
+  gates += ccu(0, 1, 2, X)                                   # Toffoli
+  gates += ccu(5, 3, 6, oracle.GATES["z"])                   # ccz
+  gates += ccu(4, 6, 0, oracle.u1(0.3))                      # ccu1
+  gates += [(0, 3, oracle.GATES["v"])]
+  gates += ccu(2, 4, 1, oracle.GATES["y"])
+  broken = ccu(1, 2, 3, X)
+  broken[2] = (broken[2][0], broken[2][1], broken[0][2])     # V instead of V^dagger: NOT a ccx
+  gates += broken
+  wrong_ctl = ccu(0, 5, 4, X)
+  wrong_ctl[3] = (1 << 6, 5, X)                              # second cx from another control
+  gates += wrong_ctl
+  fused, nruns = _cabi.fuse_gates(gates)
+  assert nruns == 4 and len(fused) == len(gates)
+  two_ctl = [g for g in fused if bin(g[0]).count("1") == 2]
+  assert len(two_ctl) == 4
+  # the Toffoli came out as the exact permutation matrix (so it runs as a pure swap)
+  assert np.array_equal(two_ctl[0][2], np.array([[0, 1], [1, 0]], dtype=np.complex128))
+  psi0 = random_state(n, 9)
+  want = run_bits(psi0.copy(), n, gates)
+  got = run_bits(psi0.copy(), n, fused)
+  assert np.abs(got - want).max() < 1e-13
+  # and the planner's output for the fused list still matches the oracle
+  from helpers import interpret_plan
+  out = interpret_plan(_cabi.plan_json(n, fused, 6), n, fused, psi0.copy())
+  assert np.abs(out - want).max() < 1e-12
