@@ -29,10 +29,22 @@ from qcc_b200 import _cabi, dumpers, ir, ops, state
 HOST_COMBINE_LIMIT = 28  # largest state (qubits) we will kron / expand through host memory
 
 
+_SQRTM_CACHE = {}
+
+
 def _sqrtm2(m: np.ndarray) -> np.ndarray:
-  """Principal square root of a 2x2 (circuit.py:238 uses scipy.linalg.sqrtm)."""
-  from scipy.linalg import sqrtm
-  return np.asarray(sqrtm(np.asarray(m, dtype=np.complex128)), dtype=np.complex128)
+  """Principal square root of a 2x2 (circuit.py:238 uses scipy.linalg.sqrtm).  Memoised on the matrix bytes: a
+  Toffoli ladder asks for the root of the same X thousands of times."""
+  a = np.ascontiguousarray(np.asarray(m, dtype=np.complex128))
+  key = a.tobytes()
+  r = _SQRTM_CACHE.get(key)
+  if r is None:
+    from scipy.linalg import sqrtm
+    r = np.asarray(sqrtm(a), dtype=np.complex128)
+    r.setflags(write=False)
+    if len(_SQRTM_CACHE) < 4096:
+      _SQRTM_CACHE[key] = r
+  return r
 
 
 class qc:

@@ -220,16 +220,23 @@ enum { QB_X_NCCL = 0, QB_X_SWAP = 1, QB_X_PUSH = 2 };
 // Fused execution: plan the queue into tile-resident passes and launch one kernel per pass.  With
 // `push` (an exchange event follows these gates, push mode) the LAST pass, when it is a fused pass,
 // stores through the event's bit permutation into the alternate buffers; *pushed says whether it did.
+double host_now_ms();
+
 int run_fused(qb_state *s, const std::vector<QbGate> &gates, const qb::PushMap *push, bool *pushed) {
+  static const bool trace = getenv("QCC_B200_TRACE_FLUSH") != nullptr;
+  const double t_a = trace ? host_now_ms() : 0.0;
   qb::Plan plan;
   qb::plan_gates(s->n, gates.data(), int64_t(gates.size()), s->tile_bits, &plan);
+  const double t_b = trace ? host_now_ms() : 0.0;
   // The staging buffers are reused flush after flush: wait until the previous plan's
   // kernels have consumed them.
   CU(cudaEventSynchronize(s->plan_free));
   size_t bytes = plan.blob_bytes();
   QB(ensure_plan_buffers(s, bytes));
+  const double t_c = trace ? host_now_ms() : 0.0;
   plan.serialize(static_cast<char *>(s->h_plan));
   CU(cudaMemcpyAsync(s->d_plan, s->h_plan, bytes, cudaMemcpyHostToDevice, s->stream));
+  const double t_d = trace ? host_now_ms() : 0.0;
   const char *dbase = static_cast<const char *>(s->d_plan);
   for (size_t k = 0; k < plan.passes.size(); ++k) {
     const qb::PlannedPass &pp = plan.passes[k];
@@ -244,10 +251,8 @@ int run_fused(qb_state *s, const std::vector<QbGate> &gates, const qb::PushMap *
     dp.ops = pp.ops.data();
     dp.rounds = pp.rounds.data();
     dp.tables = pp.desc.ntable ? reinterpret_cast<const double2 *>(dbase + pp.tables_off) : nullptr;
-    dp.outbits = pp.noutbits ? reinterpret_cast<const int32_t *>(dbase + pp.outbits_off) : nullptr;
     dp.outph = pp.outph.empty() ? nullptr : reinterpret_cast<const double2 *>(dbase + pp.outph_off);
     dp.jbtab = reinterpret_cast<const uint32_t *>(dbase + pp.jbtab_off);
-    dp.noutbits = pp.noutbits;
     const bool carry = push && k + 1 == plan.passes.size();
     if (carry) dp.push = push;
     double sweep = double(s->len) * 32.0;
@@ -263,6 +268,10 @@ int run_fused(qb_state *s, const std::vector<QbGate> &gates, const qb::PushMap *
     s->cnt.bytes_algorithmic += uint64_t(pp.bytes_algorithmic_per_amp * double(s->len));
   }
   CU(cudaEventRecord(s->plan_free, s->stream));
+  if (trace)
+    fprintf(stderr, "qcc_b200 run_fused: %zu gates, %zu passes: plan %.2f ms, wait for the previous plan %.2f ms, "
+            "stage %zu KiB %.2f ms, launches %.2f ms\n", gates.size(), plan.passes.size(), t_b - t_a, t_c - t_b,
+            bytes >> 10, t_d - t_c, host_now_ms() - t_d);
   return QB_OK;
 }
 
@@ -520,6 +529,8 @@ void make_layout(const qb_state *s, qb::ShardLayout *L) {
   L->pass_targets = std::max(1, s->tile_bits - QB_TILE_LOW);
 }
 
+}  // namespace
+namespace {
 double host_now_ms() {
   timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);

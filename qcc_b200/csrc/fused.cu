@@ -85,8 +85,10 @@ struct FusedParams {
   QbPassDesc desc;
   const double2 *tables;
   const double2 *outph;
-  const int32_t *outbits;
   const uint32_t *jbtab;
+  int nlad;                                   // ladder ops of the pass ...
+  uint32_t lad_tab[QB_MAX_PASS_LADDERS];      // ... first entry of their lookup tables in `tables`
+  uint32_t lad_ph[QB_MAX_PASS_LADDERS];       // ... first entry of their per-tile-constant tables in `outph`
   int push_on;   // 1: the store stage writes through `push` (exchange event fused into this pass)
   PushMap push;
   int debug;  // timing experiments only -- 1: skip the op loop, 2: skip the rounds, 4: skip the store, 8: skip the load, 16: no round programs, 32: (unused), 64: CTA barrier after every round
@@ -763,7 +765,6 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
 
   const uint32_t ngroups = tileN >> 3;
   const int gbits = K - QB_ROUND_BITS;
-  const int nb_tab = gbits > QB_LADDER_LANE_BITS ? 1 << (gbits - QB_LADDER_LANE_BITS) : 1;  // entries of T_b
   uint64_t base = blockIdx.x < ntiles ? tile_base(blockIdx.x) : 0;
   if (blockIdx.x < ntiles) issue_load(base);
   // ---- STAGE (once per CTA, behind the first tile's copy): ladder tables -> shared memory ----
@@ -779,32 +780,22 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
       const uint32_t bal = __ballot_sync(0xffffffffu, on);
       if ((tid & 31u) == 0) s_active[tid >> 5] = bal;
     }
-    // per-tile constants of the phase ladders (overlaps the wait for the tile's data): one
-    // warp per ladder, lane k owns outside bit k, product by butterfly shuffles.  (One warp with a
-    // lane per ladder needs 4x fewer instructions but was measured 9 % SLOWER on QFT-30: its serial
-    // chain of up to 18 dependent complex multiplies sits on every CTA's critical path.)
-    for (int oi = int(tid >> 5); oi < P.desc.nops; oi += kFThreads / 32) {
-      const QbOp *op = s_ops + oi;
-      const int k8 = op->kind & 0xff;
-      if (k8 == QB_K_LADDER || k8 == QB_K_ULADDER) {
-        const int lane = int(tid & 31u);
-        const double2 *ph = P.outph + op->outph_off;
-        double2 c = make_double2(1.0, 0.0);
-        if (lane < op->nout && ((base >> __ldg(P.outbits + op->out_off + lane)) & 1)) c = __ldg(ph + 1 + lane);
-        if (lane == 0) c = cmul(c, __ldg(ph));
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          double2 d;
-          d.x = __shfl_xor_sync(0xffffffffu, c.x, o);
-          d.y = __shfl_xor_sync(0xffffffffu, c.y, o);
-          c = cmul(c, d);
-        }
-        // Fold the per-tile constant into this tile's copy of T_b (<= 32 entries), so the hot
-        // loop needs one multiply less and one dependent shared-memory read less per op.
-        if (lane < nb_tab) {
-          const int e = op->table_off + (1 << QB_LADDER_LANE_BITS) + lane;
-          s_tab[e] = cmul(__ldg(P.tables + e), c);
-        }
+    // per-tile constants of the phase ladders, folded into this tile's copy of T_b (<= 32 entries per ladder)
+    // so the hot loop needs one multiply and one dependent shared-memory read less per op.  One thread per
+    // (ladder, T_b entry): three table entries selected by the fields of the tile number (host-built,
+    // planner.cc build_ladder_tables; L2-resident: 3 x 64 entries per ladder at 30 qubits), three complex
+    // multiplies, no shuffles, no serial chain -- it overlaps the wait for the tile's data.
+    {
+      const uint32_t f0 = t & ((1u << P.desc.lad_w[0]) - 1u);
+      const uint32_t f1 = (1u << P.desc.lad_w[0]) + ((t >> P.desc.lad_w[0]) & ((1u << P.desc.lad_w[1]) - 1u));
+      const uint32_t f2 = (1u << P.desc.lad_w[0]) + (1u << P.desc.lad_w[1]) + (t >> (P.desc.lad_w[0] + P.desc.lad_w[1]));
+      const int nb_log2 = gbits > QB_LADDER_LANE_BITS ? gbits - QB_LADDER_LANE_BITS : 0;
+      for (uint32_t x = tid; x < (uint32_t(P.nlad) << nb_log2); x += kFThreads) {
+        const uint32_t l = x >> nb_log2;
+        const double2 *ph = P.outph + P.lad_ph[l];
+        const uint32_t e = P.lad_tab[l] + (1u << QB_LADDER_LANE_BITS) + (x & ((1u << nb_log2) - 1u));
+        const double2 c = cmul(cmul(__ldg(ph + f0), __ldg(ph + f1)), __ldg(ph + f2));
+        s_tab[e] = cmul(__ldg(P.tables + e), c);
       }
     }
     if (warp_io) {
@@ -1022,7 +1013,15 @@ cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cuda
   memcpy(P.rounds, p.rounds, size_t(p.desc.nrounds) * sizeof(QbRound));
   P.tables = p.tables;
   P.outph = p.outph;
-  P.outbits = p.outbits;
+  P.nlad = 0;
+  for (int k = 0; k < p.desc.nops; ++k) {
+    const int k8 = p.ops[k].kind & 0xff;
+    if (k8 != QB_K_LADDER && k8 != QB_K_ULADDER) continue;
+    if (P.nlad == QB_MAX_PASS_LADDERS) return cudaErrorInvalidValue;
+    P.lad_tab[P.nlad] = uint32_t(p.ops[k].table_off);
+    P.lad_ph[P.nlad] = uint32_t(p.ops[k].outph_off);
+    ++P.nlad;
+  }
   P.jbtab = p.jbtab;
   static const int dbg = getenv("QCC_B200_FUSED_DEBUG") ? atoi(getenv("QCC_B200_FUSED_DEBUG")) : 0;
   P.debug = dbg;

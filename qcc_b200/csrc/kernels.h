@@ -77,10 +77,8 @@ struct DevicePass {
   const QbOp *ops;        // HOST: copied into the kernel parameters
   const QbRound *rounds;  // HOST
   const double2 *tables;  // device (ladder lookup tables, staged into smem) or nullptr
-  const double2 *outph;   // device (ladder per-tile constant + outside-bit phases) or nullptr
-  const int32_t *outbits; // device (ladder outside-bit lists) or nullptr
+  const double2 *outph;   // device (per ladder: three tables of per-tile constants, planner.cc) or nullptr
   const uint32_t *jbtab;  // device (per round, per group: base index | swizzled slot << 16)
-  int noutbits = 0;       // entries in outbits
   const PushMap *push = nullptr;  // HOST: the pass stores through this exchange event's bit permutation
 };
 cudaError_t fused_configure(int device);  // opt in to large dynamic shared memory, query SM count

@@ -296,7 +296,17 @@ void split_pred(const TileMap &tm, const int *rbit, int nr, uint64_t mask, uint6
   }
 }
 
-void build_ladder_tables(const TileMap &tm, const QbRound &r, const Item &it, int slot, PlannedPass *pp, QbOp *op) {
+// How the tile NUMBER (bit i = i-th index bit outside the tile, ascending) is cut into three fields for
+// the per-tile ladder constants: widths w0 >= w1 >= w2, w0 + w1 + w2 = nbits - K.
+void ladder_field_widths(int nbits, int K, int w[3]) {
+  const int nt = nbits - K;
+  w[0] = (nt + 2) / 3;
+  w[1] = (nt - w[0] + 1) / 2;
+  w[2] = nt - w[0] - w[1];
+}
+
+void build_ladder_tables(const TileMap &tm, const QbRound &r, const Item &it, int slot, int nbits, PlannedPass *pp,
+                         QbOp *op) {
   const int K = tm.K;
   // per tile-local position phase (1 where the position is not a partner / the pivot)
   Cplx per[QB_MAX_TILE_BITS];
@@ -331,8 +341,12 @@ void build_ladder_tables(const TileMap &tm, const QbRound &r, const Item &it, in
   //   [32, 32 + 2^(K-3-5))        T_b[q >> 5]  -- uniform per warp: broadcast reads; the kernel
   //                                               folds the per-tile constant into its copy
   // The 8 combinations of the round's own bits, F[e], travel inside the op descriptor (constant
-  // bank).  The per-tile constant lives in a second array (outph, from outph_off): the constant
-  // factor (self phase when the pivot is outside the tile), then one phase per outside bit.
+  // bank).  The per-tile constant -- the product of the phases of the partner bits OUTSIDE the tile that
+  // are set in the tile's base, times the self phase when the pivot is outside the tile -- is looked up
+  // too: the tile number is cut into three fields (ladder_field_widths) and a second array (outph, from
+  // outph_off) holds one small table per field, C_0[2^w0] (carrying the constant factor), C_1[2^w1],
+  // C_2[2^w2]; the kernel multiplies three entries per tile and ladder instead of walking the bits
+  // (18 outside bits at 30 qubits: 3 x 64 entries).
   op->table_off = int32_t(pp->tables.size());
   const int gbits = K - r.nbits;                       // group-index bits
   const int a_bits = std::min(gbits, QB_LADDER_LANE_BITS);
@@ -357,11 +371,31 @@ void build_ladder_tables(const TileMap &tm, const QbRound &r, const Item &it, in
     op->F[2 * e + 1] = p.y;
   }
   op->outph_off = int32_t(pp->outph.size());
-  pp->outph.push_back(self_out);
-  for (auto &p : out_ph) pp->outph.push_back(p);
+  {
+    std::vector<Cplx> per_t;   // phase of tile-number bit i
+    for (int b = 0; b < nbits; ++b) {
+      if (tm.mask >> b & 1) continue;
+      Cplx ph{1.0, 0.0};
+      for (size_t k = 0; k < out_bits.size(); ++k)
+        if (out_bits[k] == b) ph = cmulh(ph, out_ph[k]);
+      per_t.push_back(ph);
+    }
+    int w[3];
+    ladder_field_widths(nbits, K, w);
+    int first = 0;
+    for (int f = 0; f < 3; ++f) {
+      for (int v = 0; v < (1 << w[f]); ++v) {
+        Cplx p = f == 0 ? self_out : Cplx{1.0, 0.0};
+        for (int k = 0; k < w[f]; ++k)
+          if (v >> k & 1) p = cmulh(p, per_t[size_t(first + k)]);
+        pp->outph.push_back(p);
+      }
+      first += w[f];
+    }
+  }
   op->nout = int32_t(out_bits.size());
   op->out_off = int32_t(pp->outbits.size());
-  for (int b : out_bits) pp->outbits.push_back(b);
+  for (int b : out_bits) pp->outbits.push_back(b);   // kept for the plan dump; the kernel reads the tables
   op->flags = slot;
 }
 
@@ -661,7 +695,7 @@ std::vector<RoundPlan> schedule_rounds(const TileMap &tm, const std::vector<cons
   return out;
 }
 
-void close_round(const TileMap &tm, RoundPlan &rp, int *nladders, PlannedPass *pp) {
+void close_round(const TileMap &tm, RoundPlan &rp, int *nladders, int nbits, PlannedPass *pp) {
   std::vector<int> &rset = rp.rset;
   std::vector<PendingOp> &pend = rp.pend;
   const std::vector<int> &order = rp.order;
@@ -813,12 +847,12 @@ void close_round(const TileMap &tm, RoundPlan &rp, int *nladders, PlannedPass *p
       for (int k = 0; k < nr; ++k)
         if (r.rbit[k] == lp) op.tpos = k;
       memcpy(op.m, it.g.m, sizeof op.m);
-      build_ladder_tables(tm, r, lad, (*nladders)++, pp, &op);
+      build_ladder_tables(tm, r, lad, (*nladders)++, nbits, pp, &op);
       if (!lad_of[pi]) ++pi;
     } else if (it.kind == QB_K_LADDER) {
       op.kind = QB_K_LADDER;
       split_pred(tm, r.rbit, nr, uint64_t(1) << it.pivot, uint64_t(1) << it.pivot, &op);
-      build_ladder_tables(tm, r, it, (*nladders)++, pp, &op);
+      build_ladder_tables(tm, r, it, (*nladders)++, nbits, pp, &op);
     } else if (it.kind == QB_K_PHASE) {
       uint64_t bits = it.g.ctl_mask | (uint64_t(1) << it.g.target);
       split_pred(tm, r.rbit, nr, bits, bits, &op);
@@ -961,7 +995,8 @@ void emit_pass(int nbits, int K, const std::vector<const Item *> &items, const s
     if (sched.size() <= rplans.size()) rplans.swap(sched);
   }
   assign_group_maps(tm, &rplans, &pp.desc);
-  for (RoundPlan &rp : rplans) close_round(tm, rp, &nlad, &pp);
+  for (RoundPlan &rp : rplans) close_round(tm, rp, &nlad, nbits, &pp);
+  ladder_field_widths(nbits, tm.K, pp.desc.lad_w);
   pp.desc.nrounds = int32_t(pp.rounds.size());
   pp.desc.nops = int32_t(pp.ops.size());
   {
@@ -1172,8 +1207,6 @@ size_t Plan::blob_bytes() {
     off = align16(off + p.rounds.size() * sizeof(QbRound));
     p.tables_off = off;
     off = align16(off + p.tables.size() * sizeof(Cplx));
-    p.outbits_off = off;
-    off = align16(off + p.outbits.size() * sizeof(int32_t));
     p.outph_off = off;
     off = align16(off + p.outph.size() * sizeof(Cplx));
     p.jbtab_off = off;
@@ -1188,7 +1221,6 @@ void Plan::serialize(char *dst) const {
     memcpy(dst + p.ops_off, p.ops.data(), p.ops.size() * sizeof(QbOp));
     memcpy(dst + p.rounds_off, p.rounds.data(), p.rounds.size() * sizeof(QbRound));
     if (!p.tables.empty()) memcpy(dst + p.tables_off, p.tables.data(), p.tables.size() * sizeof(Cplx));
-    if (!p.outbits.empty()) memcpy(dst + p.outbits_off, p.outbits.data(), p.outbits.size() * sizeof(int32_t));
     if (!p.outph.empty()) memcpy(dst + p.outph_off, p.outph.data(), p.outph.size() * sizeof(Cplx));
     memcpy(dst + p.jbtab_off, p.jbtab.data(), p.jbtab.size() * sizeof(uint32_t));
   }
@@ -1213,8 +1245,9 @@ std::string Plan::to_json() const {
       s += "]}";
       continue;
     }
-    snprintf(buf, sizeof buf, "{\"single_gate\":-1,\"ngates\":%lld,\"K\":%d,\"warp_io\":%d,\"st_direct\":%d,\"ld_map\":[",
-             (long long)p.ngates, p.desc.K, p.desc.warp_io, p.desc.st_direct);
+    snprintf(buf, sizeof buf, "{\"single_gate\":-1,\"ngates\":%lld,\"K\":%d,\"warp_io\":%d,\"st_direct\":%d,\"lad_w\":[%d,%d,%d],\"ld_map\":[",
+             (long long)p.ngates, p.desc.K, p.desc.warp_io, p.desc.st_direct, p.desc.lad_w[0], p.desc.lad_w[1],
+             p.desc.lad_w[2]);
     s += buf;
     for (int k = 0; k < p.desc.K; ++k) {
       snprintf(buf, sizeof buf, "%s%d", k ? "," : "", p.desc.ld_map[k]);

@@ -27,8 +27,8 @@ struct PlannedPass {
   std::vector<QbOp> ops;
   std::vector<QbRound> rounds;
   std::vector<Cplx> tables;      // per ladder: T_a[32], T_b[2^(K-8)], indexed by group number (staged in smem)
-  std::vector<Cplx> outph;       // per ladder: constant factor, then one phase per outside bit
-  std::vector<int32_t> outbits;  // per ladder: the outside partner bits
+  std::vector<Cplx> outph;       // per ladder: three tables of per-tile constants over the fields of the tile number
+  std::vector<int32_t> outbits;  // per ladder: the outside partner bits (plan dump only)
   std::vector<uint32_t> jbtab;   // per round, per group q: jb | swizzled slot(jb) << 16
   // filled by Plan::layout(): byte offsets inside the serialized blob
   size_t ops_off = 0, rounds_off = 0, tables_off = 0, outbits_off = 0, outph_off = 0, jbtab_off = 0;

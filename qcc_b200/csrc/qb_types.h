@@ -96,10 +96,10 @@ struct alignas(16) QbOp {   // 256 bytes; lives in the kernel parameters (consta
   int32_t flags;     // LADDER: slot (0..63) of its per-tile constant in shared memory
   uint64_t gmask, gwant;   // PARSWAP: gmask = control bits outside the tile (parity), gwant unused
   double m[8];       // U/PERM: a b c d; PHASE: p in m[0..1]
-  int32_t nout;      // LADDER: number of partner bits outside the tile
-  int32_t out_off;   // LADDER: first entry in the pass's outside-bit array
+  int32_t nout;      // LADDER: number of partner bits outside the tile (plan dump only)
+  int32_t out_off;   // LADDER: first entry in the pass's outside-bit list (plan dump only)
   int32_t mflags;    // QB_MF_* properties of m
-  int32_t outph_off; // LADDER: first entry in the pass's outside-phase array ([0] = constant factor)
+  int32_t outph_off; // LADDER: first entry of its three per-tile-constant tables in the pass's outside-phase array
   double F[16];      // LADDER: phase of the round's own bits for each of the 8 registers (re, im)
 };
 
@@ -121,8 +121,10 @@ struct QbPassDesc {
   int32_t nseg;                        // runs of consecutive non-tile index bits (tile number -> base)
   int32_t seg_pos[QB_MAX_SEGS];        // first index bit of run r
   int32_t seg_len[QB_MAX_SEGS];        // its length; nseg > QB_MAX_SEGS is flagged as nseg = -1 (generic loop)
-  int32_t nout_total;                  // entries in the pass's outside-bit / outside-phase arrays
+  int32_t nout_total;                  // entries in the pass's outside-phase array
   int32_t pad_;
+  int32_t lad_w[3];                    // field widths of the tile number for the per-tile ladder constants (planner.cc)
+  int32_t pad3_;
   int32_t tile_bits[QB_MAX_TILE_BITS + 3];  // index-bit positions, ascending
   uint64_t tile_mask;                  // OR of 1 << tile_bits[k]
   // Tile <-> HBM copy maps: bit k of the copy index c = tid + 256 * iteration drives tile-local position

@@ -1,0 +1,9 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+./scripts/microbench/nvlink_write 2>&1 | tee gpurun_out/r02_nvlink_write.log
+timeout 600 python -m pytest tests/test_gpu_multi.py -m gpu -q -x -k "push-2" 2>&1 | tail -4
+PORT=$((29300 + RANDOM % 500))
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $PORT bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | tail -1 > gpurun_out/r02_qft30_2gpu_b.json
+python -c "
+import json; d=json.load(open('gpurun_out/r02_qft30_2gpu_b.json')); print(d['ms_per_step'], d['passes_per_step'], d['kernel_ms'], d['exchange']['nvlink_gbs_per_direction_rank0'])"

@@ -247,11 +247,14 @@ def interpret_plan(plan_json: str, n: int, gates, psi: np.ndarray) -> np.ndarray
           else:
             lad_rmask, lad_rwant = op["rmask"], op["rwant"]
           t0 = op["table_off"]
+          # per-tile constant: three tables over the fields of the tile number (planner.cc build_ladder_tables)
           cbase = op["outph_off"]
-          pout = np.full(ntiles, outph[cbase], dtype=np.complex128)
-          for k in range(op["nout"]):
-            bit = outbits[op["out_off"] + k]
-            pout = np.where((base >> bit) & 1 == 1, pout * outph[cbase + 1 + k], pout)
+          w0, w1, w2 = p["lad_w"]
+          assert w0 + w1 + w2 == n - K
+          pout = (outph[cbase + (tids & ((1 << w0) - 1))] *
+                  outph[cbase + (1 << w0) + ((tids >> w0) & ((1 << w1) - 1))] *
+                  outph[cbase + (1 << w0) + (1 << w1) + (tids >> (w0 + w1))])
+          assert all(b not in tb for b in outbits[op["out_off"]:op["out_off"] + op["nout"]])
           # tables are indexed by the group number: T_a[q & 31] (the lane), T_b[q >> 5]
           c = pout[:, None] * tables[t0 + (q & 31)][None, :] * tables[t0 + 32 + (q >> 5)][None, :]
           F = np.array([complex(op["F"][2 * e], op["F"][2 * e + 1]) for e in range(8)])
