@@ -96,6 +96,9 @@ struct qb_state {
   std::vector<cudaEvent_t> xevents;
   // CUDA IPC mappings of the other ranks' allocations (swap / push)
   std::vector<double2 *> peer_base; // [rank] -> mapping of its `base` (our own pointer for ourselves)
+  int nbuf = 1;                     // shards in `base` (2: push); the barrier counters sit behind them
+  unsigned long long xbar_epoch = 0;
+  bool peer_barrier = false;        // barriers through the counters in peer memory instead of an NCCL all-reduce
   double *d_sync = nullptr;        // scratch of the stream-ordered cross-rank barrier
   cudaStream_t stream = nullptr;
   double2 *psi = nullptr;
@@ -216,28 +219,65 @@ int ensure_plan_buffers(qb_state *s, size_t bytes) {
 }
 
 enum { QB_X_NCCL = 0, QB_X_SWAP = 1, QB_X_PUSH = 2 };
+constexpr size_t kBarrierBytes = 4096;   // arrival counters of the peer-memory barrier, behind the shard(s)
 
 // Fused execution: plan the queue into tile-resident passes and launch one kernel per pass.  With
 // `push` (an exchange event follows these gates, push mode) the LAST pass, when it is a fused pass,
 // stores through the event's bit permutation into the alternate buffers; *pushed says whether it did.
 double host_now_ms();
 
-int run_fused(qb_state *s, const std::vector<QbGate> &gates, const qb::PushMap *push, bool *pushed) {
+// One run of local gates of a flush.  All segments of a flush are planned first and staged as ONE blob with one
+// upload (stage_segments), so that the host never waits for the device between the segments of a sharded flush.
+struct Segment {
+  const std::vector<QbGate> *gates = nullptr;
+  qb::Plan plan;
+  bool planned = false;      // false: gate by gate (fusion off, or a shard too small for a tile)
+  size_t blob_off = 0;
+};
+
+int stage_segments(qb_state *s, std::vector<Segment> *segs, const std::vector<char> &event_follows) {
   static const bool trace = getenv("QCC_B200_TRACE_FLUSH") != nullptr;
   const double t_a = trace ? host_now_ms() : 0.0;
-  qb::Plan plan;
-  qb::plan_gates(s->n, gates.data(), int64_t(gates.size()), s->tile_bits, &plan);
+  size_t total = 0, npass = 0, ngates = 0;
+  for (size_t k = 0; k < segs->size(); ++k) {
+    Segment &sg = (*segs)[k];
+    if (!sg.gates || sg.gates->empty() || !(s->fusion && s->n > QB_TILE_LOW)) continue;
+    // an exchange event follows: the segment's last pass is made a fused pass whenever it has anything to do,
+    // so that the event can ride on its store stage
+    qb::plan_gates(s->n, sg.gates->data(), int64_t(sg.gates->size()), s->tile_bits, &sg.plan, event_follows[k] != 0);
+    sg.planned = true;
+    sg.blob_off = total;
+    total += (sg.plan.blob_bytes() + 255) & ~size_t(255);
+    npass += sg.plan.passes.size();
+    ngates += sg.gates->size();
+  }
+  if (!total) return QB_OK;
   const double t_b = trace ? host_now_ms() : 0.0;
-  // The staging buffers are reused flush after flush: wait until the previous plan's
-  // kernels have consumed them.
+  // The staging buffers are reused flush after flush: wait until the previous flush's kernels have consumed them.
   CU(cudaEventSynchronize(s->plan_free));
-  size_t bytes = plan.blob_bytes();
-  QB(ensure_plan_buffers(s, bytes));
+  QB(ensure_plan_buffers(s, total));
   const double t_c = trace ? host_now_ms() : 0.0;
-  plan.serialize(static_cast<char *>(s->h_plan));
-  CU(cudaMemcpyAsync(s->d_plan, s->h_plan, bytes, cudaMemcpyHostToDevice, s->stream));
-  const double t_d = trace ? host_now_ms() : 0.0;
-  const char *dbase = static_cast<const char *>(s->d_plan);
+  for (Segment &sg : *segs)
+    if (sg.planned) sg.plan.serialize(static_cast<char *>(s->h_plan) + sg.blob_off);
+  CU(cudaMemcpyAsync(s->d_plan, s->h_plan, total, cudaMemcpyHostToDevice, s->stream));
+  if (trace)
+    fprintf(stderr, "qcc_b200 stage: %zu gates in %zu segment(s), %zu passes: plan %.2f ms, wait for the previous flush "
+            "%.2f ms, stage %zu KiB %.2f ms\n", ngates, segs->size(), npass, t_b - t_a, t_c - t_b, total >> 10,
+            host_now_ms() - t_c);
+  return QB_OK;
+}
+
+// Launch the passes of one staged segment.  With `push` (an exchange event follows these gates, push mode) the
+// LAST pass, when it is a fused pass, stores through the event's bit permutation into the alternate buffers;
+// *pushed says whether it did.
+int launch_segment(qb_state *s, const Segment &sg, const qb::PushMap *push, bool *pushed) {
+  if (!sg.gates || sg.gates->empty()) return QB_OK;
+  if (!sg.planned) {
+    for (const QbGate &g : *sg.gates) QB(run_single(s, g));
+    return QB_OK;
+  }
+  const qb::Plan &plan = sg.plan;
+  const char *dbase = static_cast<const char *>(s->d_plan) + sg.blob_off;
   for (size_t k = 0; k < plan.passes.size(); ++k) {
     const qb::PlannedPass &pp = plan.passes[k];
     if (pp.single_gate >= 0) {
@@ -267,18 +307,16 @@ int run_fused(qb_state *s, const std::vector<QbGate> &gates, const qb::PushMap *
     s->cnt.gates_applied += uint64_t(pp.ngates);
     s->cnt.bytes_algorithmic += uint64_t(pp.bytes_algorithmic_per_amp * double(s->len));
   }
-  CU(cudaEventRecord(s->plan_free, s->stream));
-  if (trace)
-    fprintf(stderr, "qcc_b200 run_fused: %zu gates, %zu passes: plan %.2f ms, wait for the previous plan %.2f ms, "
-            "stage %zu KiB %.2f ms, launches %.2f ms\n", gates.size(), plan.passes.size(), t_b - t_a, t_c - t_b,
-            bytes >> 10, t_d - t_c, host_now_ms() - t_d);
   return QB_OK;
 }
 
-int run_local(qb_state *s, const std::vector<QbGate> &q, const qb::PushMap *push = nullptr, bool *pushed = nullptr) {
+int run_local(qb_state *s, const std::vector<QbGate> &q) {
   if (q.empty()) return QB_OK;
-  if (s->fusion && s->n > QB_TILE_LOW) return run_fused(s, q, push, pushed);
-  for (const QbGate &g : q) QB(run_single(s, g));
+  std::vector<Segment> segs(1);
+  segs[0].gates = &q;
+  QB(stage_segments(s, &segs, std::vector<char>(1, 0)));
+  QB(launch_segment(s, segs[0], nullptr, nullptr));
+  if (segs[0].planned) CU(cudaEventRecord(s->plan_free, s->stream));
   return QB_OK;
 }
 
@@ -297,10 +335,18 @@ int agree_min(qb_state *s, double *val) {
 // Stream-ordered barrier over all ranks: everything the ranks enqueued before it (their kernels' writes
 // into peer memory included -- a kernel's stores are performed when it completes) is done before anything
 // enqueued after it starts.
-int stream_barrier(qb_state *s) {
+int stream_barrier(qb_state *s, cudaStream_t st = nullptr) {
+  if (!st) st = s->stream;
+  if (s->peer_barrier) {
+    unsigned long long *rows[qb::kPushMaxRanks];
+    for (int q = 0; q < s->nranks; ++q)
+      rows[q] = reinterpret_cast<unsigned long long *>(s->peer_base[size_t(q)] + uint64_t(s->nbuf) * s->len);
+    CU(qb::launch_peer_barrier(rows, s->rank, s->nranks, ++s->xbar_epoch, st));
+    return QB_OK;
+  }
   const qb::NcclApi *nc = qb::nccl_api(nullptr);
   if (!nc || !s->comm) return fail(QB_ERR_COMM, "no communicator");
-  NC(nc, nc->AllReduce(s->d_sync, s->d_sync, 1, ncclDouble, ncclMin, s->comm, s->stream));
+  NC(nc, nc->AllReduce(s->d_sync, s->d_sync, 1, ncclDouble, ncclMin, s->comm, st));
   return QB_OK;
 }
 
@@ -491,27 +537,37 @@ int do_event(qb_state *s, const qb::ShardStep &ev) {
 }
 
 int run_steps(qb_state *s, const std::vector<qb::ShardStep> &steps) {
+  static const bool no_fuse = getenv("QCC_B200_NO_PUSH_FUSE") != nullptr;
+  std::vector<Segment> segs(steps.size());
+  std::vector<char> event_follows(steps.size(), 0);
+  for (size_t k = 0; k < steps.size(); ++k) {
+    if (steps[k].kind != 0) continue;
+    segs[k].gates = &steps[k].gates;
+    event_follows[k] = s->xmode == QB_X_PUSH && !no_fuse && k + 1 < steps.size() && steps[k + 1].kind == 1;
+  }
+  QB(stage_segments(s, &segs, event_follows));
+  bool any_planned = false;
   for (size_t k = 0; k < steps.size(); ++k) {
     const qb::ShardStep &st = steps[k];
     if (st.kind == 1) {
       QB(do_event(s, st));
       continue;
     }
+    any_planned = any_planned || segs[k].planned;
     // push mode: the event that follows these gates rides on the store stage of their last pass
-    const qb::ShardStep *ev = s->xmode == QB_X_PUSH && k + 1 < steps.size() && steps[k + 1].kind == 1 ? &steps[k + 1] : nullptr;
-    static const bool no_fuse = getenv("QCC_B200_NO_PUSH_FUSE") != nullptr;
-    if (no_fuse) ev = nullptr;
+    const qb::ShardStep *ev = event_follows[k] ? &steps[k + 1] : nullptr;
     qb::PushMap pm;
     if (ev) QB(make_push_map(s, *ev, &pm));
     bool pushed = false;
     const uint64_t before = s->cnt.gates_applied;
-    QB(run_local(s, st.gates, ev ? &pm : nullptr, &pushed));
+    QB(launch_segment(s, segs[k], ev ? &pm : nullptr, &pushed));
     s->cnt.gates_applied = before + uint64_t(st.retired);
     if (pushed) {
       QB(finish_push(s, *ev));
       ++k;
     }
   }
+  if (any_planned) CU(cudaEventRecord(s->plan_free, s->stream));
   return QB_OK;
 }
 
@@ -774,7 +830,7 @@ static int create_impl(int nqubits, uint64_t init_label, int device, int rank, i
     int rc = QB_OK;
     if (mode == QB_X_PUSH) {
       double ok = 2 * need + margin <= freeb ? 1.0 : 0.0;
-      if (ok != 0.0 && cudaMalloc(&s->base, 2 * need) != cudaSuccess) {
+      if (ok != 0.0 && cudaMalloc(&s->base, 2 * need + kBarrierBytes) != cudaSuccess) {
         cudaGetLastError();
         s->base = nullptr;
         ok = 0.0;
@@ -784,11 +840,13 @@ static int create_impl(int nqubits, uint64_t init_label, int device, int rank, i
         if (s->base) cudaFree(s->base);
         s->base = nullptr;
         mode = QB_X_SWAP;
+      } else {
+        s->nbuf = 2;
       }
     }
     if (rc == QB_OK && !s->base) {
       double ok = need + margin <= freeb ? 1.0 : 0.0;
-      if (ok != 0.0 && cudaMalloc(&s->base, need) != cudaSuccess) {
+      if (ok != 0.0 && cudaMalloc(&s->base, need + kBarrierBytes) != cudaSuccess) {
         cudaGetLastError();
         s->base = nullptr;
         ok = 0.0;
@@ -798,9 +856,13 @@ static int create_impl(int nqubits, uint64_t init_label, int device, int rank, i
         rc = fail(QB_ERR_NOMEM, "shard needs %zu MiB on every rank (this device has %zu MiB free)", need >> 20, freeb >> 20);
     }
     if (rc == QB_OK && mode != QB_X_NCCL) {
+      // the barrier counters behind the shard(s) start at zero on every rank before anybody can touch them
+      if (cudaMemsetAsync(s->base + uint64_t(s->nbuf) * s->len, 0, kBarrierBytes, s->stream) != cudaSuccess)
+        rc = fail(QB_ERR_CUDA, "barrier counters");
       bool mapped = false;
-      rc = map_peers(s, &mapped);
+      if (rc == QB_OK) rc = map_peers(s, &mapped);   // its agreement rounds order the memset before any peer access
       if (!mapped) mode = QB_X_NCCL;
+      else s->peer_barrier = nranks <= qb::kPushMaxRanks && !getenv("QCC_B200_NCCL_BARRIER");
     }
     if (rc != QB_OK) {
       qb_state_destroy(s);
@@ -1485,7 +1547,8 @@ int qb_shard_plan_stats(int nqubits, int nranks, int rank, const qb_gate *gates,
     steps.push_back(st);
   }
   bool tail_fused = false;
-  for (const qb::ShardStep &st : steps) {
+  for (size_t si = 0; si < steps.size(); ++si) {
+    const qb::ShardStep &st = steps[si];
     if (st.kind == 1) {
       stats[0] += 1;
       stats[1] += int64_t(st.rank_bits.size());
@@ -1496,7 +1559,8 @@ int qb_shard_plan_stats(int nqubits, int nranks, int rank, const qb_gate *gates,
     tail_fused = false;
     if (st.gates.empty()) continue;
     qb::Plan plan;
-    qb::plan_gates(nqubits - pbits, st.gates.data(), int64_t(st.gates.size()), tile_bits, &plan);
+    qb::plan_gates(nqubits - pbits, st.gates.data(), int64_t(st.gates.size()), tile_bits, &plan,
+                   prefetch && si + 1 < steps.size() && steps[si + 1].kind == 1);
     for (const qb::PlannedPass &pp : plan.passes) {
       stats[2] += 1;
       if (pp.single_gate < 0) {

@@ -69,6 +69,10 @@ inline uint64_t push_apply(const PushMap &m, uint64_t local) {   // distributed 
   return a;
 }
 cudaError_t launch_push_remap(const double2 *psi, const PushMap &m, cudaStream_t st);
+// Stream-ordered barrier over all ranks through counters in peer memory: rows[q] = rank q's row of kPushMaxRanks
+// arrival counters (mapped), epoch = 1, 2, 3, ... the same on every rank.
+cudaError_t launch_peer_barrier(unsigned long long *const *rows, int rank, int nranks, unsigned long long epoch,
+                                cudaStream_t st);
 cudaError_t launch_cvt_f2d(const float2 *in, double2 *out, uint64_t n, cudaStream_t st);
 
 // ---- fused tile-resident pass (fused.cu) ---------------------------------------

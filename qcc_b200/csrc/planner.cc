@@ -951,7 +951,7 @@ void close_round(const TileMap &tm, RoundPlan &rp, int *nladders, int nbits, Pla
 }
 
 void emit_pass(int nbits, int K, const std::vector<const Item *> &items, const std::vector<int> &targets_hi,
-               Plan *out) {
+               Plan *out, bool must_fuse = false) {
   if (items.empty()) return;
   // Cheap cases first: one real gate, or a handful of plain PHASE gates whose own sweeps
   // move less data than a full 32 B/amplitude pass.
@@ -964,8 +964,8 @@ void emit_pass(int nbits, int K, const std::vector<const Item *> &items, const s
     bytes += it->bytes_per_amp;
     if (it->kind != QB_K_PHASE) all_phase = false;
   }
-  if (real == 0 || (real == 1 && items.size() == 1 && items[0]->kind != QB_K_LADDER) ||
-      (all_phase && bytes <= 24.0)) {
+  if (real == 0 || (!must_fuse && ((real == 1 && items.size() == 1 && items[0]->kind != QB_K_LADDER) ||
+                                   (all_phase && bytes <= 24.0)))) {
     for (const Item *it : items) {
       PlannedPass pp;
       pp.single_gate = it->first_gate;
@@ -1143,7 +1143,7 @@ int64_t fuse_ccu_runs(QbGate *g, int64_t n) {
   return fused;
 }
 
-void plan_gates(int nbits, const QbGate *gates, int64_t ngates, int tile_bits, Plan *out) {
+void plan_gates(int nbits, const QbGate *gates, int64_t ngates, int tile_bits, Plan *out, bool fuse_last) {
   out->passes.clear();
   int K = std::max(4, std::min(tile_bits, QB_MAX_TILE_BITS));
   K = std::min(K, nbits);
@@ -1194,7 +1194,7 @@ void plan_gates(int nbits, const QbGate *gates, int64_t ngates, int tile_bits, P
     if (it.kind == QB_K_LADDER) nlad_pass += 1;
     cur.push_back(&it);
   }
-  emit_pass(nbits, K, cur, targets, out);
+  emit_pass(nbits, K, cur, targets, out, fuse_last);
 }
 
 size_t Plan::blob_bytes() {

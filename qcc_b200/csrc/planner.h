@@ -57,7 +57,9 @@ double gate_bytes_per_amp(const QbGate &g);
 // one doubly-controlled gate + four no-ops.  Returns the number of runs replaced.  See planner.cc.
 int64_t fuse_ccu_runs(QbGate *gates, int64_t ngates);
 
-void plan_gates(int nbits, const QbGate *gates, int64_t ngates, int tile_bits, Plan *out);
+// fuse_last: the last pass is made a fused pass even where a plain single-gate sweep would be cheaper (a sharded
+// state's exchange event is about to ride on its store stage).
+void plan_gates(int nbits, const QbGate *gates, int64_t ngates, int tile_bits, Plan *out, bool fuse_last = false);
 
 }  // namespace qb
 
