@@ -91,6 +91,8 @@ struct FusedParams {
   uint32_t lad_ph[QB_MAX_PASS_LADDERS];       // ... first entry of their per-tile-constant tables in `outph`
   int push_on;   // 1: the store stage writes through `push` (exchange event fused into this pass)
   PushMap push;
+  int stagger;   // experiment (QCC_B200_STAGGER=cycles): first-wave CTAs of resident slot j start j * stagger clocks late
+  int nsm;
   int debug;  // timing experiments only -- 1: skip the op loop, 2: skip the rounds, 4: skip the store, 8: skip the load, 16: no round programs, 32: (unused), 64: CTA barrier after every round
   // per copy iteration i (thread t moves copy index t + 256 i, see QbPassDesc::ld_map / st_map): global
   // offset of copy index 256 i in units of 8 amplitudes, and the XOR that takes the byte slot of copy
@@ -312,14 +314,12 @@ __device__ __forceinline__ void hladder(double2 (&a)[8], double r, double2 cf, c
 // non-trivial in-round phase and stage 2 none (true for the QFT; otherwise all of F is used).
 template <bool UPPER, bool FULL, bool SCALED, int IO = 0, int THREADS = kFThreads>
 __device__ __forceinline__ void round_hl3(const uint32_t tile_sa, const uint32_t tab_sa,
-                                          const uint32_t *__restrict__ jbt, const QbOp *__restrict__ o,
+                                          const uint32_t *__restrict__ jbt, const double2 *__restrict__ F0,
+                                          const double2 *__restrict__ F1, const double2 *__restrict__ F2,
                                           const QbRound *__restrict__ R, const RoundAux *__restrict__ X,
                                           const uint32_t ngroups, const uint32_t tid, double2 *const gp,
                                           const uint64_t g_t) {
   const double s = X->s;
-  const double2 *F0 = reinterpret_cast<const double2 *>(o[0].F);
-  const double2 *F1 = reinterpret_cast<const double2 *>(o[1].F);
-  const double2 *F2 = reinterpret_cast<const double2 *>(o[2].F);
   const uint32_t giters = FULL ? (ngroups / THREADS) : ((ngroups + THREADS - 1) / THREADS);
   const uint32_t b0 = X->b[0], b1 = X->b[1], b2 = X->b[2];
   // ladder tables: T_a[lane] (fixed per thread), T_b[q >> 5] (uniform per warp)
@@ -625,7 +625,10 @@ __device__ __forceinline__ void round_sync(bool warp_only) {
   else __syncthreads();
 }
 
-// One round that has a round program (QbRound::prog != GENERIC).
+// One round that has a round program (QbRound::prog != GENERIC).  (Specialising this code on the round number, so
+// that every per-round constant sits at a compile-time address of the parameter block, was measured in round 2:
+// no gain on QFT-30 -- fp64 instructions take their constants through uniform registers either way -- and 8 %
+// slower on larose-28 from the code growth.)
 template <bool FULL, int THREADS>
 __device__ __forceinline__ void program_round(const FusedParams &P, const int r, const int ob, const int oe,
                                               const uint32_t tile_sa, const uint32_t tab_sa,
@@ -634,6 +637,9 @@ __device__ __forceinline__ void program_round(const FusedParams &P, const int r,
   const QbRound *R = P.rounds + r;
   const RoundAux *X = P.aux + r;
   const QbOp *o = P.ops + ob;
+  const double2 *F0 = reinterpret_cast<const double2 *>(o[0].F);
+  const double2 *F1 = reinterpret_cast<const double2 *>(o[1].F);
+  const double2 *F2 = reinterpret_cast<const double2 *>(o[2].F);
   const uint32_t *jbt = P.jbtab + (size_t(r) << P.desc.ngroups_log2);
   const bool upper = R->prog == QB_PROG_HL3U;
   const bool st = FULL && direct && r + 1 == P.desc.nrounds && P.desc.st_direct;
@@ -659,11 +665,11 @@ __device__ __forceinline__ void program_round(const FusedParams &P, const int r,
   if (R->prog == QB_PROG_UX) {
     QB_ROUND_IO((round_ux<FULL, IO, THREADS>(tile_sa, jbt, o, oe - ob, R, X, ngroups, tid, base, gp, g_t, tab_sa)));
   } else if (X->s != 1.0) {
-    if (upper) QB_ROUND_IO((round_hl3<true, FULL, true, IO, THREADS>(tile_sa, tab_sa, jbt, o, R, X, ngroups, tid, gp, g_t)));
-    else QB_ROUND_IO((round_hl3<false, FULL, true, IO, THREADS>(tile_sa, tab_sa, jbt, o, R, X, ngroups, tid, gp, g_t)));
+    if (upper) QB_ROUND_IO((round_hl3<true, FULL, true, IO, THREADS>(tile_sa, tab_sa, jbt, F0, F1, F2, R, X, ngroups, tid, gp, g_t)));
+    else QB_ROUND_IO((round_hl3<false, FULL, true, IO, THREADS>(tile_sa, tab_sa, jbt, F0, F1, F2, R, X, ngroups, tid, gp, g_t)));
   } else {
-    if (upper) QB_ROUND_IO((round_hl3<true, FULL, false, IO, THREADS>(tile_sa, tab_sa, jbt, o, R, X, ngroups, tid, gp, g_t)));
-    else QB_ROUND_IO((round_hl3<false, FULL, false, IO, THREADS>(tile_sa, tab_sa, jbt, o, R, X, ngroups, tid, gp, g_t)));
+    if (upper) QB_ROUND_IO((round_hl3<true, FULL, false, IO, THREADS>(tile_sa, tab_sa, jbt, F0, F1, F2, R, X, ngroups, tid, gp, g_t)));
+    else QB_ROUND_IO((round_hl3<false, FULL, false, IO, THREADS>(tile_sa, tab_sa, jbt, F0, F1, F2, R, X, ngroups, tid, gp, g_t)));
   }
 #undef QB_ROUND_IO
 }
@@ -766,10 +772,21 @@ __global__ void __launch_bounds__(kFThreads, FAST ? 3 : 2) k_fused_pass(const __
   const uint32_t ngroups = tileN >> 3;
   const int gbits = K - QB_ROUND_BITS;
   uint64_t base = blockIdx.x < ntiles ? tile_base(blockIdx.x) : 0;
+  if (P.stagger > 0 && blockIdx.x >= uint32_t(P.nsm) && blockIdx.x < 3u * uint32_t(P.nsm)) {
+    // the CTAs of the first wave would all load, then all compute, then all store together, and their
+    // successors inherit the phase: the second and third resident CTA of an SM start a fraction of a tile late
+    const long long t0 = clock64(), wait = (long long)(P.stagger) * (long long)(blockIdx.x / uint32_t(P.nsm));
+    while (clock64() - t0 < wait) {
+    }
+  }
   if (blockIdx.x < ntiles) issue_load(base);
-  // ---- STAGE (once per CTA, behind the first tile's copy): ladder tables -> shared memory ----
-  for (int i = tid; i < P.desc.ntable; i += kFThreads) s_tab[i] = __ldg(P.tables + i);
-  __syncthreads();
+  // ---- STAGE (once per CTA, behind the first tile's copy): the per-lane halves T_a of the ladder tables ->
+  // shared memory.  The T_b halves are written per tile below (with the per-tile constant folded in), by
+  // other threads: staging them here as well would need a barrier in between.
+  for (uint32_t x = tid; x < (uint32_t(P.nlad) << QB_LADDER_LANE_BITS); x += kFThreads) {
+    const uint32_t e = P.lad_tab[x >> QB_LADDER_LANE_BITS] + (x & ((1u << QB_LADDER_LANE_BITS) - 1u));
+    s_tab[e] = __ldg(P.tables + e);
+  }
   for (uint32_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const uint32_t tn = t + gridDim.x;
     const bool more = tn < ntiles;
@@ -1025,6 +1042,9 @@ cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cuda
   P.jbtab = p.jbtab;
   static const int dbg = getenv("QCC_B200_FUSED_DEBUG") ? atoi(getenv("QCC_B200_FUSED_DEBUG")) : 0;
   P.debug = dbg;
+  static const int stagger = getenv("QCC_B200_STAGGER") ? atoi(getenv("QCC_B200_STAGGER")) : 0;
+  P.stagger = stagger;
+  P.nsm = g_sms;
   const int K = p.desc.K;
   if (K < 4 || K > QB_MAX_TILE_BITS || K > nbits) return cudaErrorInvalidValue;
   const unsigned ntiles = 1u << (nbits - K);
