@@ -705,11 +705,13 @@ def main():
                     "CUDA-event time of that kernel inside the timed region; traffic (ncu dram bytes) "
                     "is recorded under profiles/"}
   by_gate_alg = (c1["bytes_algorithmic"] - c0["bytes_algorithmic"]) / (ms * 1e-3) / 1e9
-  # ncu dram bytes per launch of the same kernels (profiles/r01_traffic.json, one --set full capture)
+  # ncu dram bytes per launch of the same kernels: a CONSTANT from profiles/r02_traffic.json (one --set full
+  # capture, provenance recorded there and copied into the line), not something this run measured
   try:
-    traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
-    if roof and n == traffic.get("qubits"):
+    traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+    if roof and n == traffic.get("qubits") and world == 1:
       roof["traffic"] = traffic.get(roof["kernel"])
+      roof["traffic_source"] = "profiles/r02_traffic.json: " + traffic.get("provenance", {}).get(roof["kernel"], "?")
   except Exception:  # pylint: disable=broad-except
     traffic = {}
 

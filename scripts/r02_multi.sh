@@ -26,7 +26,7 @@ if [ "$N" = 4 ]; then
   trun matrix_4 --matrix qft:28,qft:32,qft:34,supremacy:28,supremacy:30,supremacy:32,supremacy:34 --steps 4 --warmup 3
 fi
 if [ "$N" = 2 ]; then
-  trun matrix_2 --matrix qft:28,qft:32,supremacy:28,supremacy:30,supremacy:32 --steps 4 --warmup 3
+  trun matrix_2 --matrix qft:28,qft:32,supremacy:28,supremacy:30,supremacy:32,qft:34 --steps 4 --warmup 3
 fi
 python - <<PY
 import json, glob
