@@ -67,6 +67,7 @@ struct ProfRec {
   int kclass;
   double bytes;
   cudaEvent_t e0, e1;
+  std::string tag;   // QCC_B200_TRACE_FLUSH: what this launch was (printed with its time)
 };
 
 }  // namespace
@@ -156,10 +157,11 @@ struct ProfScope {
   qb_state *s;
   ProfRec rec;
   bool on;
-  ProfScope(qb_state *st, int kclass, double bytes) : s(st), on(st->profiling) {
+  ProfScope(qb_state *st, int kclass, double bytes, const std::string &tag = std::string()) : s(st), on(st->profiling) {
     if (on) {
       rec.kclass = kclass;
       rec.bytes = bytes;
+      rec.tag = tag;
       rec.e0 = get_event(s);
       rec.e1 = get_event(s);
       cudaEventRecord(rec.e0, s->stream);
@@ -181,6 +183,7 @@ int resolve_profile(qb_state *s) {
     s->prof.launches[r.kclass] += 1;
     s->prof.ms[r.kclass] += ms;
     s->prof.bytes[r.kclass] += r.bytes;
+    if (!r.tag.empty()) fprintf(stderr, "qcc_b200 launch: %.3f ms  %s\n", ms, r.tag.c_str());
     s->event_pool.push_back(r.e0);
     s->event_pool.push_back(r.e1);
   }
@@ -296,8 +299,19 @@ int launch_segment(qb_state *s, const Segment &sg, const qb::PushMap *push, bool
     const bool carry = push && k + 1 == plan.passes.size();
     if (carry) dp.push = push;
     double sweep = double(s->len) * 32.0;
+    std::string tag;
+    static const bool trace = getenv("QCC_B200_TRACE_FLUSH") != nullptr;
+    if (trace && s->profiling) {
+      tag = carry ? "push pass, tile bits" : "pass, tile bits";
+      for (int b = 0; b < pp.desc.K; ++b) tag += " " + std::to_string(pp.desc.tile_bits[b]);
+      if (carry) {
+        tag += "; moved";
+        for (int b = 0; b < push->nmoved; ++b) tag += " " + std::to_string(push->src[b]) + "->" + std::to_string(push->dst[b]);
+      }
+      tag += "; rounds " + std::to_string(pp.desc.nrounds) + " ops " + std::to_string(pp.desc.nops);
+    }
     {
-      ProfScope ps(s, carry ? QB_KCLASS_FUSED_PUSH : QB_KCLASS_FUSED, sweep);
+      ProfScope ps(s, carry ? QB_KCLASS_FUSED_PUSH : QB_KCLASS_FUSED, sweep, tag);
       CU(qb::launch_fused_pass(s->psi, s->n, dp, s->stream));
     }
     if (carry && pushed) *pushed = true;
