@@ -759,9 +759,19 @@ def main():
           s.xg_apply_gates(packed)
           _cabi.check(_cabi.lib().qb_copy_out(s._h, 0, 1 << n, host.array.ctypes.data))
         dt = time.perf_counter() - t0
+        # the two PCIe copies on their own (nothing queued), so that the step can be read against them
+        s.sync()
+        t1 = time.perf_counter()
+        _cabi.check(_cabi.lib().qb_copy_in(s._h, 0, 1 << n, host.array.ctypes.data))
+        t2 = time.perf_counter()
+        _cabi.check(_cabi.lib().qb_copy_out(s._h, 0, 1 << n, host.array.ctypes.data))
+        t3 = time.perf_counter()
         e2e = {"value": ngates * args.e2e_steps / dt, "unit": "gates/s",
                "h2d_bytes_per_step": (1 << n) * 16 + len(packed) * 80, "d2h_bytes_per_step": (1 << n) * 16,
                "steps": args.e2e_steps, "ms_per_step": dt / args.e2e_steps * 1e3,
+               "copy_in_ms": (t2 - t1) * 1e3, "copy_out_ms": (t3 - t2) * 1e3,
+               "step_over_the_two_copies": dt / args.e2e_steps / (t3 - t1),
+               "pcie_gbs": {"h2d": (1 << n) * 16 / (t2 - t1) / 1e9, "d2h": (1 << n) * 16 / (t3 - t2) / 1e9},
                "path": "pinned host complex128 state -> qb_copy_in -> qb_xg_apply_gates -> qb_copy_out "
                        "(what a host-buffer caller such as the libxgates/libq faces pays per circuit)"}
         host.close()

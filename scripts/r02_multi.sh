@@ -17,7 +17,8 @@ trun() {  # name, then bench args
 timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q -x -k "push-$N or swap-$N or nccl-$N" 2>&1 | tail -6 | tee gpurun_out/r02_pytest_multi$N.log
 trun scale_qft30_$N --steps 10 --warmup 3 --no-cpu-baseline --no-e2e
 if [ "$N" = 8 ]; then
-  trun qft34_8gpu --qubits 34 --steps 4 --warmup 3 --no-cpu-baseline --no-e2e
+  QCC_B200_TRACE_FLUSH=1 trun qft34_8gpu --qubits 34 --steps 4 --warmup 3 --no-cpu-baseline --no-e2e
+  grep "qcc_b200 launch" gpurun_out/r02_qft34_8gpu.err | sort | uniq -c | sort -k3 -n | tail -40 > gpurun_out/r02_qft34_8gpu_launches.txt
   trun supremacy34_8gpu --workload supremacy --qubits 34 --depth 20
   trun matrix_8 --matrix qft:28,qft:32,supremacy:28,supremacy:30,supremacy:32,supremacy:34 --steps 4 --warmup 3
 fi
