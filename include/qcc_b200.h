@@ -234,12 +234,12 @@ int qb_fuse_gates(qb_gate *gates, int64_t ngates, int64_t *fused);
  * Host only. */
 int qb_shard_plan_stats(int nqubits, int nranks, int rank, const qb_gate *gates, int64_t ngates, int tile_bits,
                         int window, int hoist, int prefetch, int64_t stats[8]);
-/* Where the push exchange of engine.cu writes: for one exchange event (npairs pairs: rank bit k <-> local
- * victim bit) and each local index of `rank`'s shard, the index in the DISTRIBUTED vector
- * (destination rank << nlocal | destination local index).  Host only; the CPU tests check it against the
- * pairwise send/recv layout. */
-int qb_shard_event_dest(int nlocal, int nranks, int rank, const int *rank_bits, const int *victims, int npairs,
-                        const uint64_t *local, uint64_t *dest, int64_t count);
+/* Where the push exchange of engine.cu writes: for one exchange event (npairs pairs: local victim bit -> rank
+ * bit, rank bit -> landing bit, landing bit -> victim bit; lands == NULL or lands[k] == victims[k]: plain swap)
+ * and each local index of `rank`'s shard, the index in the DISTRIBUTED vector (destination rank << nlocal |
+ * destination local index).  Host only; the CPU tests check it against the pairwise send/recv layout. */
+int qb_shard_event_dest(int nlocal, int nranks, int rank, const int *rank_bits, const int *victims, const int *lands,
+                        int npairs, const uint64_t *local, uint64_t *dest, int64_t count);
 /* Tile size (log2 amplitudes per CTA tile, 4..13, default 12) used by qb_flush. */
 int qb_set_tile_bits(qb_state *s, int tile_bits);
 

@@ -67,7 +67,8 @@ PROTOTYPES = {
     "qb_fuse_gates": [ctypes.POINTER(qb_gate), ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)],
     "qb_shard_plan_stats": [_I, _I, _I, ctypes.POINTER(qb_gate), ctypes.c_int64, _I, _I, _I, _I,
                             ctypes.POINTER(ctypes.c_int64)],
-    "qb_shard_event_dest": [_I, _I, _I, ctypes.POINTER(_I), ctypes.POINTER(_I), _I, _P, _P, ctypes.c_int64],
+    "qb_shard_event_dest": [_I, _I, _I, ctypes.POINTER(_I), ctypes.POINTER(_I), ctypes.POINTER(_I), _I, _P, _P,
+                            ctypes.c_int64],
     "qb_state_destroy": [_P],
     "qb_state_nqubits": [_P, ctypes.POINTER(_I)],
     "qb_set_basis": [_P, _U64],
@@ -235,12 +236,14 @@ def shard_plan_stats(nqubits: int, nranks: int, rank: int, gates, tile_bits: int
 
 
 def shard_event_dest(nlocal: int, nranks: int, rank: int, pairs, local: np.ndarray) -> np.ndarray:
-  """Distributed destination index of each local index under one exchange event (host only)."""
+  """Distributed destination index of each local index under one exchange event (host only).
+  pairs: (rank bit, victim bit[, landing bit])."""
   rb = (ctypes.c_int * len(pairs))(*[int(p[0]) for p in pairs])
   vb = (ctypes.c_int * len(pairs))(*[int(p[1]) for p in pairs])
+  lb = (ctypes.c_int * len(pairs))(*[int(p[2]) if len(p) > 2 else int(p[1]) for p in pairs])
   local = np.ascontiguousarray(local, dtype=np.uint64)
   dest = np.empty_like(local)
-  check(lib().qb_shard_event_dest(nlocal, nranks, rank, rb, vb, len(pairs), local.ctypes.data, dest.ctypes.data,
+  check(lib().qb_shard_event_dest(nlocal, nranks, rank, rb, vb, lb, len(pairs), local.ctypes.data, dest.ctypes.data,
                                   local.size))
   return dest
 

@@ -488,34 +488,48 @@ int do_exchange(qb_state *s, int rank_bit, int victim) {
 }
 
 // The bit permutation of an exchange event as the store map of one rank (push mode); out[] is left empty.
-int event_map(int nl, int p, int rank, const int *rank_bits, const int *victims, size_t np, qb::PushMap *m) {
+// Pair k: local victim bit -> rank bit, rank bit -> landing bit, and (landing != victim) landing bit -> victim bit.
+int event_map(int nl, int p, int rank, const int *rank_bits, const int *victims, const int *lands, size_t np,
+              qb::PushMap *m) {
   *m = qb::PushMap();
-  if (np == 0 || np > size_t(qb::kPushMaxMoved)) return fail(QB_ERR_ARG, "exchange event with %zu pairs", np);
+  if (np == 0 || 2 * np > size_t(qb::kPushMaxMoved)) return fail(QB_ERR_ARG, "exchange event with %zu pairs", np);
   m->nl = nl;
-  m->nmoved = int(np);
   uint64_t rt = 0;
   for (int b = 0; b < p; ++b) {
     int dest = nl + b;   // a rank bit outside the event stays a rank bit
     for (size_t k = 0; k < np; ++k)
-      if (rank_bits[k] == b) dest = victims[k];
+      if (rank_bits[k] == b) dest = lands ? lands[k] : victims[k];
     rt |= uint64_t((rank >> b) & 1) << dest;
   }
   m->rank_term = rt;
+  uint64_t seen = 0;
   for (size_t k = 0; k < np; ++k) {
-    if (victims[k] < QB_TILE_LOW || victims[k] >= nl || rank_bits[k] < 0 || rank_bits[k] >= p)
-      return fail(QB_ERR_ARG, "exchange pair (rank bit %d, victim bit %d)", rank_bits[k], victims[k]);
+    const int land = lands ? lands[k] : victims[k];
+    if (victims[k] < QB_TILE_LOW || victims[k] >= nl || land < QB_TILE_LOW || land >= nl || rank_bits[k] < 0 ||
+        rank_bits[k] >= p)
+      return fail(QB_ERR_ARG, "exchange pair (rank bit %d, victim bit %d, landing bit %d)", rank_bits[k], victims[k], land);
     for (size_t j = 0; j < k; ++j)
-      if (victims[j] == victims[k] || rank_bits[j] == rank_bits[k]) return fail(QB_ERR_ARG, "exchange pairs overlap");
-    m->src[k] = victims[k];
-    m->dst[k] = nl + rank_bits[k];
+      if (rank_bits[j] == rank_bits[k]) return fail(QB_ERR_ARG, "exchange pairs overlap");
+    if ((seen >> victims[k] & 1) || (land != victims[k] && (seen >> land & 1))) return fail(QB_ERR_ARG, "exchange pairs overlap");
+    seen |= (uint64_t(1) << victims[k]) | (uint64_t(1) << land);
+    m->src[m->nmoved] = victims[k];
+    m->dst[m->nmoved] = nl + rank_bits[k];
     m->moved_mask |= uint64_t(1) << victims[k];
+    ++m->nmoved;
+    if (land != victims[k]) {
+      m->src[m->nmoved] = land;
+      m->dst[m->nmoved] = victims[k];
+      m->moved_mask |= uint64_t(1) << land;
+      ++m->nmoved;
+    }
   }
   return QB_OK;
 }
 
 int make_push_map(const qb_state *s, const qb::ShardStep &ev, qb::PushMap *m) {
-  if (ev.rank_bits.size() != ev.victims.size()) return fail(QB_ERR_ARG, "bad exchange event");
-  QB(event_map(s->n, s->p, s->rank, ev.rank_bits.data(), ev.victims.data(), ev.rank_bits.size(), m));
+  if (ev.rank_bits.size() != ev.victims.size() || ev.lands.size() != ev.victims.size())
+    return fail(QB_ERR_ARG, "bad exchange event");
+  QB(event_map(s->n, s->p, s->rank, ev.rank_bits.data(), ev.victims.data(), ev.lands.data(), ev.rank_bits.size(), m));
   for (int r = 0; r < s->nranks; ++r) m->out[r] = s->peer_base[size_t(r)] + (s->bufsel ? 0 : s->len);
   return QB_OK;
 }
@@ -596,6 +610,7 @@ void make_layout(const qb_state *s, qb::ShardLayout *L) {
   L->hoist = s->xmode != QB_X_NCCL ? 1 : 0;
   L->prefetch = s->xmode == QB_X_PUSH ? 1 : 0;
   if (getenv("QCC_B200_NO_PREFETCH")) L->prefetch = 0;
+  L->land = s->xmode == QB_X_PUSH && !getenv("QCC_B200_NO_LAND") ? 1 : 0;
   L->pass_targets = std::max(1, s->tile_bits - QB_TILE_LOW);
 }
 
@@ -1510,6 +1525,7 @@ int qb_shard_lower_json(int nqubits, int nranks, int rank, const qb_gate *gates,
   if (const char *w = getenv("QCC_B200_VICTIM_WINDOW")) L.window = std::max(1, atoi(w));  // tests: the peer-swap window
   if (const char *h = getenv("QCC_B200_HOIST")) L.hoist = atoi(h);                        // ... and its exchange hoisting
   if (const char *h = getenv("QCC_B200_PREFETCH")) L.prefetch = atoi(h);                  // ... and multi-bit events
+  if (const char *h = getenv("QCC_B200_LAND")) L.land = atoi(h);                          // ... landing on the high bits
   std::vector<qb::ShardStep> steps;
   qb::lower_for_rank(&L, q.data(), ngates, &steps);
   if (canonicalize) qb::canonicalize_steps(&L, &steps);
@@ -1553,6 +1569,7 @@ int qb_shard_plan_stats(int nqubits, int nranks, int rank, const qb_gate *gates,
     L.window = std::max(1, std::min(window, L.nl));
     L.hoist = hoist;
     L.prefetch = prefetch;
+    L.land = prefetch && !getenv("QCC_B200_NO_LAND") ? 1 : 0;
     L.pass_targets = std::max(1, tile_bits - QB_TILE_LOW);
     qb::lower_for_rank(&L, q.data(), ngates, &steps);
   } else {
@@ -1606,14 +1623,14 @@ int qb_fuse_gates(qb_gate *gates, int64_t ngates, int64_t *fused) {
   return QB_OK;
 }
 
-int qb_shard_event_dest(int nlocal, int nranks, int rank, const int *rank_bits, const int *victims, int npairs,
-                        const uint64_t *local, uint64_t *dest, int64_t count) {
+int qb_shard_event_dest(int nlocal, int nranks, int rank, const int *rank_bits, const int *victims, const int *lands,
+                        int npairs, const uint64_t *local, uint64_t *dest, int64_t count) {
   if (!rank_bits || !victims || (!local && count) || (!dest && count)) return fail(QB_ERR_ARG, "null pointer");
   if (nranks < 1 || (nranks & (nranks - 1)) || rank < 0 || rank >= nranks) return fail(QB_ERR_ARG, "bad rank/nranks");
   int pbits = 0;
   while ((1 << pbits) < nranks) ++pbits;
   qb::PushMap m;
-  QB(event_map(nlocal, pbits, rank, rank_bits, victims, size_t(npairs), &m));
+  QB(event_map(nlocal, pbits, rank, rank_bits, victims, lands, size_t(npairs), &m));
   for (int64_t k = 0; k < count; ++k) dest[k] = qb::push_apply(m, local[k]);
   return QB_OK;
 }

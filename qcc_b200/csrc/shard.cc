@@ -49,28 +49,48 @@ int64_t next_need(const QbGate *gates, int64_t ngates, int64_t from, int lq) {
 // value of the LOGICAL qubit that lives at global physical position pb, on this rank
 int global_bit(const ShardLayout &L, int pb) { return int(((uint32_t(L.rank) ^ L.flip) >> (pb - L.nl)) & 1u); }
 
-// One exchange event: every (global position, victim) pair is swapped; a relabelled (flipped) rank bit
-// arrives in its victim bit as the negation of its qubit: one local x puts it right, and the new
-// occupant of the rank bit is plain.
+// One exchange event: every (global position, victim) pair is exchanged -- the victim's qubit goes to the rank
+// bit, the rank bit's qubit to the landing bit (the victim bit itself unless L->land picks a higher one, whose
+// occupant then moves down into the victim bit).  A relabelled (flipped) rank bit arrives as the negation of its
+// qubit: one local x on the landing bit puts it right, and the new occupant of the rank bit is plain.
 void exchange_event(ShardLayout *L, const std::vector<std::pair<int, int>> &pairs, ShardStep *cur,
                     std::vector<ShardStep> *steps) {
   close_step(cur, steps);
   ShardStep ex;
   ex.kind = 1;
-  for (const auto &pr : pairs) {
-    const int global_pos = pr.first, victim = pr.second;
+  // landing bits: the highest local bits that are not victims of this event, highest first, for the pairs in
+  // order; a pair whose victim is already above what is left keeps the plain swap
+  std::vector<int> lands(pairs.size());
+  {
+    std::vector<char> taken(static_cast<size_t>(L->nl), 0);
+    for (const auto &pr : pairs) taken[size_t(pr.second)] = 1;
+    int h = L->nl - 1;
+    for (size_t k = 0; k < pairs.size(); ++k) {
+      lands[k] = pairs[k].second;
+      if (!L->land) continue;
+      while (h >= 0 && taken[size_t(h)]) --h;
+      if (h > pairs[k].second) {
+        lands[k] = h;
+        taken[size_t(h)] = 1;
+      }
+    }
+  }
+  for (size_t k = 0; k < pairs.size(); ++k) {
+    const int global_pos = pairs[k].first, victim = pairs[k].second, land = lands[k];
     ex.rank_bits.push_back(global_pos - L->nl);
     ex.victims.push_back(victim);
+    ex.lands.push_back(land);
     std::vector<int> inv = inverse_of(L->perm);
-    const int la = inv[size_t(global_pos)], lb = inv[size_t(victim)];
-    L->perm[size_t(la)] = victim;
-    L->perm[size_t(lb)] = global_pos;
+    const int q_in = inv[size_t(global_pos)], q_out = inv[size_t(victim)], q_down = inv[size_t(land)];
+    L->perm[size_t(q_out)] = global_pos;
+    L->perm[size_t(q_in)] = land;
+    if (land != victim) L->perm[size_t(q_down)] = victim;
     const uint32_t fb = 1u << (global_pos - L->nl);
     if (L->flip & fb) {
       L->flip &= ~fb;
       QbGate x{};
       x.ctl_mask = 0;
-      x.target = victim;
+      x.target = land;
       x.kind = QB_K_PERM;
       memcpy(x.m, kX, sizeof kX);
       cur->gates.push_back(x);
@@ -328,7 +348,7 @@ std::string steps_to_json(const ShardLayout &L, const std::vector<ShardStep> &st
     if (st.kind == 1) {
       s += "{\"kind\":1,\"pairs\":[";
       for (size_t j = 0; j < st.rank_bits.size(); ++j) {
-        snprintf(buf, sizeof buf, "%s[%d,%d]", j ? "," : "", st.rank_bits[j], st.victims[j]);
+        snprintf(buf, sizeof buf, "%s[%d,%d,%d]", j ? "," : "", st.rank_bits[j], st.victims[j], st.lands[j]);
         s += buf;
       }
       s += "]}";

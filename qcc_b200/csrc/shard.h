@@ -43,6 +43,12 @@ struct ShardStep {
   int64_t retired = 0;   // logical gate records this step accounts for (incl. skipped ones)
   std::vector<int> rank_bits;
   std::vector<int> victims;
+  // lands[k]: the local bit where the qubit that comes in from rank bit rank_bits[k] is put.  == victims[k]: a
+  // plain swap.  Otherwise a 3-cycle (push exchange only, which is an out-of-place remap anyway): victim bit ->
+  // rank bit, rank bit -> lands[k], lands[k] -> victim bit.  Landing on the HIGHEST local bits keeps the low
+  // address bits of every (source, destination) flow free: with the rank bits of the source frozen into LOW
+  // address bits of the destination, NVLink pushes were measured at 155-570 GB/s instead of 690.
+  std::vector<int> lands;
 };
 
 struct ShardLayout {
@@ -66,6 +72,7 @@ struct ShardLayout {
   // extra bits are nearly free, whereas a separate event later costs another half shard.  Only with the
   // push exchange; the pairwise exchanges pay half a shard per bit either way.
   int prefetch = 0;
+  int land = 0;    // 1: arriving qubits land on the highest local bits (see ShardStep::lands); push exchange only
 };
 
 // Victims are taken from the top `kVictimWindow` local bits so that the exchanged half

@@ -102,8 +102,10 @@ def _worker(rank, world, port, n, out_dir):
               assert g["ctl_mask"] < (1 << nl) and g["target"] < nl
               apply_masked(shard, nl, g["ctl_mask"], g["target"], m)
             continue
-          assert len({k for k, _ in st["pairs"]}) == len(st["pairs"]) == len({v for _, v in st["pairs"]})
-          for k, v in st["pairs"]:   # the pairs of an event are disjoint: one after the other == all at once
+          assert len({k for k, _, _ in st["pairs"]}) == len(st["pairs"])
+          assert len({v for _, v, _ in st["pairs"]} | {h for _, _, h in st["pairs"]}) == \
+              len(st["pairs"]) + sum(1 for _, v, h in st["pairs"] if h != v)
+          for k, v, h in st["pairs"]:   # the pairs of an event are disjoint: one after the other == all at once
             b = (rank >> k) & 1
             partner = rank ^ (1 << k)
             sel = 0 if b else 1
@@ -115,6 +117,10 @@ def _worker(rank, world, port, n, out_dir):
             for r in reqs:
               r.wait()
             view[:, sel, :] = recv.numpy().view(np.complex128).reshape(nruns, run)
+            if h != v:                  # landing bit: the arrived qubit moves on to bit h, bit h's occupant down to v
+              idx = np.arange(1 << nl)
+              bv, bh = (idx >> v) & 1, (idx >> h) & 1
+              shard = shard[idx ^ ((bv ^ bh) << v) ^ ((bv ^ bh) << h)]
         if not canon:
           assert retired == len(gates)
         # gather shards on rank 0 and undo the bit permutation
@@ -143,10 +149,11 @@ def _worker(rank, world, port, n, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n,window,hoist,prefetch",
-                         [(2, 9, None, 0, 0), (4, 10, None, 0, 0), (4, 10, 30, 0, 0), (4, 10, 30, 1, 0), (2, 12, 30, 1, 0),
-                          (4, 10, 7, 1, 1), (8, 12, 9, 1, 1), (4, 13, 10, 0, 1)])
-def test_sharded_lowering_over_gloo(world, n, window, hoist, prefetch, tmp_path, monkeypatch):
+@pytest.mark.parametrize("world,n,window,hoist,prefetch,land",
+                         [(2, 9, None, 0, 0, 0), (4, 10, None, 0, 0, 0), (4, 10, 30, 0, 0, 0), (4, 10, 30, 1, 0, 0),
+                          (2, 12, 30, 1, 0, 0), (4, 10, 7, 1, 1, 0), (8, 12, 9, 1, 1, 1), (4, 13, 10, 0, 1, 1),
+                          (2, 11, 8, 1, 1, 1)])
+def test_sharded_lowering_over_gloo(world, n, window, hoist, prefetch, land, tmp_path, monkeypatch):
   """window: the victim window of the peer-memory exchanges (any local bit above the lowest few),
   QCC_B200_VICTIM_WINDOW; hoist = 1: exchanges moved back to pass boundaries (QCC_B200_HOIST), gates in
   between lowered again; prefetch = 1: multi-bit events (QCC_B200_PREFETCH), the push exchange's setting."""
@@ -157,6 +164,8 @@ def test_sharded_lowering_over_gloo(world, n, window, hoist, prefetch, tmp_path,
     monkeypatch.setenv("QCC_B200_HOIST", "1")
   if prefetch:
     monkeypatch.setenv("QCC_B200_PREFETCH", "1")
+  if land:
+    monkeypatch.setenv("QCC_B200_LAND", "1")   # arriving qubits land on the highest local bits (3-cycles)
   port = _free_port()
   mp.spawn(_worker, args=(world, port, n, str(tmp_path)), nprocs=world, join=True)
   flips_seen = 0
@@ -218,16 +227,24 @@ def test_push_event_destinations_equal_pairwise_exchanges():
   from qcc_b200 import _cabi
   rng = np.random.default_rng(7)
   for world, nl, pairs in [(2, 6, [(0, 4)]), (4, 7, [(1, 5)]), (4, 7, [(0, 3), (1, 6)]), (8, 8, [(2, 7), (0, 4)]),
-                           (8, 9, [(1, 3), (2, 8), (0, 5)])]:
+                           (8, 9, [(1, 3), (2, 8), (0, 5)]), (2, 7, [(0, 3, 6)]), (8, 10, [(1, 3, 9), (2, 4, 8), (0, 7, 7)]),
+                           (4, 9, [(0, 5, 8), (1, 3, 7)])]:
     full = rng.normal(size=world << nl) + 1j * rng.normal(size=world << nl)
     shards = [full[r << nl:(r + 1) << nl].copy() for r in range(world)]
     want = [x.copy() for x in shards]
-    for k, v in pairs:
+    for pr in pairs:
+      k, v = pr[0], pr[1]
+      h = pr[2] if len(pr) > 2 else v
       nxt = [x.copy() for x in want]
       run, nruns = 1 << v, 1 << (nl - 1 - v)
       for r in range(world):
         sel = 0 if (r >> k) & 1 else 1
         nxt[r].reshape(nruns, 2, run)[:, sel, :] = want[r ^ (1 << k)].reshape(nruns, 2, run)[:, 1 - sel, :]
+      if h != v:    # landing bit: then local bits v and h trade places on every rank
+        idx = np.arange(1 << nl)
+        bv, bh = (idx >> v) & 1, (idx >> h) & 1
+        sw = idx ^ ((bv ^ bh) << v) ^ ((bv ^ bh) << h)
+        nxt = [x[sw] for x in nxt]
       want = nxt
     got = np.full(world << nl, np.nan + 0j)
     for r in range(world):
