@@ -891,7 +891,9 @@ static int create_impl(int nqubits, uint64_t init_label, int device, int rank, i
       bool mapped = false;
       if (rc == QB_OK) rc = map_peers(s, &mapped);   // its agreement rounds order the memset before any peer access
       if (!mapped) mode = QB_X_NCCL;
-      else s->peer_barrier = nranks <= qb::kPushMaxRanks && !getenv("QCC_B200_NCCL_BARRIER");
+      // The counters-in-peer-memory barrier (k_peer_barrier) is opt-in: 23 us instead of 85 us per event on 2
+      // GPUs, but runs with it were not reproducibly as fast as runs with the NCCL all-reduce.
+      else s->peer_barrier = nranks <= qb::kPushMaxRanks && getenv("QCC_B200_PEER_BARRIER") != nullptr;
     }
     if (rc != QB_OK) {
       qb_state_destroy(s);
