@@ -610,7 +610,8 @@ void make_layout(const qb_state *s, qb::ShardLayout *L) {
   L->hoist = s->xmode != QB_X_NCCL ? 1 : 0;
   L->prefetch = s->xmode == QB_X_PUSH ? 1 : 0;
   if (getenv("QCC_B200_NO_PREFETCH")) L->prefetch = 0;
-  L->land = s->xmode == QB_X_PUSH && !getenv("QCC_B200_NO_LAND") ? 1 : 0;
+  // landing bits (ShardStep::lands) are opt-in: measured on 8 GPUs at 34 qubits they did not help
+  L->land = s->xmode == QB_X_PUSH && getenv("QCC_B200_LAND") && atoi(getenv("QCC_B200_LAND")) ? 1 : 0;
   L->pass_targets = std::max(1, s->tile_bits - QB_TILE_LOW);
 }
 
@@ -1571,7 +1572,7 @@ int qb_shard_plan_stats(int nqubits, int nranks, int rank, const qb_gate *gates,
     L.window = std::max(1, std::min(window, L.nl));
     L.hoist = hoist;
     L.prefetch = prefetch;
-    L.land = prefetch && !getenv("QCC_B200_NO_LAND") ? 1 : 0;
+    L.land = prefetch && getenv("QCC_B200_LAND") && atoi(getenv("QCC_B200_LAND")) ? 1 : 0;
     L.pass_targets = std::max(1, tile_bits - QB_TILE_LOW);
     qb::lower_for_rank(&L, q.data(), ngates, &steps);
   } else {

@@ -46,8 +46,8 @@ struct ShardStep {
   // lands[k]: the local bit where the qubit that comes in from rank bit rank_bits[k] is put.  == victims[k]: a
   // plain swap.  Otherwise a 3-cycle (push exchange only, which is an out-of-place remap anyway): victim bit ->
   // rank bit, rank bit -> lands[k], lands[k] -> victim bit.  Landing on the HIGHEST local bits keeps the low
-  // address bits of every (source, destination) flow free: with the rank bits of the source frozen into LOW
-  // address bits of the destination, NVLink pushes were measured at 155-570 GB/s instead of 690.
+  // address bits of every (source, destination) flow free.  Opt-in (QCC_B200_LAND=1): measured on 8 GPUs at 34
+  // qubits it did not make the slow push passes (low victim bits) any faster.
   std::vector<int> lands;
 };
 
@@ -72,7 +72,7 @@ struct ShardLayout {
   // extra bits are nearly free, whereas a separate event later costs another half shard.  Only with the
   // push exchange; the pairwise exchanges pay half a shard per bit either way.
   int prefetch = 0;
-  int land = 0;    // 1: arriving qubits land on the highest local bits (see ShardStep::lands); push exchange only
+  int land = 0;    // 1: arriving qubits land on the highest local bits (see ShardStep::lands); push exchange only, opt-in
 };
 
 // Victims are taken from the top `kVictimWindow` local bits so that the exchanged half

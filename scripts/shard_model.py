@@ -37,7 +37,7 @@ def model(name, n, world, reps, mode="push", rank=0):
     os.environ["QCC_B200_VICTIM_WINDOW"] = str(min(max(6, nl - 5), nl - 3))
     os.environ["QCC_B200_HOIST"] = "1"
     os.environ["QCC_B200_PREFETCH"] = "1"
-    os.environ["QCC_B200_LAND"] = "0" if os.environ.get("QCC_B200_NO_LAND") else "1"
+    os.environ.setdefault("QCC_B200_LAND", "0")
   elif mode == "swap":
     os.environ["QCC_B200_VICTIM_WINDOW"] = str(max(6, nl - 5))
     os.environ["QCC_B200_HOIST"] = "1"
