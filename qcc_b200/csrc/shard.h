@@ -81,6 +81,7 @@ struct ShardLayout {
 // kPeerSwapMinVictim.
 constexpr int kVictimWindow = 6;
 constexpr int kPeerSwapMinVictim = 5;
+constexpr int kPeerSwapMinVictimLarge = 9;   // shards with >= 29 local bits (engine.cu create_impl)
 
 // Lowers `gates` (LOGICAL index bits, kinds already classified) for layout->rank, updating
 // layout->perm as exchanges are scheduled.
