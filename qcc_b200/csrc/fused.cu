@@ -87,8 +87,10 @@ struct FusedParams {
   const double2 *outph;
   const uint32_t *jbtab;
   int nlad;                                   // ladder ops of the pass ...
-  uint32_t lad_tab[QB_MAX_PASS_LADDERS];      // ... first entry of their lookup tables in `tables`
-  uint32_t lad_ph[QB_MAX_PASS_LADDERS];       // ... first entry of their per-tile-constant tables in `outph`
+  // (any op of the pass can be one: the planner's QB_MAX_PASS_LADDERS counts LADDER items, and close_round
+  // synthesises more for the short tails of Hadamard+ladder rounds -- order finding reaches 14 per pass)
+  uint32_t lad_tab[QB_MAX_PASS_OPS];          // ... first entry of their lookup tables in `tables`
+  uint32_t lad_ph[QB_MAX_PASS_OPS];           // ... first entry of their per-tile-constant tables in `outph`
   int push_on;   // 1: the store stage writes through `push` (exchange event fused into this pass)
   PushMap push;
   int stagger;   // experiment (QCC_B200_STAGGER=cycles): first-wave CTAs of resident slot j start j * stagger clocks late
@@ -1034,7 +1036,7 @@ cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cuda
   for (int k = 0; k < p.desc.nops; ++k) {
     const int k8 = p.ops[k].kind & 0xff;
     if (k8 != QB_K_LADDER && k8 != QB_K_ULADDER) continue;
-    if (P.nlad == QB_MAX_PASS_LADDERS) return cudaErrorInvalidValue;
+    if (P.nlad == QB_MAX_PASS_OPS) return cudaErrorInvalidValue;
     P.lad_tab[P.nlad] = uint32_t(p.ops[k].table_off);
     P.lad_ph[P.nlad] = uint32_t(p.ops[k].outph_off);
     ++P.nlad;

@@ -40,7 +40,7 @@ cudaError_t launch_argmax(const double2 *psi, uint64_t n, double *blk_prob, uint
 cudaError_t launch_list_above(const double2 *psi, uint64_t n, double thr, uint64_t cap,
                               unsigned long long *counter, uint64_t *labels, double2 *amps,
                               cudaStream_t st);
-// Pair exchange through peer memory (engine.cu do_exchange, QCC_B200_PEER_SWAP): swaps this rank's outgoing
+// Pair exchange through peer memory, in place (engine.cu do_exchange, QCC_B200_EXCHANGE=swap): swaps this rank's outgoing
 // half -- the amplitudes whose bit `victim` equals `sel_local` -- element by element with the partner's
 // outgoing half (bit `victim` == 1 - sel_local) in the partner's shard, reached through `peer` (a CUDA IPC
 // mapping of its state vector).  Each rank of the pair handles one half of the element range (`upper`),

@@ -150,11 +150,9 @@ def test_cx_fan_in_and_scheduling(n, tile_bits, seed):
 
 @pytest.mark.parametrize("workload,n", [("qft", 12), ("qft", 15), ("qft", 19), ("larose", 13), ("larose", 17),
                                         ("larose", 20)])
-def test_pipelined_kernel_small_states(workload, n, monkeypatch):
-  """The persistent software-pipelined kernel (k_fused_pipe) normally takes only program-only passes
-  with >= 4 tiles per SM; QCC_B200_FUSED_PIPE=2 forces it so that 1, 8 and 128+ tiles per pass
-  (fewer tiles than ring slots, fewer CTAs than SMs, ...) are checked against the oracle."""
-  monkeypatch.setenv("QCC_B200_FUSED_PIPE", "2")
+def test_program_passes_on_small_states(workload, n):
+  """Program-only passes (HL3 / UX round programs, direct-store last rounds) at K = 12 on states of 1, 8 and
+  128+ tiles per pass -- fewer tiles than SMs, fewer CTAs than resident slots -- against the oracle."""
   stream = []
   if workload == "qft":
     for i in reversed(range(n)):
@@ -172,9 +170,6 @@ def test_pipelined_kernel_small_states(workload, n, monkeypatch):
   want = oracle.c_run(psi0.copy(), n, stream)
   got, _ = run_device(n, psi0, stream, True, 12)
   assert np.abs(got - want).max() <= TOL
-  monkeypatch.setenv("QCC_B200_FUSED_PIPE", "0")
-  got0, _ = run_device(n, psi0, stream, True, 12)
-  assert np.abs(got0 - want).max() <= TOL
 
 
 @pytest.mark.parametrize("n", [10, 16, 21])
