@@ -221,6 +221,10 @@ int qb_plan_json(int nqubits, const qb_gate *gates, int64_t ngates, int tile_bit
  * identity layout.  Host only: the CPU tests execute it with numpy shards + gloo send/recv. */
 int qb_shard_lower_json(int nqubits, int nranks, int rank, const qb_gate *gates, int64_t ngates,
                         int canonicalize, char *buf, size_t cap, size_t *needed);
+/* Plans `ngates` gates as qb_flush would (peephole included) and runs every fused pass through the HOST half of
+ * its kernel launch (capacity of the parameter block and of shared memory, address terms): QB_ERR_UNSUPPORTED if
+ * the planner produced a pass the kernel cannot take.  No GPU needed; the CPU tests run it over every golden. */
+int qb_plan_check(int nqubits, const qb_gate *gates, int64_t ngates, int tile_bits, int64_t *passes);
 /* The queue's peephole, applied in place to a gate list (host only): every adjacent five-gate
  * Sleator-Weinfurter run cu(a,t,V) cx(a,b) cu(b,t,V^dagger) cx(a,b) cu(b,t,V) -- how circuit.py:227-246 spells
  * ccx / ccu / ccu1 -- becomes ONE doubly-controlled V^2 on t followed by four identity gates (so the gate count is

@@ -64,6 +64,7 @@ PROTOTYPES = {
     "qb_state_exchange_mode": [_P, ctypes.POINTER(_I)],
     "qb_shard_lower_json": [_I, _I, _I, ctypes.POINTER(qb_gate), ctypes.c_int64, _I, ctypes.c_char_p,
                             ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)],
+    "qb_plan_check": [_I, ctypes.POINTER(qb_gate), ctypes.c_int64, _I, ctypes.POINTER(ctypes.c_int64)],
     "qb_fuse_gates": [ctypes.POINTER(qb_gate), ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)],
     "qb_shard_plan_stats": [_I, _I, _I, ctypes.POINTER(qb_gate), ctypes.c_int64, _I, _I, _I, _I,
                             ctypes.POINTER(ctypes.c_int64)],
@@ -213,6 +214,15 @@ def shard_lower_json(nqubits: int, nranks: int, rank: int, gates, canonicalize: 
   check(lib().qb_shard_lower_json(nqubits, nranks, rank, arr, len(arr), int(canonicalize), buf, need.value,
                                   ctypes.byref(need)))
   return buf.value.decode()
+
+
+def plan_check(nqubits: int, gates, tile_bits: int = 12) -> int:
+  """Plan + host half of every pass's kernel launch (host only); returns the number of passes, raises QbError
+  when a pass does not fit the kernel."""
+  arr = gates if isinstance(gates, ctypes.Array) else pack_gates(gates)
+  n = ctypes.c_int64(0)
+  check(lib().qb_plan_check(nqubits, arr, len(arr), tile_bits, ctypes.byref(n)))
+  return n.value
 
 
 def fuse_gates(gates):

@@ -1612,6 +1612,39 @@ int qb_shard_plan_stats(int nqubits, int nranks, int rank, const qb_gate *gates,
   return QB_OK;
 }
 
+int qb_plan_check(int nqubits, const qb_gate *gates, int64_t ngates, int tile_bits, int64_t *passes) {
+  if ((!gates && ngates) || !passes) return fail(QB_ERR_ARG, "null pointer");
+  if (nqubits < 4 || nqubits > 40) return fail(QB_ERR_ARG, "nqubits out of range [4,40]");
+  std::vector<QbGate> q(static_cast<size_t>(ngates));
+  for (int64_t k = 0; k < ngates; ++k) {
+    const qb_gate &g = gates[k];
+    if (g.target < 0 || g.target >= nqubits || (g.ctl_mask >> g.target & 1) || (g.ctl_mask >> nqubits))
+      return fail(QB_ERR_ARG, "gate %lld: bad bits", (long long)k);
+    q[size_t(k)].ctl_mask = g.ctl_mask;
+    q[size_t(k)].target = g.target;
+    q[size_t(k)].kind = classify(g.m);
+    memcpy(q[size_t(k)].m, g.m, sizeof g.m);
+  }
+  qb::fuse_ccu_runs(q.data(), ngates);
+  qb::Plan plan;
+  qb::plan_gates(nqubits, q.data(), ngates, tile_bits, &plan);
+  plan.blob_bytes();
+  *passes = int64_t(plan.passes.size());
+  for (size_t k = 0; k < plan.passes.size(); ++k) {
+    const qb::PlannedPass &pp = plan.passes[k];
+    if (pp.single_gate >= 0) continue;
+    qb::DevicePass dp;
+    dp.desc = pp.desc;
+    dp.ops = pp.ops.data();
+    dp.rounds = pp.rounds.data();
+    cudaError_t e = qb::check_fused_pass(nqubits, dp);
+    if (e != cudaSuccess)
+      return fail(QB_ERR_UNSUPPORTED, "pass %zu of %zu (%d ops, %d rounds, %d table entries) does not fit the kernel's "
+                  "parameter block / shared memory", k, plan.passes.size(), pp.desc.nops, pp.desc.nrounds, pp.desc.ntable);
+  }
+  return QB_OK;
+}
+
 int qb_fuse_gates(qb_gate *gates, int64_t ngates, int64_t *fused) {
   if ((!gates && ngates) || !fused) return fail(QB_ERR_ARG, "null pointer");
   std::vector<QbGate> q(static_cast<size_t>(ngates));

@@ -1022,7 +1022,21 @@ cudaError_t fused_configure(int device) {
   return configure_one<false, false, true>();
 }
 
+namespace {
+cudaError_t fused_pass_impl(double2 *psi, int nbits, const DevicePass &p, cudaStream_t st, bool launch);
+}
+
 cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cudaStream_t st) {
+  return fused_pass_impl(psi, nbits, p, st, true);
+}
+
+// Everything launch_fused_pass does on the host (capacity checks of the parameter block, address terms, round
+// constants) without launching: the CPU tests run every plan through it (qb_plan_check), so a planner output
+// the kernel's parameter block cannot hold is caught where no GPU exists.
+cudaError_t check_fused_pass(int nbits, const DevicePass &p) { return fused_pass_impl(nullptr, nbits, p, nullptr, false); }
+
+namespace {
+cudaError_t fused_pass_impl(double2 *psi, int nbits, const DevicePass &p, cudaStream_t st, bool launch) {
   FusedParams P;
   P.psi = psi;
   P.nbits = nbits;
@@ -1183,6 +1197,7 @@ cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cuda
   unsigned blocks = ntiles;
   if (persist > 0 && ntiles > unsigned(persist * g_sms)) blocks = unsigned(persist * g_sms);
   const bool full = ((1u << (K - 3)) % kFThreads) == 0;
+  if (!launch) return cudaSuccess;
   if (P.push_on) {
     if (full && fast) k_fused_pass<true, true, true><<<blocks, kFThreads, smem, st>>>(P);
     else if (full) k_fused_pass<true, false, true><<<blocks, kFThreads, smem, st>>>(P);
@@ -1194,5 +1209,6 @@ cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cuda
   else k_fused_pass<false, false, false><<<blocks, kFThreads, smem, st>>>(P);
   return cudaGetLastError();
 }
+}  // namespace
 
 }  // namespace qb

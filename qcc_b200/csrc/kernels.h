@@ -87,6 +87,7 @@ struct DevicePass {
 };
 cudaError_t fused_configure(int device);  // opt in to large dynamic shared memory, query SM count
 cudaError_t launch_fused_pass(double2 *psi, int nbits, const DevicePass &p, cudaStream_t st);
+cudaError_t check_fused_pass(int nbits, const DevicePass &p);   // the host half of the launch, no GPU needed
 
 }  // namespace qb
 

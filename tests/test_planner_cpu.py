@@ -258,3 +258,36 @@ def test_sleator_weinfurter_runs_become_one_doubly_controlled_gate():
   from helpers import interpret_plan
   out = interpret_plan(_cabi.plan_json(n, fused, 6), n, fused, psi0.copy())
   assert np.abs(out - want).max() < 1e-12
+
+
+def test_every_plan_fits_the_kernel_parameter_block():
+  """qb_plan_check = the planner + the HOST half of launch_fused_pass (capacity of the 32 KiB parameter block:
+  ops, rounds, ladder ops; shared memory for the tile + ladder tables).  Round 2 shipped a parameter array with
+  room for 12 ladder ops per pass for a few hours -- order finding plans 14 -- and only a GPU run noticed; this
+  runs the check where no GPU exists, over the streams the GPU suite and the bench execute."""
+  import glob
+  from helpers import GOLDEN, load_golden, stream_of, xg_to_bits
+  from qcc_b200 import circuit, workloads
+  streams = []
+  for path in sorted(glob.glob(os.path.join(GOLDEN, "circ_*.npz"))) + [os.path.join(GOLDEN, "order_N15_a4.npz")]:
+    z = load_golden(os.path.basename(path))
+    n = int(z["nbits"])
+    if n >= 4:
+      streams.append((os.path.basename(path), n, xg_to_bits(n, stream_of(z))))
+  for n in (21, 30, 34):
+    streams.append((f"qft{n}", n, xg_to_bits(n, workloads.qft(n) * 3)))
+  streams.append(("larose28", 28, xg_to_bits(28, workloads.larose(28, 3))))
+  streams.append(("supremacy34", 34, xg_to_bits(34, workloads.supremacy(34, 20, seed=0))))
+  np.random.seed(0)
+  qc, _ = workloads.grover_circuit(7, qc_factory=lambda name: circuit.qc(name, eager=False), iterations=3)
+  g = []
+  for node in qc.ir.gates:
+    if node.is_single():
+      g.append((1, 0, node.idx0, np.asarray(node.gate)))
+    elif node.is_ctl():
+      g.append((2, node.ctl, node.idx1, np.asarray(node.gate)))
+  streams.append(("grover14", 14, xg_to_bits(14, g)))
+  for name, n, gates in streams:
+    for K in (12, 13, 9, 6):
+      if K <= n:
+        assert _cabi.plan_check(n, gates, K) >= 1, (name, K)
