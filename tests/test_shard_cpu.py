@@ -278,3 +278,65 @@ def test_pair_swap_index_math_equals_send_recv_layout():
         a, b = got[r][l].copy(), got[1 - r][p].copy()
         got[r][l], got[1 - r][p] = b, a
       assert all(np.array_equal(got[r], want[r]) for r in (0, 1)), (nl, victim)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_lowering_fuzz_all_ranks_in_one_process(seed, monkeypatch):
+  """Random circuits (0-2 controls, diagonal / permuting / general gates) x random lowering parameters (victim
+  window, hoisting, prefetch = multi-bit events, landing bits) x world 2 / 4 / 8, with and without the final
+  canonicalisation: the plans of ALL ranks are executed side by side on numpy shards (events as the pairwise
+  half-shard trades they stand for, then the landing-bit swap) and the un-permuted result must be the oracle's."""
+  rng = np.random.default_rng(seed)
+  names = list(oracle.GATES)
+  from qcc_b200 import _cabi
+  for trial in range(14):
+    world = int(rng.choice([2, 4, 8]))
+    p = int(math.log2(world))
+    n = int(rng.integers(p + 6, 13))
+    nl = n - p
+    monkeypatch.setenv("QCC_B200_VICTIM_WINDOW", str(int(rng.integers(1, nl - 2))))
+    monkeypatch.setenv("QCC_B200_HOIST", str(int(rng.integers(0, 2))))
+    monkeypatch.setenv("QCC_B200_PREFETCH", str(int(rng.integers(0, 2))))
+    monkeypatch.setenv("QCC_B200_LAND", str(int(rng.integers(0, 2))))
+    gates = []
+    for _ in range(int(rng.integers(20, 140))):
+      r = rng.random()
+      m = oracle.u1(float(rng.uniform(-3, 3))) if r < 0.25 else (
+          oracle.rotation([0, 0, 1.0], float(rng.uniform(-3, 3))) if r < 0.3 else oracle.GATES[names[rng.integers(len(names))]])
+      b = [int(x) for x in rng.permutation(n)[:3]]
+      mask = 0
+      for c in b[1:1 + int(rng.choice([0, 0, 1, 1, 2]))]:
+        mask |= 1 << c
+      gates.append((mask, b[0], m))
+    psi0 = random_state(n, 100 * seed + trial)
+    plans = [json.loads(_cabi.shard_lower_json(n, world, r, gates, canonicalize=bool(trial % 2))) for r in range(world)]
+    shards = [psi0[r << nl:(r + 1) << nl].copy() for r in range(world)]
+    assert len({len(pl["steps"]) for pl in plans}) == 1
+    for si, st0 in enumerate(plans[0]["steps"]):
+      if st0["kind"] == 0:
+        for r in range(world):
+          for g in plans[r]["steps"][si]["gates"]:
+            m = np.array([complex(g["m"][2 * i], g["m"][2 * i + 1]) for i in range(4)])
+            apply_masked(shards[r], nl, g["ctl_mask"], g["target"], m)
+        continue
+      for k, v, h in st0["pairs"]:
+        run, nruns = 1 << v, 1 << (nl - 1 - v)
+        new = [x.copy() for x in shards]
+        for r in range(world):
+          sel = 0 if (r >> k) & 1 else 1
+          new[r].reshape(nruns, 2, run)[:, sel, :] = shards[r ^ (1 << k)].reshape(nruns, 2, run)[:, 1 - sel, :]
+        if h != v:
+          idx = np.arange(1 << nl)
+          bv, bh = (idx >> v) & 1, (idx >> h) & 1
+          sw = idx ^ ((bv ^ bh) << v) ^ ((bv ^ bh) << h)
+          new = [x[sw] for x in new]
+        shards = new
+    phys = np.concatenate(shards)
+    perm, flip = plans[0]["perm"], plans[0]["flip"]
+    idx = np.arange(1 << n)
+    pidx = np.zeros_like(idx)
+    for bl in range(n):
+      f = (flip >> (perm[bl] - nl)) & 1 if perm[bl] >= nl else 0
+      pidx |= (((idx >> bl) & 1) ^ f) << perm[bl]
+    want = run_bits(psi0.copy(), n, gates)
+    assert np.abs(phys[pidx] - want).max() <= 1e-12, (seed, trial, world, n)
