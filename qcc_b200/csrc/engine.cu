@@ -227,7 +227,11 @@ constexpr size_t kBarrierBytes = 4096;   // arrival counters of the peer-memory 
 // Fused execution: plan the queue into tile-resident passes and launch one kernel per pass.  With
 // `push` (an exchange event follows these gates, push mode) the LAST pass, when it is a fused pass,
 // stores through the event's bit permutation into the alternate buffers; *pushed says whether it did.
-double host_now_ms();
+double host_now_ms() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return double(ts.tv_sec) * 1e3 + double(ts.tv_nsec) * 1e-6;
+}
 
 // One run of local gates of a flush.  All segments of a flush are planned first and staged as ONE blob with one
 // upload (stage_segments), so that the host never waits for the device between the segments of a sharded flush.
@@ -615,13 +619,6 @@ void make_layout(const qb_state *s, qb::ShardLayout *L) {
   L->pass_targets = std::max(1, s->tile_bits - QB_TILE_LOW);
 }
 
-}  // namespace
-namespace {
-double host_now_ms() {
-  timespec ts;
-  clock_gettime(CLOCK_MONOTONIC, &ts);
-  return double(ts.tv_sec) * 1e3 + double(ts.tv_nsec) * 1e-6;
-}
 
 int flush_impl(qb_state *s);
 

@@ -75,6 +75,7 @@ class DevicePsi:
       start, stop, step = idx.indices(len(self))
       if step != 1:
         return self.numpy()[idx]
+      self._whole_vector_only("slicing")
       return self._dev.copy_out(start, max(0, stop - start))
     idx = int(idx)
     if idx < 0:
@@ -113,7 +114,20 @@ class DevicePsi:
     return labels, amps, total
 
   # -- whole vector ----------------------------------------------------------------------
+  def _whole_vector_only(self, what: str) -> None:
+    if getattr(self._dev, "nranks", 1) > 1:
+      raise NotImplementedError(f"{what} a sharded state: this process holds 1/{self._dev.nranks} of the vector; "
+                                "use psi.local_slice() (this rank's slice of the canonical vector) or the "
+                                "collective readouts (ampl, prob, maxprob, nonzero, ...)")
+
+  def local_slice(self) -> np.ndarray:
+    """This rank's contiguous slice [rank * 2^n / nranks, (rank + 1) * 2^n / nranks) of the canonical vector
+    (the whole vector when the state is not sharded).  Collective on a sharded state: the engine first undoes
+    whatever bit layout the exchange events left behind."""
+    return self._dev.copy_out()
+
   def numpy(self, force: bool = False) -> np.ndarray:
+    self._whole_vector_only("copying out")
     if self.nbits > self.MATERIALIZE_LIMIT and not force:
       raise MemoryError(f"refusing to copy a {self.nbits}-qubit state to the host implicitly; "
                         "call psi.numpy(force=True)")
