@@ -340,3 +340,23 @@ def test_lowering_fuzz_all_ranks_in_one_process(seed, monkeypatch):
       pidx |= (((idx >> bl) & 1) ^ f) << perm[bl]
     want = run_bits(psi0.copy(), n, gates)
     assert np.abs(phys[pidx] - want).max() <= 1e-12, (seed, trial, world, n)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_qft30_lowering_quality(world):
+  """Regression guard for what the multi-GPU numbers rest on: ten QFT-30s queued into one flush
+  lower, on every rank alike, into 3 passes per QFT, at most 1.5 exchange events per QFT, every event on the store
+  stage of a fused pass, all log2(world) sharded qubits travelling together; the NCCL-mode lowering (narrow victim
+  window, one pair per exchange, no hoisting) cuts more passes."""
+  from qcc_b200 import _cabi
+  n, reps = 30, 10
+  gates = _circuits(n)["qft"] * reps
+  arr = _cabi.pack_gates(gates)
+  push = [_cabi.shard_plan_stats(n, world, r, arr, 12, "push") for r in (0, world - 1)]
+  assert push[0] == push[1]
+  st = push[0]
+  assert st["passes"] == 3 * reps and st["fused_passes"] == st["passes"]
+  assert st["events"] <= 1.5 * reps and st["events_on_a_pass"] == st["events"]
+  assert st["pairs"] == st["events"] * int(math.log2(world))
+  nccl = _cabi.shard_plan_stats(n, world, 0, arr, 12, "nccl")
+  assert nccl["passes"] > st["passes"]
