@@ -230,3 +230,67 @@ def test_qasm_and_cirq_text_match_the_reference():
   assert "qc.append(cirq.MatrixGate(m).controlled()(r[1], r[3]))" in text
   assert "m = np.array([(1+1j, 1-1j), (1-1j, 1+1j)]) * 0.5\nqc.append(cirq.MatrixGate(m).controlled()(r[0], r[2]))" in text
   assert "cmath.exp(1j * -pi/4)" in text and text.endswith("print(res_str.encode('utf-8'))\n")
+
+
+def test_gate_batching_keeps_program_order(monkeypatch):
+  """circuit.qc batches gate records on the host (GateBuffer) and hands them to the engine in bulk.  With a
+  recording stand-in for the engine handle: every readout, direct engine call, register growth and psi
+  replacement sees exactly the gates issued before it, in order, and nothing is handed over twice."""
+  from qcc_b200 import _cabi
+
+  log = []
+
+  class FakeDev:
+    def __init__(self, n, label=0, device=0, **kw):
+      self.nqubits, self.nranks = n, kw.get("nranks", 1)
+      log.append(("create", n, label))
+
+    def set_fusion(self, on): pass
+    def set_tile_bits(self, k): pass
+    def close(self): log.append(("close",))
+    def sync(self): log.append(("sync",))
+
+    def xg_apply_buffer(self, buf):
+      for k in range(buf.n):
+        log.append(("gate", int(buf.kind[k]), int(buf.ctl[k]), int(buf.tgt[k]), complex(buf.m[k][3])))
+      buf.n = 0
+
+    def xg_apply1(self, tgt, m): log.append(("direct1", tgt))
+    def argmax(self): log.append(("argmax",)); return 0, 1.0
+    def amplitude(self, i): log.append(("ampl", i)); return 1.0 + 0j
+    def prob_bit_value(self, bit, value): log.append(("weight", bit, value)); return 0.5
+    def copy_out(self, first=0, count=None): log.append(("copy_out",)); return np.ones(1 << self.nqubits, dtype=np.complex128)
+    def copy_in(self, arr, first=0): log.append(("copy_in", len(arr)))
+
+  monkeypatch.setattr(_cabi, "DeviceState", FakeDev)
+  qc = circuit.qc("batch")
+  qc.reg(3, 0b101)
+  qc.h(0)
+  qc.cx(0, 1)
+  qc.u1(2, 0.5)
+  assert [e[0] for e in log] == ["create"]                     # nothing crossed the ABI yet
+  qc.psi.maxprob()
+  assert [e[0] for e in log] == ["create", "gate", "gate", "gate", "argmax"]
+  assert [(e[1], e[2], e[3]) for e in log if e[0] == "gate"] == [(1, 0, 0), (2, 0, 1), (1, 0, 2)]
+  qc.x(1)
+  qc.measure_bit(1, 1, collapse=True)                          # readout, then a direct engine call
+  assert [e[0] for e in log][5:] == ["gate", "weight", "direct1"]
+  qc.t(0)
+  qc.reg(1, 1)                                                 # the state grows: queued gates first, then the copy
+  qc.h(3)
+  qc.psi[0]
+  tail = [e[0] for e in log][8:]
+  assert tail == ["gate", "copy_out", "close", "create", "copy_in", "gate", "ampl"], tail
+  qc.z(2)
+  qc.psi = np.ones(16) / 4.0                                   # replaced wholesale: the queued z is dropped with it
+  qc.s(1)
+  qc.sync()
+  assert [e[0] for e in log][-5:] == ["close", "create", "copy_in", "gate", "sync"]
+  n_gates = sum(1 for e in log if e[0] == "gate")
+  assert n_gates == 7                                          # h cx u1 x t h s -- each exactly once
+  # a full buffer is handed over on its own
+  big = circuit.qc("big")
+  big.reg(2, 0)
+  for _ in range(big._gbuf.cap + 5):
+    big.h(0)
+  assert sum(1 for e in log if e[0] == "gate") == n_gates + big._gbuf.cap
