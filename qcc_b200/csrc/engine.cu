@@ -900,8 +900,9 @@ static int create_impl(int nqubits, uint64_t init_label, int device, int rank, i
     s->xmode = mode;
     // peer-memory exchanges do not care how many contiguous runs the exchanged part is made of
     // Shards of 8 GiB and more: victims stay above bit 8.  The per-launch trace of QFT-34 on 8 GPUs
-    // (profiles/r02_qft34_8gpu_*launches*.txt) has the push passes at 43 ms with victims 27-29, 53-80 ms with
-    // 9-11 and 80-199 ms with 5-7; the lowering model gives the same number of events and passes either way.
+    // (profiles/r02_qft34_8gpu_trace_run2.err) has the push passes at 43 ms with victims 27-29,
+    // 53-80 ms with 9-11 and 174-199 ms with 5-7; the lowering model gives the same number of events and passes
+    // either way.
     const int min_victim = s->n >= 29 ? qb::kPeerSwapMinVictimLarge : qb::kPeerSwapMinVictim;
     if (mode != QB_X_NCCL) s->victim_window = std::max(qb::kVictimWindow, s->n - min_victim);
     if (mode == QB_X_PUSH) s->victim_window = std::min(s->victim_window, s->n - QB_TILE_LOW);  // bits 0..2 never move
