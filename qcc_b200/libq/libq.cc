@@ -63,6 +63,12 @@ void refresh(qureg *reg) {
   im->dirty = false;
 }
 
+// Callers of the reference read the public fields between gates (libq_test.cc:12 reads q->size right after its
+// gates), and `maxsize` -- "Maximum # of states" of print_qureg_stats, qureg.cc:80-86 -- is a running maximum over
+// the program, part of the stdout the golden tests compare.  So registers of up to kEagerWidth qubits keep their
+// mirrors exact after EVERY gate (a device listing per gate: microseconds at these sizes, and the listing
+// buffers live in the engine state, not allocated per call); wider registers refresh lazily at flush / print /
+// sync, where the queue can fuse.
 void touched(qureg *reg) {
   reg->impl->dirty = true;
   if (reg->width <= kEagerWidth) refresh(reg);
